@@ -1,0 +1,120 @@
+/*
+ * vegas_b200.h -- C ABI of libvegas_b200.so, the B200 (sm_100a) vegas / vegas+ sampling engine.
+ *
+ * The reference (gplepage/vegas 6.4.1) has no C ABI: its boundary is the Python API of the
+ * Cython module src/vegas/_vegas.pyx ("pyx:N" below).  This library implements the body of one
+ * iteration of Integrator.__call__ (pyx:2086-2217) -- allocate -> sample -> map -> evaluate ->
+ * per-hypercube reduce -> train -- plus the AdaptiveMap array methods, behind plain-C entry
+ * points that the Python host layer (vegas_b200/_lib.py, ctypes) binds.  INTEGRATION.md shows
+ * the stub a maintainer of the reference would add to call it from _vegas.pyx.
+ *
+ * Conventions: every function returns 0 on success and a negative code on error (message via
+ * vb200_last_error()).  Pointers named *_dev are DEVICE pointers owned by the caller (torch
+ * tensors in the Python layer); *_host are host pointers.  Calls are asynchronous on `stream`
+ * (a cudaStream_t passed as void*) unless stated.  One host thread per context.
+ */
+#ifndef VEGAS_B200_H
+#define VEGAS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB200_ABI_VERSION 1
+#define VB200_MAXDIM 32          /* largest number of integration dimensions */
+#define VB200_CHUNK 256          /* hypercubes per work chunk; slab sizes are multiples of this */
+
+typedef struct vb200_ctx vb200_ctx;
+
+/* flags of vb200_iterate_fused / vb200_reduce */
+#define VB200_UPDATE_SIGF  1     /* adaptive_strat at pyx:2052-2055: write sigf, sum sum_sigf   */
+#define VB200_TRAIN        2     /* pyx:2196-2197: map.add_training_data(y, fdv2)               */
+#define VB200_TRAIN_ERRORS 4     /* pyx:2187-2193: adapt_to_errors training                     */
+#define VB200_CORRELATE    8     /* pyx:2170-2172: covariances between integrand components     */
+
+/* built-in device integrands ("device functors compiled into the library") */
+#define VB200_F_POLY          0  /* c0 + sum_d c[d]*x[d]**p[d]                                   */
+#define VB200_F_GAUSS_MIX     1  /* norm * sum_p exp(-a |x-c_p|^2)   examples/simple.py, doc/eg6 */
+#define VB200_F_RIDGE         2  /* norm * mean_k exp(-a sum_d (x_d-x0_k)^2)  examples/ridge.py  */
+#define VB200_F_GENZ_OSC      3
+#define VB200_F_GENZ_PRODPEAK 4
+#define VB200_F_GENZ_CORNER   5
+#define VB200_F_GENZ_GAUSS    6
+#define VB200_F_GENZ_C0       7
+#define VB200_F_GENZ_DISC     8
+#define VB200_F_PATHINT       9  /* examples/path_integrand.pyx:88-142                           */
+
+/* parameter blocks for vb200_set_integrand (host memory, copied) */
+typedef struct { double c0; double c[VB200_MAXDIM]; int32_t p[VB200_MAXDIM]; } vb200_poly_t;
+typedef struct { int32_t npeak; int32_t pad; double a, norm; const double* centers_host; /* [npeak][dim] */ } vb200_gaussmix_t;
+typedef struct { int32_t n; int32_t pad; double a, norm; const double* x0_host; /* [n] */ } vb200_ridge_t;
+typedef struct { double a[VB200_MAXDIM]; double u[VB200_MAXDIM]; } vb200_genz_t;
+typedef struct { double T, m, xscale, c2, c4; int32_t nx0; int32_t pad; double x0list[7]; } vb200_pathint_t;
+
+int         vb200_abi_version(void);
+const char* vb200_last_error(void);
+
+/* context: owns the device copy of the map, scratch buffers and the integrand parameters */
+int  vb200_create(vb200_ctx** out, int device);
+void vb200_destroy(vb200_ctx* ctx);
+int  vb200_set_seed(vb200_ctx* ctx, uint64_t seed);                  /* Philox key (replaces gvar.RNG, pyx:1676-1680) */
+
+/* AdaptiveMap state: grid_host[d*gstride + i], i = 0..ninc[d]        (pyx:112-137; inc is derived) */
+int  vb200_set_map(vb200_ctx* ctx, const double* grid_host, const int64_t* ninc, int dim, int64_t gstride);
+
+/* stratification (pyx:1346-1407 computes nstrat on the host) + this rank's block-cyclic share of
+ * the hypercube index range: slabs of `slab` cubes dealt round-robin to `world` ranks. */
+int  vb200_set_strata(vb200_ctx* ctx, const int64_t* nstrat, int dim, int64_t slab, int rank, int world,
+                      int64_t* nlocal_out);
+
+int  vb200_set_integrand(vb200_ctx* ctx, int id, const void* params, size_t nbytes, int* nf_out);
+
+/* vegas+ allocation (pyx:1657-1662, 1692-1706): neval_hcube[h] = min(max_nh, (int)(sigf[h]*neval_sigf)
+ * + min_nh) for this rank's cubes (sigf_dev == NULL: uniform_neval everywhere).  Writes the
+ * per-cube counts to neval_hcube_dev if non-NULL, builds the per-chunk offsets used by
+ * vb200_sample / vb200_reduce, and returns stats_host = {sum, min, max, nchunks}.  Synchronous. */
+int  vb200_plan(vb200_ctx* ctx, const double* sigf_dev, double neval_sigf, int64_t min_neval_hcube,
+                int64_t max_neval_hcube, int64_t uniform_neval, int32_t* neval_hcube_dev,
+                int64_t stats_host[4], void* stream);
+int  vb200_chunk_offsets(vb200_ctx* ctx, int64_t* out_host, int64_t count);   /* count <= nchunks+1 */
+
+/* One fused iteration over this rank's cubes with the built-in integrand (pyx:2096-2197 in one
+ * kernel).  acc_dev (+=): mean[nf], var lower triangle [nf(nf+1)/2] (row-major s>=t), sum_sigf.
+ * sum_f_dev / n_f_dev (+=): training histogram [dim][hstride].  status_dev[0] != 0: NaN seen. */
+int  vb200_iterate_fused(vb200_ctx* ctx, uint32_t itn, double beta, int flags, double* sigf_dev,
+                         double* acc_dev, double* sum_f_dev, uint64_t* n_f_dev, int64_t hstride,
+                         int32_t* status_dev, void* stream);
+
+/* Unfused path, stage 1 (pyx:1732-1759, Integrator.random_batch): samples of local chunks
+ * [chunk_begin, chunk_end) in hypercube order.  x_dev[rows][dim] (or [dim][rows] if x_transposed),
+ * wgt_dev[rows]; y_dev, jac1d_dev ([rows][dim]) and hcube_dev are optional (NULL). */
+int  vb200_sample(vb200_ctx* ctx, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* x_dev,
+                  double* wgt_dev, double* y_dev, double* jac1d_dev, int64_t* hcube_dev,
+                  int x_transposed, void* stream);
+/* Unfused path, stage 2 (pyx:2136-2197): reduce f_dev[rows][nf] of the same chunk range. */
+int  vb200_reduce(vb200_ctx* ctx, uint32_t itn, double beta, int flags, int64_t chunk_begin,
+                  int64_t chunk_end, const double* f_dev, int nf, const double* wgt_dev,
+                  double* sigf_dev, double* acc_dev, double* sum_f_dev, uint64_t* n_f_dev,
+                  int64_t hstride, int32_t* status_dev, void* stream);
+
+/* AdaptiveMap array methods on device buffers (pyx:310-360, 362-416, 265-295, 421-464) */
+int  vb200_map(vb200_ctx* ctx, const double* y_dev, double* x_dev, double* jac_dev, int64_t n, void* stream);
+int  vb200_invmap(vb200_ctx* ctx, const double* x_dev, double* y_dev, double* jac_dev, int64_t n, void* stream);
+int  vb200_jac1d(vb200_ctx* ctx, const double* y_dev, double* jac1d_dev, int64_t n, void* stream);
+int  vb200_add_training_data(vb200_ctx* ctx, const double* y_dev, const double* f_dev, int64_t n,
+                             double* sum_f_dev, uint64_t* n_f_dev, int64_t hstride, void* stream);
+
+/* engine uniforms for testing: u_dev[rows][dim] of local chunks [chunk_begin, chunk_end) */
+int  vb200_uniforms(vb200_ctx* ctx, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* u_dev, void* stream);
+
+/* measurement helpers: FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops) and kernel
+ * launch count since context creation. */
+int     vb200_fp64_peak(int device, int iters, double* tflops_out, double* ms_out);
+int64_t vb200_launch_count(vb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -301,7 +301,9 @@ void vo_reduce_batch(const double *wgt, const double *fx, int64_t nf,
  * same numbers.
  *   key     = (seed_lo, seed_hi)
  *   counter = (k, (itn << 8) | pair, hcube_lo, hcube_hi)      k = sample index inside the cube
- *   u[2*pair]   = ((r1:r0) >> 11) * 2^-53,  u[2*pair+1] = ((r3:r2) >> 11) * 2^-53
+ *   u[2*pair]   = ((r1:r0) >> 12) * 2^-52,  u[2*pair+1] = ((r3:r2) >> 12) * 2^-52
+ * (52-bit uniforms: the mantissa is or-ed under the exponent of 1.0 on the device, then 1.0 is
+ * subtracted -- exact, and the same value as this integer form.)
  */
 static inline void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1)
 {
@@ -342,8 +344,8 @@ void vo_philox_uniforms(uint64_t seed, uint32_t itn, int dim, int64_t hcube0,
                 vo_philox4x32_10(ctr, key, r);
                 uint64_t a = ((uint64_t)r[1] << 32) | r[0];
                 uint64_t b = ((uint64_t)r[3] << 32) | r[2];
-                yran[i * dim + 2 * p] = (double)(a >> 11) * 0x1.0p-53;
-                if (2 * p + 1 < dim) yran[i * dim + 2 * p + 1] = (double)(b >> 11) * 0x1.0p-53;
+                yran[i * dim + 2 * p] = (double)(a >> 12) * 0x1.0p-52;
+                if (2 * p + 1 < dim) yran[i * dim + 2 * p + 1] = (double)(b >> 12) * 0x1.0p-52;
             }
     }
 }

@@ -1,0 +1,165 @@
+// common.cuh -- shared device helpers for the vegas_b200 engine (sm_100a).
+//
+// Philox4x32-10 counter-based RNG, exact fp64 division by a stratum count, the parameter
+// blocks passed to kernels by value, and small warp/block reduction helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define VB_MAXD 32          // compile-time bound on dimensions carried in kernel parameters
+#define VB_NT 256           // threads per CTA of the engine kernels
+#define VB_CH 256           // hypercubes per chunk (== VB_NT: one cube per thread in set-up)
+#define VB_WARP_CUBE 64     // cubes with more samples than this are reduced by a whole warp
+#define VB_EPSILON (2.220446049250313e-16 * 1e4)   // reference EPSILON, _vegas.pyx:36
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  key = seed; counter = (k, itn<<8 | pair, h_lo, h_hi).
+// One call yields two 52-bit uniforms in [0,1): u = ((hi:lo) >> 12) * 2^-52, built by
+// or-ing the mantissa under the exponent of 1.0 and subtracting 1.0 (exact).
+// ---------------------------------------------------------------------------------------------
+struct PhiloxKey { uint32_t k[20]; };   // per-round keys, precomputed on the host (uniform)
+
+__host__ __device__ inline void philox_make_key(uint64_t seed, PhiloxKey& K)
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k[2 * r] = k0; K.k[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ void philox4x32_10(const PhiloxKey& K, uint32_t c0, uint32_t c1,
+                                              uint32_t c2, uint32_t c3, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ K.k[2 * r];
+        uint32_t n2 = hi0 ^ c3 ^ K.k[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double u52(uint32_t lo, uint32_t hi)
+{
+    // ((hi:lo) >> 12) or-ed under the exponent of 1.0 -> [1,2); minus 1.0 is exact
+    uint32_t mlo = (lo >> 12) | (hi << 20);
+    uint32_t mhi = (hi >> 12) | 0x3FF00000u;
+    return __hiloint2double((int)mhi, (int)mlo) - 1.0;
+}
+
+// two uniforms for (cube h, sample k, iteration itn, axis pair p)
+__device__ __forceinline__ void philox_pair(const PhiloxKey& K, uint32_t itn, int64_t h, uint32_t k,
+                                            int p, double& ua, double& ub)
+{
+    uint32_t r[4];
+    philox4x32_10(K, k, ((itn & 0xFFFFFFu) << 8) | (uint32_t)p, (uint32_t)(uint64_t)h,
+                  (uint32_t)((uint64_t)h >> 32), r);
+    ua = u52(r[0], r[1]);
+    ub = u52(r[2], r[3]);
+}
+
+// Correctly rounded a / b for b a small positive integer (as double), rb = RN(1/b).
+// q = RN(a*rb) is within 1 ulp; one FMA residual step then gives RN(a/b) (Markstein).
+__device__ __forceinline__ double div_exact(double a, double b, double rb)
+{
+    double q = __dmul_rn(a, rb);
+    double e = __fma_rn(-q, b, a);
+    return __fma_rn(e, rb, q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// parameter blocks
+// ---------------------------------------------------------------------------------------------
+struct MapP {                 // AdaptiveMap on the device: grid[d*gstride + i], i = 0..ninc[d]
+    const double* grid;
+    int dim;
+    int gstride;
+    int ninc[VB_MAXD];
+};
+
+struct StrataP {              // stratification of y-space + this rank's share of the hypercubes
+    int64_t nhcube;           // global number of hypercubes
+    int64_t nlocal;           // hypercubes owned by this rank (dense local index space)
+    int64_t slab;             // block-cyclic slab size in cubes (multiple of VB_CH)
+    int rank, world;
+    int nstrat[VB_MAXD];
+    double dns[VB_MAXD];      // (double) nstrat[d]
+    double rns[VB_MAXD];      // RN(1 / nstrat[d])
+};
+
+struct AllocP {               // vegas+ allocation of samples to hypercubes (_vegas.pyx:1692-1706)
+    const double* sigf;       // [nlocal] or nullptr when not adaptive
+    double neval_sigf;
+    int min_neval_hcube;
+    int max_neval_hcube;
+    int uniform_neval;        // used when sigf == nullptr
+};
+
+__device__ __forceinline__ int64_t local_to_global(const StrataP& s, int64_t lh)
+{
+    if (s.world == 1) return lh;
+    int64_t ls = lh / s.slab;
+    return (ls * s.world + s.rank) * s.slab + (lh - ls * s.slab);
+}
+
+__device__ __forceinline__ int alloc_neval(const AllocP& a, int64_t lh)
+{
+    if (a.sigf == nullptr) return a.uniform_neval;
+    double p = __dmul_rn(a.sigf[lh], a.neval_sigf);
+    long long n = (long long)__double2int_rz(p) + a.min_neval_hcube;   // cvt saturates; NaN -> 0
+    if (n > a.max_neval_hcube) n = a.max_neval_hcube;
+    return (int)n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// fixed-tree block sum; result valid in thread 0.  red: >= VB_NT/32 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double* red)
+{
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < VB_NT / 32; ++w) t += red[w];
+    }
+    return t;
+}
+
+// block-wide exclusive scan of one int per thread (VB_NT threads); returns exclusive prefix,
+// total through *total.  scratch: VB_NT/32 ints of shared memory.
+__device__ __forceinline__ long long block_exscan(int v, long long* scratch, long long* total)
+{
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) scratch[w] = x;
+    __syncthreads();
+    long long base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < VB_NT / 32; ++i) {
+        long long s = scratch[i];
+        if (i < w) base += s;
+        tot += s;
+    }
+    *total = tot;
+    return base + x - v;
+}
