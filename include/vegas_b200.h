@@ -106,6 +106,13 @@ int  vb200_jac1d(vb200_ctx* ctx, const double* y_dev, double* jac1d_dev, int64_t
 int  vb200_add_training_data(vb200_ctx* ctx, const double* y_dev, const double* f_dev, int64_t n,
                              double* sum_f_dev, uint64_t* n_f_dev, int64_t hstride, void* stream);
 
+/* AdaptiveMap.adapt (pyx:467-594): host-side smoothing / damping / regrid of every axis, called
+ * once per iteration.  All pointers are HOST pointers; sum_f_host/n_f_host may be NULL (no
+ * training data: regrid only).  new_grid_host[d*ngstride + i], i = 0..new_ninc[d]. */
+int  vb200_map_adapt(const double* grid_host, const int64_t* ninc, int dim, int64_t gstride,
+                     const double* sum_f_host, const double* n_f_host, int64_t hstride, double alpha,
+                     const int64_t* new_ninc, double* new_grid_host, int64_t ngstride);
+
 /* engine uniforms for testing: u_dev[rows][dim] of local chunks [chunk_begin, chunk_end) */
 int  vb200_uniforms(vb200_ctx* ctx, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* u_dev, void* stream);
 

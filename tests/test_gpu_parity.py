@@ -1,0 +1,315 @@
+"""GPU parity tests: the CUDA engine (through the C ABI / Python host layer) against the CPU oracle
+on the same seeded inputs.  Integers bit-exact; fp64 within the stated relative tolerance."""
+import numpy as np
+import pytest
+
+from tests.parity import run_engine_iterations, run_oracle_iterations, compare_iterations, _oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12          # north_star: fp64 results of deterministic pieces within 1e-12 relative
+
+
+def _vegas():
+    import vegas_b200
+    return vegas_b200
+
+
+# ----------------------------------------------------------------------------- AdaptiveMap
+def test_map_known_answers():
+    """reference tests/test_vegas.py:76-112 (map / jac / invmap on a 2-increment grid)"""
+    vegas = _vegas()
+    m = vegas.AdaptiveMap(grid=[[0, 1, 3], [-2, 0, 6]])
+    y = np.array([[0, 0], [0.25, 0.25], [0.5, 0.5], [0.75, 0.75], [1.0, 1.0]])
+    x = np.empty_like(y)
+    jac = np.empty(len(y))
+    m.map(y, x, jac)
+    np.testing.assert_allclose(x, [[0, -2], [0.5, -1], [1, 0], [2, 3], [3, 6]], rtol=1e-15, atol=0)
+    np.testing.assert_allclose(jac, [8, 8, 48, 48, 48], rtol=1e-15)
+    np.testing.assert_allclose(m(y), x)
+    np.testing.assert_allclose(m.jac(y), jac)
+    np.testing.assert_allclose(m.jac1d(y), [[2, 4], [2, 4], [4, 12], [4, 12], [4, 12]])
+    y2 = np.empty_like(y)
+    jac2 = np.empty(len(y))
+    m.invmap(x, y2, jac2)
+    np.testing.assert_allclose(y2, y, rtol=1e-15, atol=1e-16)
+    np.testing.assert_allclose(jac2, jac)
+
+
+def test_map_vs_oracle_random():
+    vegas = _vegas()
+    O = _oracle()
+    rng = np.random.default_rng(5)
+    grid = [np.sort(np.concatenate([[0., 1.], rng.random(n - 1)])) * s + o
+            for n, s, o in [(100, 1., 0.), (37, 3., -1.), (1000, 1e-3, 5.)]]
+    m = vegas.AdaptiveMap(grid)
+    om = O.Map(grid)
+    y = rng.random((200000, 3))
+    y[:5] = [[0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5], [1 - 1e-16, 1e-300, 0.999999999999], [0.01, 0.37, 1.0]]
+    x = np.empty_like(y)
+    jac = np.empty(len(y))
+    m.map(y, x, jac)
+    xo, jo = om.map(y)
+    assert np.array_equal(x, xo) and np.array_equal(jac, jo)          # same ops, same order: bit-exact
+    assert np.array_equal(m.jac1d(y), om.jac1d(y))
+    y2 = np.empty_like(y)
+    j2 = np.empty(len(y))
+    m.invmap(x, y2, j2)
+    yo, jo2 = om.invmap(x)
+    assert np.array_equal(y2, yo) and np.array_equal(j2, jo2)
+
+
+def test_add_training_data_and_adapt_vs_oracle():
+    vegas = _vegas()
+    O = _oracle()
+    rng = np.random.default_rng(11)
+    m = vegas.AdaptiveMap([[0, 2], [-1, 1]], ninc=[50, 33])
+    om = O.Map([[0, 2], [-1, 1]], ninc=[50, 33])
+    for alpha in (1.5, 0.5, -1.0):
+        y = rng.random((50000, 2))
+        y[0] = [0.0, 1.0]              # boundary points are skipped (pyx:460)
+        f = rng.standard_normal(50000) ** 2 * np.exp(-3 * y[:, 0])
+        m.add_training_data(y, f)
+        om.add_training_data(y, f)
+        assert np.array_equal(np.rint(m.n_f), np.rint(om.n_f))
+        np.testing.assert_allclose(m.sum_f, om.sum_f, rtol=1e-12)
+        m.adapt(alpha=alpha)
+        om.adapt(alpha=alpha)
+        for d in range(2):
+            np.testing.assert_allclose(m.grid[d, :m.ninc[d] + 1], om.grid[d, :om.ninc[d] + 1], rtol=1e-11, atol=1e-15)
+
+
+# ----------------------------------------------------------------------------- RNG + allocation
+def test_philox_uniforms_bit_exact():
+    import torch
+    vegas = _vegas()
+    O = _oracle()
+    integ = vegas.Integrator(5 * [[0, 1]], neval=3000, seed=987654321012345)
+    ctx, _ = integ._engine()
+    nh = torch.zeros(integ._nlocal, dtype=torch.int32, device=ctx.device)
+    total, nmax, _ = integ._plan(ctx, nh)
+    u = torch.empty((total, 5), dtype=torch.float64, device=ctx.device)
+    ctx.uniforms(7, 0, integ._nchunks, u)
+    uo = O.philox_uniforms(987654321012345, 7, 5, 0, nh.cpu().numpy().astype(np.int64))
+    assert np.array_equal(u.cpu().numpy(), uo)
+    assert uo.min() >= 0 and uo.max() < 1
+
+
+@pytest.mark.parametrize('nh,neval,mx', [(100000, 1e6, 50000), (1000, 1e7, 200), (777, 5e3, 50000)])
+def test_allocation_bit_exact(nh, neval, mx):
+    """neval_hcube from sigf: integer results bit-exact against the reference formula
+    (pyx:1692-1706) for heavy-tailed sigf, including the max_neval_hcube clamp"""
+    import torch
+    from vegas_b200 import _lib
+    O = _oracle()
+    rng = np.random.default_rng(nh)
+    sigf = np.abs(rng.standard_cauchy(nh)) ** 0.75
+    sigf[::97] = 0.0
+    neval_sigf = 0.75 * neval / sigf.sum()
+    ctx = _lib.Context()
+    ctx.set_strata([nh], _lib.CHUNK)
+    sd = torch.from_numpy(sigf).cuda()
+    out = torch.zeros(nh, dtype=torch.int32, device='cuda')
+    total, nmin, nmax, nchunks = ctx.plan(sd, neval_sigf, 2, mx, 0, out)
+    ref = np.empty(nh, np.int64)
+    rng2 = np.array([2, 2], np.int64)
+    tot = O.lib().vo_alloc_neval(O._dp(sigf), nh, neval_sigf, 2, mx, O._ip(ref), O._ip(rng2))
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert total == tot and nmax == ref.max() and nmin == ref.min()
+    off = ctx.chunk_offsets(nchunks + 1)
+    assert off[0] == 0 and off[-1] == tot
+    assert np.array_equal(np.diff(off), np.add.reduceat(ref, np.arange(0, nh, _lib.CHUNK)))
+
+
+# ----------------------------------------------------------------------------- full iterations
+def _cases():
+    import vegas_b200 as vegas
+    F = vegas.integrands
+    rng = np.random.default_rng(3)
+    return {
+        'poly2': (2 * [[0., 2.]], F.Poly(0.5, [1.0, 2.0], [2, 3]), dict(neval=4000)),
+        'gauss4': ([[-1., 1.]] + 3 * [[0., 1.]], F.GaussMix([4 * [0.5]], 100., 1013.2118364296088), dict(neval=10000)),
+        'ridge8': (8 * [[0., 1.]], F.Ridge(8, N=17), dict(neval=60000)),
+        'ridge4_nomap': (4 * [[0., 1.]], F.Ridge(4, N=5), dict(neval=5000, alpha=0.0)),
+        'genz10_pp': (10 * [[0., 1.]], F.Genz('product_peak', 2 + 3 * rng.random(10), rng.random(10)), dict(neval=50000)),
+        'genz10_osc': (10 * [[0., 1.]], F.Genz('oscillatory', rng.random(10), rng.random(10)), dict(neval=50000, beta=0.0)),
+        'genz3_corner': (3 * [[0., 1.]], F.Genz('corner_peak', 1 + rng.random(3), rng.random(3)), dict(neval=8000, adapt_to_errors=True)),
+        'peaks20': (20 * [[0., 1.]], F.GaussMix([5 * [c] + 15 * [0.45] for c in (.23, .39, .74)], 100., 356047712484621.56),
+                    dict(neval=200000, nstrat=5 * [6] + 15 * [1])),
+        'pathint10': (10 * [[-np.pi / 2, np.pi / 2]], F.PathIntegral(T=4., ndT=10, x0list=np.linspace(0, 2., 6)),
+                      dict(neval=40000, alpha=0.1)),
+        'pathint8_nocorr': (8 * [[-np.pi / 2, np.pi / 2]], F.PathIntegral(T=4., ndT=8, x0list=np.linspace(0, 2., 6)),
+                            dict(neval=30000, correlate_integrals=False)),
+    }
+
+
+CASES = ['poly2', 'gauss4', 'ridge8', 'ridge4_nomap', 'genz10_pp', 'genz10_osc', 'genz3_corner', 'peaks20',
+         'pathint10', 'pathint8_nocorr']
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_fused_iterations_vs_oracle(name):
+    """three adapting iterations of the fused kernel vs the oracle on the same uniforms"""
+    limits, f, kw = _cases()[name]
+    eng = run_engine_iterations(limits, f, nitn=3, seed=1000 + len(name), **kw)
+    ora = run_oracle_iterations(limits, f, nitn=3, seed=1000 + len(name), engine=eng, **kw)
+    compare_iterations(eng, ora, rtol=1e-11 if name.startswith('pathint') else RTOL, var_rtol=1e-10)
+
+
+@pytest.mark.parametrize('name', ['poly2', 'gauss4', 'genz10_pp', 'pathint10', 'genz3_corner'])
+def test_unfused_iterations_vs_oracle(name):
+    """sample -> host numpy integrand -> reduce (the callback path) vs the oracle"""
+    limits, f, kw = _cases()[name]
+    eng = run_engine_iterations(limits, f, nitn=3, seed=77, fused=False, **kw)
+    ora = run_oracle_iterations(limits, f, nitn=3, seed=77, engine=eng, **kw)
+    compare_iterations(eng, ora, rtol=RTOL, var_rtol=1e-10)
+
+
+def test_fused_equals_unfused_streams():
+    """the fused kernel and the unfused path consume the same samples"""
+    limits, f, kw = _cases()['gauss4']
+    a = run_engine_iterations(limits, f, nitn=2, seed=5, fused=True, **kw)
+    b = run_engine_iterations(limits, f, nitn=2, seed=5, fused=False, **kw)
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra['neval_hcube'], rb['neval_hcube'])
+        assert np.array_equal(ra['n_f'], rb['n_f'])
+        np.testing.assert_allclose(ra['mean'], rb['mean'], rtol=1e-12)
+
+
+def test_random_batch_matches_oracle():
+    """Integrator.random_batch: x, y, wgt, hcube in hypercube order (pyx:1601-1634)"""
+    vegas = _vegas()
+    O = _oracle()
+    integ = vegas.Integrator([[0, 1], [-1, 3], [0, 10]], neval=5000, seed=42, min_neval_batch=1500)
+    parts = list(integ.random_batch(yield_hcube=True, yield_y=True))
+    assert len(parts) > 1
+    x = np.concatenate([p[0] for p in parts]); y = np.concatenate([p[1] for p in parts])
+    w = np.concatenate([p[2] for p in parts]); hc = np.concatenate([p[3] for p in parts])
+    assert len(x) == integ.last_neval and np.all(np.diff(hc) >= 0)
+    v = O.Vegas([[0, 1], [-1, 3], [0, 10]], neval=5000)
+    nh, _ = v.allocation()
+    u = O.philox_uniforms(42, 1, 3, 0, nh)
+    yo = np.empty_like(u); hco = np.empty(len(u), np.int64)
+    O.lib().vo_stratify(O._ip(v.nstrat), 3, 0, len(nh), O._ip(nh), O._dp(u), O._dp(yo), O._ip(hco))
+    xo, jo = v.map.map(yo)
+    O.lib().vo_weights(O._dp(jo), O._ip(nh), len(nh), 1. / v.nhcube)
+    assert np.array_equal(hc, hco) and np.array_equal(y, yo)
+    np.testing.assert_allclose(x, xo, rtol=1e-15)
+    np.testing.assert_allclose(w, jo, rtol=1e-15)
+    assert abs(w.sum() - 40.0) < 1e-9            # sum of weights = volume
+
+
+# ----------------------------------------------------------------------------- integrals
+def test_integrals_statistically_correct():
+    """reference-style checks (tests/test_vegas.py:791-838): |mean - exact| < 5 sigma, Q > 1e-3"""
+    vegas = _vegas()
+    F = vegas.integrands
+    rng = np.random.default_rng(8)
+    cases = [
+        ([[-1., 1.]] + 3 * [[0., 1.]], F.GaussMix([4 * [0.5]], 100., 1013.2118364296088), 1.0, dict(neval=20000)),
+        (8 * [[0., 1.]], F.Ridge(8, N=30), None, dict(neval=400000)),
+        (6 * [[0., 1.]], F.Genz('gaussian', 2 + 2 * rng.random(6), 0.3 + 0.4 * rng.random(6)), 'exact', dict(neval=100000)),
+        (5 * [[0., 1.]], F.Genz('c0', 1 + 2 * rng.random(5), rng.random(5)), 'exact', dict(neval=100000)),
+        (4 * [[0., 1.]], F.Genz('discontinuous', rng.random(4), 0.2 + 0.6 * rng.random(4)), 'exact', dict(neval=100000)),
+        (7 * [[0., 1.]], F.Genz('corner_peak', 0.2 + rng.random(7), rng.random(7)), 'exact', dict(neval=100000)),
+    ]
+    for limits, f, exact, kw in cases:
+        integ = vegas.Integrator(limits, seed=31, **kw)
+        integ(f, nitn=6)
+        r = integ(f, nitn=8)
+        if exact == 'exact':
+            exact = f.exact()
+        if exact is None:
+            from scipy.special import erf
+            # ridge: mean over k of prod_d Gaussian integral over [0,1]
+            x0 = f.x0
+            one = 0.5 * (erf(10 * (1 - x0)) + erf(10 * x0))
+            exact = float(np.mean(one ** f.dim))
+        assert abs(r.mean - exact) < 5 * r.sdev, (type(f).__name__, getattr(f, 'kind', ''), r.mean, r.sdev, exact)
+        assert r.Q > 1e-3, (type(f).__name__, r.Q)
+        assert r.sdev < 0.02 * abs(exact)
+
+
+def test_constant_and_zero_integrands():
+    """reference tests/test_vegas.py:774-789, 1272-1296: EPSILON clamp and the sum_sigf == 0 reset"""
+    vegas = _vegas()
+    F = vegas.integrands
+    integ = vegas.Integrator([[-1, 1], [0, 4]], seed=3)
+    r = integ(F.Poly(2.0))
+    np.testing.assert_allclose(r.mean, 16, rtol=1e-6)
+    assert r.sdev < 1e-6
+    integ = vegas.Integrator([(0, 1)], neval=100, alpha=0, seed=4)
+    res = integ(F.Poly(7.0), nitn=4)
+    assert abs(res.itn_results[0].sdev / res.itn_results[1].sdev - 1.0) < 1e-7
+    assert abs(res.itn_results[0].sdev / res.sdev - 2.0) < 1e-7
+    assert abs(res.mean - 7.0) < 1e-7
+    res = integ(F.Poly(7.0), nitn=4, neval=1e2, adapt=False)
+    assert abs(res.itn_results[0].sdev / res.sdev - 2.0) < 1e-7
+    integ = vegas.Integrator([(0, 1)], seed=5)
+    res = integ(F.Poly(0.0), nitn=4, neval=100)
+    assert res.mean == 0.0
+
+
+def test_python_integrands_through_gpu_sampler():
+    """scalar / lbatch / rbatch / dict-valued python integrands (pyx:2959-3383) on GPU samples"""
+    vegas = _vegas()
+    integ = vegas.Integrator([[0, 1], [0, 2]], neval=4000, seed=11)
+
+    def fs(x):
+        return x[0] * x[1]
+
+    @vegas.lbatchintegrand
+    def fl(x):
+        return x[:, 0] * x[:, 1]
+
+    @vegas.rbatchintegrand
+    def fr(x):
+        return dict(a=x[0] * x[1], b=[x[0], x[1] ** 2])
+
+    for f in (fs, fl):
+        r = integ(f, nitn=5)
+        assert abs(r.mean - 1.0) < 5 * r.sdev and r.sdev < 0.01
+    r = integ(fr, nitn=5)
+    assert abs(r['a'].mean - 1.0) < 5 * r['a'].sdev
+    assert abs(r['b'][0].mean - 1.0) < 5 * r['b'][0].sdev
+    assert abs(r['b'][1].mean - 8. / 3.) < 5 * r['b'][1].sdev
+
+    def bad(x):
+        return float('nan')
+
+    with pytest.raises(ValueError):
+        integ(bad, nitn=1)
+
+    def boom(x):
+        return 1 / 0
+
+    with pytest.raises(ZeroDivisionError):
+        integ(boom, nitn=1)
+
+
+def test_device_batch_callback():
+    """@devicebatchintegrand: torch CUDA tensors in HBM, no host round trip"""
+    import torch
+    vegas = _vegas()
+
+    @vegas.devicebatchintegrand
+    def f(x):
+        assert x.is_cuda and x.dtype == torch.float64
+        return torch.exp(-100. * ((x - 0.5) ** 2).sum(dim=1)) * 1013.2118364296088
+
+    integ = vegas.Integrator([[-1., 1.]] + 3 * [[0., 1.]], neval=50000, seed=2)
+    integ(f, nitn=5)
+    r = integ(f, nitn=5)
+    assert abs(r.mean - 1.0) < 5 * r.sdev and r.sdev < 0.01
+
+
+def test_large_cubes_and_giant_cube_paths():
+    """cubes above VB_WARP_CUBE samples (warp reduce) and above the staging capacity (global
+    scratch) agree with the oracle"""
+    vegas = _vegas()
+    F = vegas.integrands
+    f = F.GaussMix([[0.3, 0.6]], 400., 1.0)
+    for kw in (dict(neval=40000, nstrat=[4, 3]), dict(neval=30000, nstrat=[1, 2]), dict(neval=9000, nstrat=[1, 1])):
+        eng = run_engine_iterations(2 * [[0., 1.]], f, nitn=2, seed=9, **kw)
+        ora = run_oracle_iterations(2 * [[0., 1.]], f, nitn=2, seed=9, engine=eng, **kw)
+        compare_iterations(eng, ora, rtol=1e-11, var_rtol=1e-9)

@@ -1,0 +1,487 @@
+"""Gaussian-variable support for the result classes (``RAvg`` / ``RAvgArray`` / ``RAvgDict``).
+
+The reference builds its results on the third-party ``gvar`` package (gvar>=13.1.5,
+/root/reference/pyproject.toml:28; ``RAvg(gvar.GVar)`` _vegas.pyx:2276, ``RAvgDict(gvar.BufferDict)``
+_vegas.pyx:2453).  If ``gvar`` is importable it is used unchanged, so results interoperate with
+the rest of a user's gvar code.  Otherwise the minimal implementation below provides what the
+integration path touches: ``GVar`` with linear error propagation, ``gvar()``, ``mean/sdev/var/
+evalcov``, ``BufferDict``, ``SVD`` with svdcut, ``gammaQ`` and the ``1.35(86)`` formatter.
+This is host-side bookkeeping of a few numbers per iteration; it is not on the sampling path.
+"""
+import pickle as _pickle
+
+import numpy as _np
+from scipy.special import gammaincc as _gammaincc
+
+__version__ = '0.0-builtin'
+
+RNG = _np.random.default_rng()
+
+
+def ranseed(seed=None, size=3, version=None):
+    """Seed the shared generator; returns the seed used (tuple)."""
+    global RNG
+    if seed is None:
+        seed = tuple(int(s) for s in _np.random.SeedSequence().generate_state(size))
+    try:
+        seed = tuple(int(s) for s in seed)
+    except TypeError:
+        seed = (int(seed),)
+    RNG = _np.random.default_rng(list(seed))
+    # keep the legacy numpy global stream seeded as well (reference tests use it)
+    _np.random.seed(int(sum(seed)) % (2 ** 32))
+    return seed
+
+
+class GVarRef(object):
+    """Placeholder type: the reference only does isinstance checks on it."""
+
+
+class _Block(object):
+    """Shared covariance block for GVars created together."""
+    __slots__ = ('cov',)
+
+    def __init__(self, cov):
+        self.cov = _np.array(cov, dtype=float)
+
+
+class GVar(object):
+    """Gaussian variable = mean + sum_i coef_i * z_i with z ~ N(0, block.cov)."""
+
+    def __init__(self, mean=0.0, terms=None, *extra):
+        # ``internaldata`` round-trips through this signature (RAvg.__init__)
+        self.mean = float(mean)
+        self._terms = list(terms) if terms else []   # [(block, index, coef)]
+
+    @property
+    def internaldata(self):
+        return (self.mean, self._terms)
+
+    @property
+    def var(self):
+        return float(_cov_between(self, self))
+
+    @property
+    def sdev(self):
+        v = self.var
+        return float(v ** 0.5) if v > 0 else 0.0
+
+    # --- linear arithmetic -------------------------------------------------
+    def _scaled(self, c):
+        return GVar(self.mean * c, [(b, i, k * c) for b, i, k in self._terms])
+
+    def __neg__(self):
+        return self._scaled(-1.0)
+
+    def __pos__(self):
+        return self
+
+    def __add__(self, other):
+        if isinstance(other, GVar):
+            return GVar(self.mean + other.mean, self._terms + other._terms)
+        if isinstance(other, _np.ndarray):
+            return NotImplemented
+        return GVar(self.mean + float(other), self._terms)
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        if isinstance(other, _np.ndarray):
+            return NotImplemented
+        return self + (-other)
+
+    def __rsub__(self, other):
+        return (-self) + other
+
+    def __mul__(self, other):
+        if isinstance(other, GVar):
+            a = self._scaled(other.mean)
+            b = other._scaled(self.mean)
+            return GVar(self.mean * other.mean, a._terms + b._terms)
+        if isinstance(other, _np.ndarray):
+            return NotImplemented
+        return self._scaled(float(other))
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        if isinstance(other, GVar):
+            inv = GVar(1.0 / other.mean,
+                       [(b, i, -k / other.mean ** 2) for b, i, k in other._terms])
+            return self * inv
+        if isinstance(other, _np.ndarray):
+            return NotImplemented
+        return self._scaled(1.0 / float(other))
+
+    def __rtruediv__(self, other):
+        inv = GVar(1.0 / self.mean,
+                   [(b, i, -k / self.mean ** 2) for b, i, k in self._terms])
+        return inv * other
+
+    def __pow__(self, p):
+        p = float(p)
+        return GVar(self.mean ** p,
+                    [(b, i, k * p * self.mean ** (p - 1)) for b, i, k in self._terms])
+
+    def __call__(self):
+        """A random sample from the distribution."""
+        return self.mean + self.sdev * RNG.standard_normal()
+
+    def __float__(self):
+        return self.mean
+
+    def __str__(self):
+        return fmt_gvar(self.mean, self.sdev)
+
+    __repr__ = __str__
+
+    def __format__(self, spec):
+        return format(str(self), spec)
+
+
+def _cov_between(a, b):
+    tot = 0.0
+    for ba, ia, ka in a._terms:
+        for bb, ib, kb in b._terms:
+            if ba is bb:
+                tot += ka * kb * ba.cov[ia, ib]
+    return tot
+
+
+def fmt_gvar(mean, sdev):
+    """gvar's compact '1.35(86)' notation (2 significant digits on the error)."""
+    if not _np.isfinite(mean) or not _np.isfinite(sdev):
+        return '%g +- %g' % (mean, sdev)
+    if sdev == 0:
+        return '%g(0)' % mean
+    if sdev < 0:
+        sdev = -sdev
+    # exponent of the leading digit of sdev, keep 2 digits
+    e = int(_np.floor(_np.log10(sdev)))
+    s2 = round(sdev / 10.0 ** (e - 1))
+    if s2 >= 100:
+        e += 1
+        s2 = round(sdev / 10.0 ** (e - 1))
+    ndec = -(e - 1)                      # decimals needed to show 2 digits
+    if abs(mean) >= 1e16 * sdev or abs(mean) >= 1e7 or (0 < abs(mean) < 1e-5 and sdev < 1e-5):
+        # scientific fallback
+        me = int(_np.floor(_np.log10(max(abs(mean), sdev))))
+        return fmt_gvar(mean / 10.0 ** me, sdev / 10.0 ** me) + 'e%+03d' % me
+    if ndec <= 0:
+        # error >= 10: integers
+        return '%.0f(%.0f)' % (mean, round(sdev))
+    if e >= 0:
+        # 1 <= sdev < 10  ->  '13.5(8.6)'
+        return '%.*f(%.*f)' % (ndec, mean, ndec, sdev)
+    return '%.*f(%d)' % (ndec, mean, int(s2))
+
+
+def gvar(*args):
+    """gvar(mean, sdev) | gvar(mean_array, sdev_array | cov_matrix) | gvar(GVar)."""
+    if len(args) == 1:
+        a = args[0]
+        if isinstance(a, GVar):
+            return a
+        if isinstance(a, (tuple, list)) and len(a) == 2 and _np.ndim(a[0]) == 0:
+            return gvar(*a)
+        return _np.asarray(a, dtype=object)
+    m, s = args
+    if _np.ndim(m) == 0:
+        m = float(m)
+        s = float(s)
+        return GVar(m, [(_Block([[s * s]]), 0, 1.0)])
+    m = _np.asarray(m, dtype=float)
+    s = _np.asarray(s, dtype=float)
+    if s.shape == m.shape:
+        cov = _np.diag(s.reshape(-1) ** 2)
+    else:
+        cov = s.reshape(m.size, m.size)
+    blk = _Block(cov)
+    out = _np.empty(m.size, dtype=object)
+    for i, mi in enumerate(m.reshape(-1)):
+        out[i] = GVar(mi, [(blk, i, 1.0)])
+    return out.reshape(m.shape)
+
+
+def _is_bd(g):
+    return isinstance(g, BufferDict)
+
+
+def mean(g):
+    if isinstance(g, GVar):
+        return g.mean
+    if _is_bd(g):
+        return BufferDict(g, buf=mean(g.buf))
+    a = _np.asarray(g)
+    if a.dtype != object:
+        return _np.array(a, dtype=float)
+    out = _np.empty(a.shape, dtype=float)
+    for idx in _np.ndindex(a.shape):
+        v = a[idx]
+        out[idx] = v.mean if isinstance(v, GVar) else float(v)
+    return out if out.shape != () else float(out)
+
+
+def sdev(g):
+    if isinstance(g, GVar):
+        return g.sdev
+    if _is_bd(g):
+        return BufferDict(g, buf=sdev(g.buf))
+    a = _np.asarray(g)
+    out = _np.zeros(a.shape, dtype=float)
+    if a.dtype == object:
+        for idx in _np.ndindex(a.shape):
+            v = a[idx]
+            out[idx] = v.sdev if isinstance(v, GVar) else 0.0
+    return out if out.shape != () else float(out)
+
+
+def var(g):
+    return sdev(g) ** 2
+
+
+def evalcov(g):
+    if _is_bd(g):
+        g = g.buf
+    flat = list(_np.asarray(g, dtype=object).reshape(-1))
+    n = len(flat)
+    cov = _np.zeros((n, n), float)
+    for i in range(n):
+        for j in range(i + 1):
+            if isinstance(flat[i], GVar) and isinstance(flat[j], GVar):
+                cov[i, j] = cov[j, i] = _cov_between(flat[i], flat[j])
+    shape = _np.shape(g)
+    return cov.reshape(shape + shape) if len(shape) != 1 else cov
+
+
+def evalcorr(g):
+    cov = evalcov(_np.asarray(g, dtype=object).reshape(-1))
+    d = _np.sqrt(_np.diag(cov))
+    d[d == 0] = 1.0
+    return cov / d[:, None] / d[None, :]
+
+
+def corr(a, b):
+    c = _cov_between(a, b)
+    return c / (a.sdev * b.sdev) if a.sdev > 0 and b.sdev > 0 else 0.0
+
+
+def gammaQ(a, x):
+    return float(_gammaincc(a, x))
+
+
+class BufferDict(dict):
+    """Ordered dict whose values are views into one flat buffer ``buf``.
+
+    ``shape`` is always ``None`` (that is how the reference tells a dict from an
+    array, ``_vegas.pyx:1523``).
+    """
+    shape = None
+
+    def __init__(self, *args, **kargs):
+        dict.__init__(self)
+        self._slices = {}
+        buf = kargs.pop('buf', None)
+        lbatch_buf = kargs.pop('lbatch_buf', None)
+        rbatch_buf = kargs.pop('rbatch_buf', None)
+        src = args[0] if args else None
+        if src is None:
+            self._buf = _np.zeros(0, float)
+            return
+        if isinstance(src, BufferDict) and (buf is not None or lbatch_buf is not None
+                                            or rbatch_buf is not None):
+            if lbatch_buf is not None:
+                lb = _np.asarray(lbatch_buf)
+                for k in src:
+                    sl, sh = src.slice_shape(k)
+                    v = lb[:, sl]
+                    dict.__setitem__(self, k, v if sh == () else v.reshape((lb.shape[0],) + sh))
+                self._layout_from(src)
+                self._buf = lb
+                return
+            if rbatch_buf is not None:
+                rb = _np.asarray(rbatch_buf)
+                for k in src:
+                    sl, sh = src.slice_shape(k)
+                    v = rb[sl]
+                    dict.__setitem__(self, k, v if sh == () else v.reshape(sh + (rb.shape[-1],)))
+                self._layout_from(src)
+                self._buf = rb
+                return
+            b = _np.asarray(buf)
+            if b.dtype != object:
+                b = _np.array(b, dtype=float)
+            self._layout_from(src)
+            self._buf = b.reshape(-1)
+            self._refresh()
+            return
+        items = src.items() if hasattr(src, 'keys') else src
+        chunks = []
+        n = 0
+        for k, v in items:
+            a = _np.asarray(v)
+            if a.dtype != object:
+                a = _np.array(a, dtype=float)
+            if a.shape == ():
+                self._slices[k] = (n, ())
+                n += 1
+            else:
+                self._slices[k] = (slice(n, n + a.size), a.shape)
+                n += a.size
+            chunks.append(a.reshape(-1))
+        if chunks:
+            isobj = any(c.dtype == object for c in chunks)
+            self._buf = _np.concatenate([c.astype(object) if isobj else c for c in chunks])
+        else:
+            self._buf = _np.zeros(0, float)
+        self._refresh()
+
+    def _layout_from(self, src):
+        self._slices = dict(src._slices)
+        for k in src:
+            if k not in self:
+                dict.__setitem__(self, k, None)
+
+    def _refresh(self):
+        for k, (sl, sh) in self._slices.items():
+            dict.__setitem__(self, k, self._buf[sl] if sh == () else self._buf[sl].reshape(sh))
+
+    def __setitem__(self, k, v):
+        if k in self._slices:
+            sl, sh = self._slices[k]
+            if sh == ():
+                self._buf[sl] = v
+            else:
+                self._buf[sl] = _np.asarray(v).reshape(-1)
+            self._refresh()
+            return
+        a = _np.asarray(v)
+        if a.dtype != object:
+            a = _np.array(a, dtype=float)
+        n = self._buf.size
+        if a.shape == ():
+            self._slices[k] = (n, ())
+        else:
+            self._slices[k] = (slice(n, n + a.size), a.shape)
+        if a.dtype == object or self._buf.dtype == object:
+            self._buf = _np.concatenate([self._buf.astype(object), a.reshape(-1).astype(object)])
+        else:
+            self._buf = _np.concatenate([self._buf, a.reshape(-1)])
+        self._refresh()
+
+    def slice_shape(self, k):
+        return self._slices[k]
+
+    # values are read through to the buffer on every access, so in-place updates of
+    # ``buf`` (RAvgDict shares its buffer with a RAvgArray) are always visible
+    def __getitem__(self, k):
+        if k in self._slices and self._buf.ndim == 1:
+            sl, sh = self._slices[k]
+            return self._buf[sl] if sh == () else self._buf[sl].reshape(sh)
+        return dict.__getitem__(self, k)
+
+    def values(self):
+        return [self[k] for k in self]
+
+    def items(self):
+        return [(k, self[k]) for k in self]
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def __repr__(self):
+        return '{' + ', '.join('%r: %r' % (k, self[k]) for k in self) + '}'
+
+    __str__ = __repr__
+
+    @property
+    def buf(self):
+        return self._buf
+
+    @buf.setter
+    def buf(self, b):
+        b = _np.asarray(b) if not isinstance(b, _np.ndarray) else b
+        self._buf = b.reshape(-1) if b.ndim != 1 else b
+        self._refresh()
+
+    @property
+    def size(self):
+        return self._buf.size if self._buf.ndim == 1 else sum(
+            1 if sh == () else int(_np.prod(sh)) for _, sh in self._slices.values())
+
+    @property
+    def flat(self):
+        return self._buf.flat
+
+    def __reduce__(self):
+        return (BufferDict, ([(k, self[k]) for k in self],))
+
+
+def asbufferdict(g):
+    return g if isinstance(g, BufferDict) else BufferDict(g)
+
+
+class SVD(object):
+    """Eigen-analysis of a symmetric matrix with gvar-style ``svdcut``.
+
+    ``svdcut < 0`` drops modes whose eigenvalue is below ``|svdcut| * max``;
+    ``svdcut > 0`` raises them to that floor.  ``decomp(n)`` returns rows
+    ``w_i = vec_i * val_i**(n/2)`` so that ``sum_i w_i w_i^T = mat**n``.
+    """
+
+    def __init__(self, mat, svdcut=None, svdnum=None, compute_delta=False, rescale=False):
+        mat = _np.asarray(mat, dtype=float)
+        if rescale:
+            self.D = _np.fabs(mat.diagonal()) ** (-0.5)
+            work = (mat * self.D).T * self.D
+        else:
+            self.D = None
+            work = mat
+        vec, val, _ = _np.linalg.svd(work)
+        vec = vec.T[::-1]
+        val = val[::-1]                      # ascending
+        self.kappa = val[0] / val[-1] if val[-1] != 0 else None
+        self.nmod = 0
+        self.dof = len(val)
+        if svdcut:
+            floor = abs(svdcut) * val[-1]
+            if svdcut > 0:
+                small = val < floor
+                self.nmod = int(small.sum())
+                val = _np.where(small, floor, val)
+            else:
+                keep = val >= floor
+                first = int(_np.argmax(keep)) if keep.any() else len(val)
+                val = val[first:]
+                vec = vec[first:]
+                self.dof = len(val)
+        self.val = val
+        self.vec = vec
+
+    def decomp(self, n=1):
+        w = _np.array(self.vec)
+        if self.D is not None:
+            w = w * (self.D if n < 0 else 1.0 / self.D)
+        return (w.T * self.val ** (n / 2.0)).T
+
+
+def dumps(g, protocol=None):
+    return _pickle.dumps(g, protocol=protocol if protocol is not None else _pickle.HIGHEST_PROTOCOL)
+
+
+def loads(b):
+    return _pickle.loads(b)
+
+
+def remove_gvars(g, gvlist):
+    return g
+
+
+def distribute_gvars(g, gvlist):
+    return g
+
+
+def gvar_factory():
+    return gvar
+
+
+def tabulate(g, **kargs):
+    return '\n'.join('%s  %s' % (k, g[k]) for k in g) if hasattr(g, 'keys') else str(g)

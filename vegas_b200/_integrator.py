@@ -1,0 +1,762 @@
+"""``Integrator`` -- the reference's driver API (``_vegas.pyx:834-2230``) over the B200 engine.
+
+What stays on the host (small, once per call / iteration): parameter handling and the integer
+stratification set-up of ``set()`` (bit-exact with the reference), ``AdaptiveMap.adapt``, result
+averaging.  What runs on the GPU: the whole per-iteration loop -- vegas+ allocation, Philox
+sampling, stratified y, y->x map, integrand (device functor, or a batch callback fed from HBM),
+per-hypercube two-pass mean/variance, ``sigf`` update and the map's training histogram.
+
+With ``mpi=True`` and an initialised ``torch.distributed`` process group the hypercube index range
+is sharded block-cyclically over the ranks (one GPU each) and the per-iteration sums are
+all-reduced (NCCL over NVLink); every rank then performs the same host steps and returns the
+same result.
+"""
+import os
+
+import numpy as np
+
+from . import _lib
+from ._gv import gv
+from ._integrand import VegasIntegrand, DeviceIntegrand
+from ._map import AdaptiveMap, HUGE
+from ._results import VegasResult
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+class Integrator(object):
+    r""" Adaptive multidimensional Monte Carlo integration (vegas / vegas+).
+
+    Same constructor, ``set()``, ``__call__``, ``random_batch()`` ... and the same parameters as the
+    reference class (docstring at ``_vegas.pyx:834-1112``).  Additional, engine-specific settings
+    (not in ``defaults``): ``device`` (CUDA device index, default the current device), ``seed``
+    (Philox key; default drawn from ``gvar.RNG`` so ``gvar.ranseed`` makes runs reproducible),
+    ``fused`` (use the compiled device functor when the integrand has one; default True),
+    ``max_batch`` (rows per batch handed to device callbacks).
+    """
+
+    # Settings accessible via the constructor and Integrator.set (same keys as _vegas.pyx:1115-1140)
+    defaults = dict(
+        map=None,               # integration region, AdaptiveMap, or Integrator
+        neval=1000,             # number of evaluations per iteration
+        maxinc_axis=1000,       # number of adaptive-map increments per axis
+        min_neval_batch=100000,  # min. number of evaluations per batch
+        max_neval_hcube=50000,  # max number of evaluations per h-cube
+        gpu_pad=False,          # pad batches for use by GPUs
+        neval_frac=0.75,        # fraction of evaluations used for adaptive stratified sampling
+        max_mem=1e9,            # memory cutoff (# of floats)
+        nitn=10,                # number of iterations
+        alpha=0.5,              # damping parameter for importance sampling
+        beta=0.75,              # damping parameter for stratified sampliing
+        adapt=True,             # flag to turn adaptation on or off
+        correlate_integrals=True,  # calculate correlations between different integrals
+        minimize_mem=False,     # minimize work memory (when neval very large)?
+        adapt_to_errors=False,  # alternative approach to stratified sampling (low dim)?
+        uniform_nstrat=False,   # require same nstrat[d] for all directions d?
+        rtol=0,                 # relative error tolerance
+        atol=0,                 # absolute error tolerance
+        analyzer=None,          # analyzes results from each iteration
+        ran_array_generator=None,  # alternative random number generator
+        sync_ran=True,          # synchronize random generators across MPI processes?
+        mpi=False,              # allow multi-GPU (torch.distributed)?
+        uses_jac=False,         # return Jacobian to integrand?
+        nproc=1,                # number of processors to use
+    )
+    # engine-specific settings (kept out of ``defaults`` so that dict mirrors the reference)
+    engine_defaults = dict(device=None, seed=None, fused=True, max_batch=1 << 22, slab=None)
+
+    def __init__(self, map, **kargs):
+        self.neval_hcube_range = None
+        self.last_neval = 0
+        self.pool = None
+        self._ctx = None
+        self._ctx_map_version = None
+        self._ctx_strata = None
+        self._sigf_dev = None
+        self._sigf_host = None
+        self._sigf_len = 0
+        self._itn_counter = 0
+        self._launches = 0
+        self._trace = None      # test hook: called with the raw per-iteration sums before adapt
+        for k, v in self.engine_defaults.items():
+            setattr(self, k, v)
+        for k in list(kargs):
+            if k in self.engine_defaults:
+                setattr(self, k, kargs.pop(k))
+        if isinstance(map, Integrator):
+            self._set_map(map)
+            args = {}
+            for k in Integrator.defaults:
+                if k != 'map':
+                    args[k] = getattr(map, k)
+            self._sigf_host = np.array(map.sigf)
+            self._sigf_len = len(self._sigf_host)
+            self.sum_sigf = np.sum(self._sigf_host)
+            self.nstrat = np.array(map.nstrat)
+            if 'nstrat' not in kargs:
+                kargs['nstrat'] = map.nstrat
+                if 'neval' not in kargs:
+                    kargs['neval'] = map.neval
+        else:
+            self._sigf_host = np.array([], float)
+            self._sigf_len = 0
+            self.sum_sigf = HUGE
+            args = dict(Integrator.defaults)
+            del args['map']
+            self._set_map(map)
+            self.nstrat = np.full(self.map.dim, 0, dtype=np.intp)
+        for k in Integrator.defaults:
+            if k != 'map' and not hasattr(self, k):
+                setattr(self, k, Integrator.defaults[k])
+        args.update(kargs)
+        if 'nstrat' in kargs and 'neval' not in kargs and 'neval' in args:
+            del args['neval']
+        if 'neval' in kargs and 'nstrat' not in kargs and 'nstrat' in args:
+            del args['nstrat']
+        self.set(args)
+
+    # ------------------------------------------------------------------ pickling (pyx:1194-1207)
+    def __reduce__(self):
+        odict = dict()
+        for k in Integrator.defaults:
+            if k in ['map']:
+                continue
+            odict[k] = getattr(self, k)
+        odict['nstrat'] = np.asarray(self.nstrat)
+        odict['sigf'] = np.asarray(self.sigf)
+        return (Integrator, (self.map,), odict)
+
+    def __setstate__(self, odict):
+        self.set(odict)
+
+    # ------------------------------------------------------------------ sigf: host view of device state
+    def _get_sigf(self):
+        if self._sigf_dev is not None:
+            local = self._sigf_dev.cpu().numpy()
+            rank, world = self._rank_world()
+            if world == 1:
+                return local
+            return self._gather_sigf(local, rank, world)
+        if self._sigf_host is not None:
+            return self._sigf_host
+        return np.ones(self._sigf_len, float)
+
+    sigf = property(_get_sigf, doc="sigf[h] = |variance of hypercube h|**(beta/2) (host copy)")
+
+    def _gather_sigf(self, local, rank, world):
+        import torch
+        dist = _dist()
+        nh, slab = int(self.nhcube), self._slab(world)
+        counts = [len(_local_cubes(nh, slab, r, world)) for r in range(world)]
+        bufs = [torch.empty(c, dtype=torch.float64, device=self._sigf_dev.device) for c in counts]
+        dist.all_gather(bufs, self._sigf_dev)
+        out = np.empty(nh, float)
+        for r in range(world):
+            out[_local_cubes(nh, slab, r, world)] = bufs[r].cpu().numpy()
+        return out
+
+    def _set_map(self, map):
+        r""" install new map, create xsample (pyx:1209-1253) """
+        if isinstance(map, AdaptiveMap):
+            self.map = AdaptiveMap(map)
+            self.xsample = np.empty(self.map.dim, dtype=float)
+            for d in range(self.map.dim):
+                self.xsample[d] = gv.RNG.uniform(*self.map.region(d))
+        elif isinstance(map, Integrator):
+            self.map = AdaptiveMap(map.map)
+            self.xsample = gv.BufferDict(map.xsample) if map.xsample.shape is None else np.array(map.xsample)
+        elif hasattr(map, 'keys'):
+            map = gv.asbufferdict(map)
+            self.xsample = gv.BufferDict()
+            limits = []
+            for k in map:
+                shape = np.shape(map[k])[:-1]
+                if shape == ():
+                    self.xsample[k] = gv.RNG.uniform(*map[k])
+                    limits.append(map[k])
+                else:
+                    tmp = np.empty(shape, dtype=float)
+                    for idx in np.ndindex(shape):
+                        tmp[idx] = gv.RNG.uniform(*map[k][idx])
+                    self.xsample[k] = tmp
+                    limits += np.array(map[k]).reshape(-1, 2).tolist()
+            self.map = AdaptiveMap(limits)
+        else:
+            map = np.array(map, dtype=object)
+            if np.shape(map.flat[0]) == ():
+                self.xsample = np.empty(map.shape[:-1], dtype=float)
+                grid = map.reshape(-1, 2)
+            else:
+                self.xsample = np.empty(map.shape, dtype=float)
+                grid = map.reshape(-1)
+            self.map = AdaptiveMap(grid)
+            for i, idx in enumerate(np.ndindex(self.xsample.shape)):
+                self.xsample[idx] = gv.RNG.uniform(*self.map.region(i))
+
+    # ------------------------------------------------------------------ set (pyx:1256-1446)
+    def set(self, ka={}, **kargs):
+        r""" Reset default parameters in integrator; returns the dictionary of the old values so
+        that ``integ.set(old_defaults)`` restores them. """
+        if kargs:
+            kargs.update(ka)
+        else:
+            kargs = ka
+        old_val = dict()
+        nstrat = None
+        for k in kargs:
+            if k == 'map':
+                old_val['map'] = self.map
+                self._set_map(kargs['map'])
+            elif k == 'nstrat':
+                if kargs['nstrat'] is None:
+                    continue
+                old_val['nstrat'] = self.nstrat
+                nstrat = np.array(kargs['nstrat'], dtype=np.intp)
+            elif k == 'sigf':
+                old_val['sigf'] = self.sigf
+                self._sigf_host = np.fabs(np.asarray(kargs['sigf'], dtype=float))
+                self._sigf_len = len(self._sigf_host)
+                self._sigf_dev = None
+                self.sum_sigf = np.sum(self._sigf_host)
+            elif k == 'nproc':
+                old_val['nproc'] = self.nproc
+                self.nproc = kargs['nproc'] if kargs['nproc'] is not None else os.cpu_count()
+                if self.nproc is None:
+                    self.nproc = 1
+            elif k in Integrator.defaults:
+                old_val[k] = getattr(self, k)
+                try:
+                    setattr(self, k, kargs[k])
+                except Exception:
+                    setattr(self, k, type(old_val[k])(kargs[k]))
+            elif k in Integrator.engine_defaults:
+                old_val[k] = getattr(self, k)
+                setattr(self, k, kargs[k])
+                if k in ('device', 'slab'):
+                    self._ctx = None
+                    self._ctx_strata = None
+            elif k not in ['nhcube_batch', 'max_nhcube']:
+                raise AttributeError('no parameter named "%s"' % str(k))
+
+        # 2) sanity checks
+        if nstrat is not None:
+            if len(nstrat) != self.map.dim:
+                raise ValueError('nstrat[d] has wrong length: %d not %d' % (len(nstrat), self.map.dim))
+            if np.any(nstrat < 1):
+                raise ValueError('bad nstrat: ' + str(np.asarray(self.nstrat)))
+        if self.neval_frac < 0 or self.neval_frac >= 1:
+            raise ValueError('neval_frac = {} but require 0 <= neval_frac < 1'.format(self.neval_frac))
+        if 'neval' in old_val and self.neval < 2:
+            raise ValueError('neval>2 required, not ' + str(self.neval))
+        neval_frac = 0 if (self.beta == 0 or self.adapt_to_errors) else self.neval_frac
+
+        self.dim = self.map.dim
+
+        # 3) determine # strata in each direction
+        if nstrat is not None:
+            if len(nstrat) != self.dim or min(nstrat) < 1:
+                raise ValueError('bad nstrat = %s' % str(np.asarray(nstrat)))
+            nhcube = np.prod(nstrat)
+            if 'neval' not in old_val:
+                old_val['neval'] = self.neval
+                self.neval = type(self.neval)(2. * nhcube / (1. - neval_frac))
+            elif self.neval < 2. * nhcube / (1. - neval_frac):
+                raise ValueError('neval too small: {} < {}'.format(self.neval, 2. * nhcube / (1. - neval_frac)))
+        elif 'neval' in old_val or 'neval_frac' in old_val:
+            ns = int(abs((1 - neval_frac) * self.neval / 2.) ** (1. / self.dim))     # strata / axis
+            if ns < 1:
+                ns = 1
+            d = int((np.log((1 - neval_frac) * self.neval / 2.) - self.dim * np.log(ns)) / np.log(1 + 1. / ns))
+            if ((ns + 1) ** d * ns ** (self.dim - d)) > self.max_mem and not self.minimize_mem:
+                raise MemoryError("work arrays larger than max_mem; set minimize_mem=True or increase max_mem")
+            if self.uniform_nstrat:
+                d = 0
+            nstrat = np.empty(self.dim, np.intp)
+            nstrat[:d] = ns + 1
+            nstrat[d:] = ns
+        else:
+            nstrat = self.nstrat
+
+        # 4) reconfigure vegas map, if necessary
+        if self.adapt_to_errors:
+            self.map.adapt(ninc=np.asarray(nstrat))
+        else:
+            ni = min(int(self.neval / 10.), self.maxinc_axis)     # increments/axis
+            ninc = np.empty(self.dim, np.intp)
+            for d in range(self.dim):
+                if ni >= nstrat[d]:
+                    ninc[d] = int(ni / nstrat[d]) * nstrat[d]
+                elif nstrat[d] <= self.maxinc_axis:
+                    ninc[d] = nstrat[d]
+                else:
+                    nstrat[d] = int(nstrat[d] / ni) * ni
+                    ninc[d] = ni
+            if not np.all(np.equal(self.map.ninc, ninc)):
+                self.map.adapt(ninc=ninc)
+
+        if not np.all(np.equal(self.nstrat, nstrat)):
+            if 'sigf' not in old_val:
+                old_val['sigf'] = self.sigf
+                self._sigf_host = np.array([], float)
+                self._sigf_dev = None
+                self._sigf_len = 0
+                self.sum_sigf = HUGE
+            self.nstrat = nstrat
+
+        # 5) set min_neval_hcube
+        self.nhcube = int(np.prod(self.nstrat, dtype=np.int64))
+        if self.nhcube == 1:
+            self.min_neval_hcube = int(self.neval)
+        else:
+            self.min_neval_hcube = int((1 - neval_frac) * self.neval / self.nhcube)
+        if self.min_neval_hcube < 2:
+            self.min_neval_hcube = 2
+
+        # 6) sigf (lives in HBM once sampling starts; "all ones" is represented lazily)
+        nsigf = self.nhcube
+        if self.beta >= 0 and self.nhcube > 1 and not self.adapt_to_errors and self._sigf_len != nsigf:
+            self._sigf_host = None
+            self._sigf_dev = None
+            self._sigf_len = nsigf
+            self.sum_sigf = nsigf
+        workspace = self.min_neval_batch + self.max_neval_hcube
+        if workspace > self.neval:
+            workspace = self.neval + 1
+        if (3 * self.dim + 3) * workspace + (0 if self.minimize_mem else self.nhcube) > self.max_mem:
+            raise MemoryError('work arrays larger than max_mem; reduce min_neval_batch or max_neval_hcube (or increase max_mem)')
+        return old_val
+
+    # ------------------------------------------------------------------ settings (pyx:1448-1590)
+    def settings(self, ngrid=0):
+        r""" Assemble summary of integrator settings into string. """
+        nhcube = np.prod(self.nstrat)
+        neval = nhcube * self.min_neval_hcube if self.beta <= 0 else self.neval
+        ans = "Integrator Settings:\n"
+        if self.beta > 0 and not self.adapt_to_errors:
+            ans += "    %.6g (approx) integrand evaluations in each of %d iterations\n" % (self.neval, self.nitn)
+        else:
+            ans += "    %.6g integrand evaluations in each of %d iterations\n" % (neval, self.nitn)
+        ans += "    number of: strata/axis = %s\n" % np.array2string(
+            np.asarray(self.nstrat), max_line_width=80, prefix=29 * ' ')
+        ans += "               increments/axis = %s\n" % np.array2string(
+            np.asarray(self.map.ninc), max_line_width=80, prefix=33 * ' ')
+        ans += "               h-cubes = %.6g  processors = %d\n" % (nhcube, self.nproc)
+        max_neval_hcube = max(self.max_neval_hcube, self.min_neval_hcube)
+        ans += "               evaluations/batch >= %.2g\n" % (float(self.min_neval_batch),)
+        ans += "               %d <= evaluations/h-cube <= %.2g\n" % (int(self.min_neval_hcube), float(max_neval_hcube))
+        ans += "    minimize_mem = %s  adapt_to_errors = %s  adapt = %s\n" % (
+            str(self.minimize_mem), str(self.adapt_to_errors), str(self.adapt))
+        ans += "    accuracy: relative = %g  absolute = %g\n" % (self.rtol, self.atol)
+        if not self.adapt:
+            ans += "    damping: alpha = %g  beta= %g\n\n" % (0., 0.)
+        elif self.adapt_to_errors:
+            ans += "    damping: alpha = %g  beta= %g\n\n" % (self.alpha, 0.)
+        else:
+            ans += "    damping: alpha = %g  beta= %g\n\n" % (self.alpha, self.beta)
+
+        # integration limits
+        offset = 4 * ' '
+        entries = []
+        axis = 0
+        limits = list(self.map.region())
+        for i in range(len(limits)):
+            limits[i] = '({:.5}, {:.5})'.format(*[float(v) for v in limits[i]])
+        if self.xsample.shape is None:
+            for k in self.xsample:
+                if np.shape(self.xsample[k]) == ():
+                    entries.append((str(k), str(axis), str(limits[axis])))
+                    axis += 1
+                else:
+                    prefix = str(k) + ' '
+                    for idx in np.ndindex(np.shape(self.xsample[k])):
+                        str_idx = ''.join(str(idx)[1:-1].split(' '))
+                        if str_idx[-1] == ',':
+                            str_idx = str_idx[:-1]
+                        entries.append((prefix + str_idx, str(axis), str(limits[axis])))
+                        if prefix != '':
+                            prefix = ''
+                        axis += 1
+            linefmt = '{e0:>{w0}}    {e1:>{w1}}    {e2:>{w2}}'
+            headers = ('key/index', 'axis', 'integration limits')
+            w0 = max(len(ei[0]) for ei in entries)
+        elif len(self.xsample.shape) > 1:
+            for idx in np.ndindex(self.xsample.shape):
+                str_idx = ''.join(str(idx)[1:-1].split(' '))
+                if str_idx[-1] == ',':
+                    str_idx = str_idx[:-1]
+                entries.append((str_idx, str(axis), str(limits[axis])))
+                axis += 1
+            linefmt = '{e0:>{w0}}    {e1:>{w1}}    {e2:>{w2}}'
+            headers = ('key/index', 'axis', 'integration limits')
+            w0 = max(len(ei[0]) for ei in entries)
+        else:
+            for axis, limits_axis in enumerate(limits):
+                entries.append((None, str(axis), str(limits_axis)))
+            linefmt = '{e1:>{w1}}    {e2:>{w2}}'
+            headers = (None, 'axis', 'integration limits')
+            w0 = None
+        w1 = max(len(ei[1]) for ei in entries)
+        w2 = max(len(ei[2]) for ei in entries)
+        ncol = 1 if self.map.dim <= 20 else 2
+        table = ncol * [[]]
+        nl = len(entries) // ncol
+        if nl * ncol < len(entries):
+            nl += 1
+        ns = len(entries) - (ncol - 1) * nl
+        ne = (ncol - 1) * [nl] + [ns]
+        iter_entries = iter(entries)
+        for col in range(ncol):
+            e0, e1, e2 = headers
+            w0 = None if e0 is None else max(len(e0), w0)
+            w1 = max(len(e1), w1)
+            w2 = max(len(e2), w2)
+            table[col] = [linefmt.format(e0=e0, w0=w0, e1=e1, w1=w1, e2=e2, w2=w2)]
+            table[col].append(len(table[col][0]) * '-')
+            for ii in range(ne[col]):
+                e0, e1, e2 = next(iter_entries)
+                table[col].append(linefmt.format(e0=e0, w0=w0, e1=e1, w1=w1, e2=e2, w2=w2))
+        mtable = []
+        ns += 2
+        nl += 2
+        for i in range(ns):
+            mtable.append('  '.join([tabcol[i] for tabcol in table]))
+        for i in range(ns, nl):
+            mtable.append('  '.join([tabcol[i] for tabcol in table[:-1]]))
+        ans += offset + ('\n' + offset).join(mtable) + '\n'
+        if ngrid > 0:
+            ans += '\n' + self.map.settings(ngrid=ngrid)
+        return ans
+
+    def _get_mpi_rank(self):
+        return self._rank_world()[0]
+
+    mpi_rank = property(_get_mpi_rank, doc="rank (>=0) in the torch.distributed group")
+
+    @staticmethod
+    def synchronize_random():
+        """kept for API compatibility: Philox streams are a pure function of (seed, itn, hypercube,
+        sample), and the seed is broadcast from rank 0 -- nothing else to synchronise"""
+
+    # ------------------------------------------------------------------ device plumbing
+    def _rank_world(self):
+        if self.mpi:
+            try:
+                dist = _dist()
+                if dist.is_available() and dist.is_initialized():
+                    return dist.get_rank(), dist.get_world_size()
+            except ImportError:
+                pass
+        return 0, 1
+
+    def _slab(self, world):
+        if self.slab is not None:
+            return int(self.slab)
+        if world == 1:
+            return _lib.CHUNK
+        per = -(-int(self.nhcube) // (world * 8))
+        per = -(-per // _lib.CHUNK) * _lib.CHUNK
+        return int(max(_lib.CHUNK, min(64 * _lib.CHUNK, per)))
+
+    def _engine(self):
+        """bring the device context up to date with map / strata / sigf; returns (ctx, torch)"""
+        import torch
+        if self._ctx is None:
+            dev = self.device
+            if dev is None and torch.cuda.is_available():
+                dev = torch.cuda.current_device()
+            self._ctx = _lib.Context(dev)
+            self._ctx_map_version = None
+            self._ctx_strata = None
+            self._sigf_dev_stale()
+        ctx = self._ctx
+        rank, world = self._rank_world()
+        if self.seed is None:
+            seed = int(gv.RNG.integers(1, 2 ** 62))
+            if world > 1:
+                t = torch.tensor([seed], dtype=torch.int64, device=ctx.device)
+                _dist().broadcast(t, 0)
+                seed = int(t.item())
+            self.seed = seed
+        ctx.set_seed(self.seed)
+        mv = (id(self.map), self.map._version)
+        if self._ctx_map_version != mv:
+            ctx.set_map(self.map.grid, self.map.ninc)
+            self._ctx_map_version = mv
+        key = (tuple(int(v) for v in self.nstrat), rank, world, self._slab(world))
+        if self._ctx_strata != key:
+            self._nlocal = ctx.set_strata(self.nstrat, key[3], rank, world)
+            self._ctx_strata = key
+            self._sigf_dev_stale()
+        # sigf
+        need_sigf = self.beta >= 0 and self.nhcube > 1 and not self.adapt_to_errors
+        if need_sigf and self._sigf_dev is None:
+            if self._sigf_host is not None and len(self._sigf_host) == self.nhcube:
+                full = np.ascontiguousarray(self._sigf_host, dtype=float)
+                local = full[_local_cubes(self.nhcube, key[3], rank, world)] if world > 1 else full
+                self._sigf_dev = torch.from_numpy(np.ascontiguousarray(local)).to(ctx.device)
+            else:
+                self._sigf_dev = torch.ones(self._nlocal, dtype=torch.float64, device=ctx.device)
+            self._sigf_host = None
+        return ctx, torch
+
+    def _sigf_dev_stale(self):
+        if self._sigf_dev is not None:
+            self._sigf_host = self._get_sigf()
+            self._sigf_dev = None
+
+    def _plan(self, ctx, neval_hcube_out=None):
+        """vegas+ allocation for the coming iteration (pyx:1657-1706) -> (local total, max)"""
+        adaptive = self.beta > 0 and self.nhcube > 1 and not self.adapt_to_errors
+        neval_sigf = (self.neval_frac * self.neval / self.sum_sigf
+                      if self.beta > 0 and self.sum_sigf > 0 and not self.adapt_to_errors else 0.0)
+        max_nh = max(self.max_neval_hcube, self.min_neval_hcube)
+        total, nmin, nmax, nchunks = ctx.plan(self._sigf_dev if adaptive else None, neval_sigf,
+                                             self.min_neval_hcube, max_nh, int(self.neval / self.nhcube),
+                                             neval_hcube_out)
+        self._nchunks = nchunks
+        return total, nmax, adaptive
+
+    def _flags(self, nf):
+        f = 0
+        if self.beta > 0 and self.nhcube > 1 and self.adapt and not self.adapt_to_errors:
+            f |= _lib.UPDATE_SIGF
+        if self.adapt_to_errors and self.adapt:
+            f |= _lib.TRAIN_ERRORS
+        elif self.adapt and self.alpha > 0:
+            f |= _lib.TRAIN
+        if self.correlate_integrals and nf > 1:
+            f |= _lib.CORRELATE
+        return f
+
+    def _batches(self, ctx, target_rows):
+        """ranges of local chunks [c0, c1) holding >= target_rows samples each (last one smaller)"""
+        off = ctx.chunk_offsets(self._nchunks + 1)
+        out, c0 = [], 0
+        while c0 < self._nchunks:
+            c1 = int(np.searchsorted(off, off[c0] + target_rows, side='left'))
+            c1 = min(max(c1, c0 + 1), self._nchunks)
+            out.append((c0, c1, int(off[c1] - off[c0])))
+            c0 = c1
+        return out
+
+    # ------------------------------------------------------------------ sampling API (pyx:1601-1863)
+    def random_batch(self, yield_hcube=False, yield_y=False):
+        r""" Low-level batch iterator over integration points and weights: yields ``x, wgt`` (plus
+        ``y`` and/or ``hcube`` on request) as numpy arrays, one iteration's worth in total, in
+        hypercube order (``_vegas.pyx:1601-1634``).  This rank's share when sharded. """
+        for t in self._random_batch(yield_hcube, yield_y, device=False):
+            yield t
+
+    def random_batch_device(self, yield_hcube=False, yield_y=False):
+        r""" Same as :meth:`random_batch` but yields CUDA ``torch`` tensors (no host copies). """
+        for t in self._random_batch(yield_hcube, yield_y, device=True):
+            yield t
+
+    def _random_batch(self, yield_hcube, yield_y, device):
+        ctx, torch = self._engine()
+        total, nmax, adaptive = self._plan(ctx)
+        self._set_neval_stats(total, nmax, adaptive)
+        itn = self._next_itn()
+        target = self.max_batch if device else self.min_neval_batch
+        for c0, c1, rows in self._batches(ctx, target):
+            x = torch.empty((rows, self.dim), dtype=torch.float64, device=ctx.device)
+            wgt = torch.empty(rows, dtype=torch.float64, device=ctx.device)
+            y = torch.empty_like(x) if yield_y else None
+            hc = torch.empty(rows, dtype=torch.int64, device=ctx.device) if yield_hcube else None
+            ctx.sample(itn, c0, c1, x, wgt, y=y, hcube=hc)
+            self._launches += 1
+            ans = (x,)
+            if yield_y:
+                ans += (y,)
+            ans += (wgt,)
+            if yield_hcube:
+                ans += (hc,)
+            yield ans if device else tuple(t.cpu().numpy() for t in ans)
+
+    random_vec = random_batch
+
+    def random(self, yield_hcube=False, yield_y=False):
+        r""" Low-level iterator over single integration points and weights (``_vegas.pyx:1770-1814``). """
+        for t in self.random_batch(yield_hcube=yield_hcube, yield_y=yield_y):
+            for i in range(t[0].shape[0]):
+                yield tuple(ti[i] for ti in t)
+
+    def sample(self, nbatch=None, mode='rbatch'):
+        r""" Generate random sample of integration weights and points: ``wgt, x = integ.sample()`` with
+        ``sum(wgt * f(x))`` an estimate of the integral (``_vegas.pyx:1816-1863``). """
+        neval = self.last_neval if self.last_neval > 0 else self.neval
+        nbatch = neval if nbatch is None else int(nbatch)
+        nit = nbatch // neval
+        if nit * neval < nbatch:
+            nit += 1
+        samples, wgts = [], []
+        for _ in range(nit):
+            for x, w in self.random_batch():
+                samples.append(np.array(x))
+                wgts.append(np.array(w))
+        samples = np.concatenate(samples, axis=0)
+        wgts = np.concatenate(wgts) / nit
+        if self.xsample.shape is None:
+            if mode == 'rbatch':
+                samples = gv.BufferDict(self.xsample, rbatch_buf=samples.T)
+            else:
+                samples = gv.BufferDict(self.xsample, lbatch_buf=samples)
+        elif self.xsample.shape != ():
+            if mode == 'rbatch':
+                samples = samples.T
+                samples.shape = self.xsample.shape + (-1,)
+            else:
+                samples.shape = (-1,) + self.xsample.shape
+        return wgts, samples
+
+    def _next_itn(self):
+        self._itn_counter += 1
+        return self._itn_counter & 0xFFFFFF
+
+    def _set_neval_stats(self, total, nmax, adaptive):
+        rank, world = self._rank_world()
+        if world > 1:
+            import torch
+            t = torch.tensor([total, -nmax], dtype=torch.int64, device=self._ctx.device)
+            dist = _dist()
+            tot = t[:1].clone()
+            dist.all_reduce(tot)
+            mx = t[1:].clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MIN)
+            total, nmax = int(tot.item()), -int(mx.item())
+        self.last_neval = int(total)
+        # pyx:1682,1699-1702: both ends start at min_neval_hcube
+        hi = max(self.min_neval_hcube, nmax) if adaptive else self.min_neval_hcube
+        self.neval_hcube_range = np.array([self.min_neval_hcube, hi], dtype=np.intp)
+
+    def _make_std_integrand(self, fcn, xsample=None):
+        r""" Convert integrand ``fcn`` into an lbatch integrand (:class:`VegasIntegrand`). """
+        if isinstance(fcn, VegasIntegrand):
+            return fcn
+        return VegasIntegrand(fcn=fcn, map=self.map, uses_jac=self.uses_jac,
+                              xsample=self.xsample if xsample is None else xsample, mpi=False)
+
+    # ------------------------------------------------------------------ the iteration loop (pyx:1912-2230)
+    def __call__(self, fcn, save=None, saveall=None, **kargs):
+        r""" Integrate integrand ``fcn`` (reference docstring at ``_vegas.pyx:1913-2035``).
+
+        ``fcn`` may be: a plain Python function of one point; an ``@lbatchintegrand`` /
+        ``@rbatchintegrand`` (numpy, evaluated on the host from samples generated on the GPU); a
+        ``@devicebatchintegrand`` (torch CUDA tensors in HBM); or a ``DeviceIntegrand`` whose functor
+        is compiled into the library (fused kernel, nothing leaves the SMs).  Returns ``RAvg`` /
+        ``RAvgArray`` / ``RAvgDict``. """
+        if kargs:
+            self.set(kargs)
+        device_fcn = fcn if (isinstance(fcn, DeviceIntegrand) and self.fused and not self.uses_jac) else None
+        std = self._make_std_integrand(fcn)
+        nf = std.size
+        ctx, torch = self._engine()
+        dev = ctx.device
+        rank, world = self._rank_world()
+        if device_fcn is not None:
+            params, keep = device_fcn.params(self.dim)
+            nf_lib = ctx.set_integrand(device_fcn.fid, params, keep=(params, keep))
+            if nf_lib != nf:
+                raise ValueError('device integrand has %d components, its numpy twin %d' % (nf_lib, nf))
+        nv = nf * (nf + 1) // 2
+        result = VegasResult(std, weighted=self.adapt)
+        for itn in range(self.nitn):
+            if self.analyzer is not None:
+                self.analyzer.begin(itn, self)
+            ctx, torch = self._engine()          # map / sigf may have changed
+            hs = int(self.map.inc.shape[1])
+            acc = torch.zeros(nf + nv + 1, dtype=torch.float64, device=dev)
+            sum_f = torch.zeros((self.dim, hs), dtype=torch.float64, device=dev)
+            n_f = torch.zeros((self.dim, hs), dtype=torch.int64, device=dev)
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            total, nmax, adaptive = self._plan(ctx)
+            flags = self._flags(nf)
+            pitn = self._next_itn()
+            if device_fcn is not None:
+                ctx.iterate_fused(pitn, self.beta, flags, self._sigf_dev, acc, sum_f, n_f, hs, status)
+                self._launches += 2
+            else:
+                self._iterate_unfused(ctx, torch, std, pitn, flags, acc, sum_f, n_f, hs, status)
+            if world > 1:
+                dist = _dist()
+                dist.all_reduce(acc)
+                dist.all_reduce(sum_f)
+                dist.all_reduce(n_f)
+                dist.all_reduce(status, op=dist.ReduceOp.MAX)
+            self._set_neval_stats(total, nmax, adaptive)
+            if int(status.item()) != 0:
+                raise ValueError('integrand evaluates to nan')
+            acc_h = acc.cpu().numpy()
+            mean = acc_h[:nf].copy()
+            if self.correlate_integrals:
+                var = np.zeros((nf, nf), float)
+                var[np.tril_indices(nf)] = acc_h[nf:nf + nv]
+                var = var + np.tril(var, -1).T
+            else:
+                var = acc_h[nf:nf + nv][[s * (s + 1) // 2 + s for s in range(nf)]].copy()
+            sum_sigf = float(acc_h[nf + nv])
+            if self._trace is not None:
+                self._trace(dict(itn=pitn, mean=mean, var=var, sum_sigf=sum_sigf, last_neval=self.last_neval,
+                                 sum_f=sum_f.cpu().numpy(), n_f=n_f.cpu().numpy(), flags=flags))
+            result.update(mean, var, self.last_neval)
+
+            if self.beta > 0 and not self.adapt_to_errors and self.adapt:
+                if sum_sigf > 0:
+                    self.sum_sigf = sum_sigf
+                else:
+                    # integrand appears to be a constant => even distribution of points
+                    if self._sigf_dev is not None:
+                        self._sigf_dev.fill_(1.)
+                    self.sum_sigf = self._sigf_len
+            if flags & (_lib.TRAIN | _lib.TRAIN_ERRORS):
+                self.map._accumulate_training(sum_f.cpu().numpy(), n_f.cpu().numpy())
+            if self.alpha > 0 and self.adapt:
+                self.map.adapt(alpha=self.alpha)
+            if self.analyzer is not None:
+                result.update_analyzer(self.analyzer)
+            if save is not None:
+                result.save(save)
+            if saveall is not None:
+                result.saveall(self, saveall)
+            if result.converged(self.rtol, self.atol):
+                break
+        return result.result
+
+    def _iterate_unfused(self, ctx, torch, std, pitn, flags, acc, sum_f, n_f, hs, status):
+        """sample -> user batch integrand -> reduce, batch by batch (pyx:2096-2197)"""
+        nf = std.size
+        on_device = std.on_device
+        target = self.max_batch if on_device else self.min_neval_batch
+        for c0, c1, rows in self._batches(ctx, target):
+            x = torch.empty((rows, self.dim), dtype=torch.float64, device=ctx.device)
+            wgt = torch.empty(rows, dtype=torch.float64, device=ctx.device)
+            jac1d = torch.empty_like(x) if self.uses_jac else None
+            ctx.sample(pitn, c0, c1, x, wgt, jac1d=jac1d)
+            if on_device:
+                fx = std.eval(x, jac=jac1d)
+            else:
+                xh = x.cpu().numpy()
+                jh = jac1d.cpu().numpy() if self.uses_jac else None
+                fh = np.ascontiguousarray(np.asarray(std.eval(xh, jac=jh), dtype=float).reshape(rows, nf))
+                fx = torch.from_numpy(fh).to(ctx.device)
+            if fx.shape != (rows, nf):
+                raise ValueError('integrand returned shape %s for %d points, expected %s'
+                                 % (tuple(fx.shape), rows, (rows, nf)))
+            ctx.reduce(pitn, self.beta, flags, c0, c1, fx, nf, wgt, self._sigf_dev, acc, sum_f, n_f, hs, status)
+            self._launches += 3
+
+    @property
+    def gpu_launches(self):
+        """kernels launched by this integrator's context so far"""
+        return self._ctx.launch_count() if self._ctx is not None else 0
+
+
+def _local_cubes(nhcube, slab, rank, world):
+    """global hypercube indices owned by ``rank`` in local order (host mirror of the device's
+    block-cyclic ``local_to_global``)"""
+    nslab = -(-nhcube // slab)
+    idx = [np.arange(s * slab, min((s + 1) * slab, nhcube)) for s in range(rank, nslab, world)]
+    return np.concatenate(idx) if idx else np.zeros(0, np.int64)

@@ -850,3 +850,77 @@ extern "C" int vb200_fp64_peak(int device, int iters, double* tflops_out, double
     cudaFree(out);
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// AdaptiveMap.adapt (pyx:467-594): the once-per-iteration host step, O(dim * ninc).
+// Smooth the per-increment training averages, damp with alpha, then move the nodes so every new
+// increment holds an equal share.  `work` (one row, carried from axis to axis exactly like the
+// reference's avg_f array) starts at 1.  Nodes the walk never reaches are NaN.
+// ---------------------------------------------------------------------------------------------
+namespace {
+const double kTiny = 1e-257;     // 10**(min_10_exp + 50), pyx:34
+
+void smooth_and_damp(std::vector<double>& w, std::vector<double>& tmp, int64_t n, double alpha)
+{
+    tmp[0] = fabs(7. * w[0] + w[1]) / 8.;
+    tmp[n - 1] = fabs(7. * w[n - 1] + w[n - 2]) / 8.;
+    double total = tmp[0] + tmp[n - 1];
+    for (int64_t i = 1; i < n - 1; ++i) {
+        tmp[i] = fabs(6. * w[i] + w[i - 1] + w[i + 1]) / 8.;
+        total += tmp[i];
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        double a = total > 0 ? tmp[i] / total + kTiny : kTiny;
+        if (a > 0 && a <= 0.99999999) a = pow(-(1 - a) / log(a), alpha);
+        w[i] = a;
+    }
+}
+
+void regrid_axis(const double* g, int64_t n_old, const std::vector<double>& w, int64_t n_new, double* out)
+{
+    for (int64_t i = 0; i <= n_new; ++i) out[i] = NAN;
+    out[0] = g[0];
+    out[n_new] = g[n_old];
+    double share = 0.;
+    for (int64_t i = 0; i < n_old; ++i) share += w[i];
+    share /= (double)n_new;
+    int64_t j = -1;
+    double acc = 0.;
+    for (int64_t i = 1; i < n_new; ++i) {
+        while (acc < share) {
+            if (++j >= n_old) return;              // ran out of old increments
+            acc += w[j];
+        }
+        acc -= share;
+        out[i] = g[j + 1] - (acc / w[j]) * (g[j + 1] - g[j]);
+    }
+}
+}  // namespace
+
+extern "C" int vb200_map_adapt(const double* grid_host, const int64_t* ninc, int dim, int64_t gstride,
+                               const double* sum_f_host, const double* n_f_host, int64_t hstride, double alpha,
+                               const int64_t* new_ninc, double* new_grid_host, int64_t ngstride)
+{
+    if (!grid_host || !ninc || !new_ninc || !new_grid_host) return fail(-1, "vb200_map_adapt: null argument");
+    int64_t widest = 1;
+    for (int d = 0; d < dim; ++d) {
+        if (ninc[d] < 1 || new_ninc[d] < 1 || ninc[d] + 1 > gstride || new_ninc[d] + 1 > ngstride)
+            return fail(-1, "vb200_map_adapt: bad ninc on axis %d", d);
+        if (ninc[d] > widest) widest = ninc[d];
+    }
+    const bool have = sum_f_host && n_f_host;
+    std::vector<double> w((size_t)widest, 1.0), tmp((size_t)widest);
+    for (int d = 0; d < dim; ++d) {
+        const int64_t n_old = ninc[d];
+        if (alpha != 0 && n_old > 1) {
+            if (have)
+                for (int64_t i = 0; i < n_old; ++i) {
+                    double cnt = n_f_host[d * hstride + i];
+                    w[i] = cnt > 0 ? sum_f_host[d * hstride + i] / cnt : 0.;
+                }
+            if (alpha > 0) smooth_and_damp(w, tmp, n_old, alpha);
+        }
+        regrid_axis(grid_host + d * gstride, n_old, w, new_ninc[d], new_grid_host + d * ngstride);
+    }
+    return 0;
+}
