@@ -194,7 +194,7 @@ def test_random_batch_matches_oracle():
     xo, jo = v.map.map(yo)
     O.lib().vo_weights(O._dp(jo), O._ip(nh), len(nh), 1. / v.nhcube)
     assert np.array_equal(hc, hco) and np.array_equal(y, yo)
-    np.testing.assert_allclose(x, xo, rtol=1e-15)
+    assert np.array_equal(x, xo)                 # same ops in the same order, no FMA contraction
     np.testing.assert_allclose(w, jo, rtol=1e-15)
     assert abs(w.sum() - 40.0) < 1e-9            # sum of weights = volume
 

@@ -81,6 +81,7 @@ class Integrator(object):
         self._itn_counter = 0
         self._launches = 0
         self._trace = None      # test hook: called with the raw per-iteration sums before adapt
+        self._timing = None     # bench hook: list receiving per-iteration CUDA-event pairs
         for k, v in self.engine_defaults.items():
             setattr(self, k, v)
         for k in list(kargs):
@@ -672,20 +673,30 @@ class Integrator(object):
             sum_f = torch.zeros((self.dim, hs), dtype=torch.float64, device=dev)
             n_f = torch.zeros((self.dim, hs), dtype=torch.int64, device=dev)
             status = torch.zeros(1, dtype=torch.int32, device=dev)
+            if self._timing is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record()
             total, nmax, adaptive = self._plan(ctx)
             flags = self._flags(nf)
             pitn = self._next_itn()
+            if self._timing is not None:
+                ev[1].record()
             if device_fcn is not None:
                 ctx.iterate_fused(pitn, self.beta, flags, self._sigf_dev, acc, sum_f, n_f, hs, status)
                 self._launches += 2
             else:
                 self._iterate_unfused(ctx, torch, std, pitn, flags, acc, sum_f, n_f, hs, status)
+            if self._timing is not None:
+                ev[2].record()
             if world > 1:
                 dist = _dist()
                 dist.all_reduce(acc)
                 dist.all_reduce(sum_f)
                 dist.all_reduce(n_f)
                 dist.all_reduce(status, op=dist.ReduceOp.MAX)
+            if self._timing is not None:
+                ev[3].record()
+                self._timing.append((ev, total))
             self._set_neval_stats(total, nmax, adaptive)
             if int(status.item()) != 0:
                 raise ValueError('integrand evaluates to nan')

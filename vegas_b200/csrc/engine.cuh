@@ -113,7 +113,7 @@ struct FusedSrc {
                         if (iy < ni) {
                             double g0 = __ldg(g + iy), g1 = __ldg(g + iy + 1);
                             double inc = g1 - g0;
-                            x[d] = g0 + inc * (t - (double)iy);
+                            x[d] = __dadd_rn(g0, __dmul_rn(inc, __dsub_rn(t, (double)iy)));   // no FMA: bit-identical to pyx:354
                             jac *= inc * (double)ni;
                         } else {
                             double g0 = __ldg(g + ni - 1), g1 = __ldg(g + ni);

@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(VB_NT) k_sample(const EngineP p, const SampleO
                     if (iy < ni) {
                         double g0 = __ldg(g + iy), g1 = __ldg(g + iy + 1);
                         double inc = g1 - g0;
-                        xv = g0 + inc * (t - (double)iy);
+                        xv = __dadd_rn(g0, __dmul_rn(inc, __dsub_rn(t, (double)iy)));   // no FMA: bit-identical to pyx:354
                         j1 = inc * (double)ni;
                     } else {
                         double g0 = __ldg(g + ni - 1), g1 = __ldg(g + ni);
