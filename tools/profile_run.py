@@ -1,0 +1,50 @@
+"""small driver for ncu captures: a few vegas+ iterations of one workload
+   python tools/profile_run.py [ridge1000|ridge1|gauss|pathint_unfused] [neval]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import vegas_b200 as vegas
+
+what = sys.argv[1] if len(sys.argv) > 1 else 'ridge1000'
+neval = float(sys.argv[2]) if len(sys.argv) > 2 else 1e7
+F = vegas.integrands
+if what.startswith('ridge'):
+    n = int(what[5:])
+    f = F.Ridge(8, N=n, lo=0.5 if n == 1 else 0.4, hi=0.5 if n == 1 else 0.6)
+    integ = vegas.Integrator(8 * [[0., 1.]], neval=neval, seed=3)
+    integ(f, nitn=4)
+elif what == 'gauss':
+    f = F.GaussMix([4 * [0.5]], 100., 1013.2118364296088)
+    integ = vegas.Integrator([[-1., 1.]] + 3 * [[0., 1.]], neval=neval, seed=3)
+    integ(f, nitn=4)
+elif what == 'pathint_unfused':
+    f = F.PathIntegral(T=4., ndT=10, x0list=np.linspace(0, 2., 6))
+    ft = None
+
+    @vegas.devicebatchintegrand
+    def fdev(theta):
+        x = torch.tan(theta)
+        Vx = 0.5 * x * x
+        a, m_2a = 0.4, 1.25
+        jf = 1.0 + x * x
+        jac = f.norm * jf.prod(dim=1)
+        jac0 = f.norm_x0 * jf[:, 1:].prod(dim=1)
+        Smid = a * Vx[:, -1] + (m_2a * (x[:, 2:] - x[:, 1:-1]) ** 2 + a * Vx[:, 1:-1]).sum(dim=1)
+        out = torch.empty((x.shape[0], 7), dtype=torch.float64, device=x.device)
+        for i in range(7):
+            e = x[:, 0] if i == 0 else torch.full_like(x[:, 0], float(f.x0list[i - 1]))
+            Ve = 0.5 * e * e
+            S = Smid + m_2a * ((x[:, 1] - e) ** 2 + (e - x[:, -1]) ** 2) + a * Ve
+            out[:, i] = (jac if i == 0 else jac0) * torch.exp(-S)
+        return out
+    integ = vegas.Integrator(f.region, neval=neval, seed=3, alpha=0.1)
+    integ(fdev, nitn=3)
+    f = fdev
+torch.cuda.synchronize()
+r = integ(f, nitn=2)
+torch.cuda.synchronize()
+print(what, neval, r if not hasattr(r, 'keys') else r['exp(-E0*T)'], 'launches', integ.gpu_launches)

@@ -252,7 +252,7 @@ __device__ __forceinline__ void cube_epilogue(const EngineP& p, CubeAcc<NF>& A, 
 // the engine kernel
 // ---------------------------------------------------------------------------------------------
 template <class Src>
-__global__ void __launch_bounds__(VB_NT) k_engine(const EngineP p, const Src src)
+__global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ EngineP p, const __grid_constant__ Src src)
 {
     constexpr int NF = Src::NF;
     constexpr int NV = NF * (NF + 1) / 2;

@@ -542,7 +542,7 @@ struct SampleOut {
     double* u;         // raw uniforms (testing)
 };
 
-__global__ void __launch_bounds__(VB_NT) k_sample(const EngineP p, const SampleOut o)
+__global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ EngineP p, const __grid_constant__ SampleOut o)
 {
     __shared__ long long ex_s[VB_CH + 1];
     __shared__ int n_s[VB_CH];
