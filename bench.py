@@ -240,8 +240,8 @@ def variants(vegas, _lib, fp64_peak):
     (N=1) -- the integrand is then ~100 flops and the sampler itself is what is timed"""
     import torch
     out = {}
-    for n in (1, 30):
-        f = vegas.integrands.Ridge(DIM, N=n, lo=0.5 if n == 1 else 0.4, hi=0.5 if n == 1 else 0.6)
+    for n, shifted in ((1, False), (30, False), (RIDGE_N, True)):
+        f = vegas.integrands.Ridge(DIM, N=n, lo=0.5 if n == 1 else 0.4, hi=0.5 if n == 1 else 0.6, shifted=shifted)
         integ = vegas.Integrator(DIM * [[0., 1.]], neval=NEVAL_PER_GPU, seed=77)
         integ(f, nitn=5)
         integ._timing = []
@@ -250,7 +250,7 @@ def variants(vegas, _lib, fp64_peak):
         ms = float(np.sum([ev[0].elapsed_time(ev[3]) for ev, _ in integ._timing]))
         kms = float(np.sum([ev[1].elapsed_time(ev[2]) for ev, _ in integ._timing]))
         fl = (9 * DIM + 10) + f.flops_per_sample(C_EXP)
-        out['ridge_N%d' % n] = dict(value=float(r.sum_neval) / (ms * 1e-3), unit='samples/s',
+        out['ridge_N%d%s' % (n, '_shifted' if shifted else '')] = dict(value=float(r.sum_neval) / (ms * 1e-3), unit='samples/s',
                                     roofline_frac=float(r.sum_neval) * fl / (kms * 1e-3) / 1e12 / fp64_peak,
                                     flops_per_sample=fl, result=str(r))
     return out

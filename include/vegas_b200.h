@@ -49,7 +49,7 @@ typedef struct vb200_ctx vb200_ctx;
 /* parameter blocks for vb200_set_integrand (host memory, copied) */
 typedef struct { double c0; double c[VB200_MAXDIM]; int32_t p[VB200_MAXDIM]; } vb200_poly_t;
 typedef struct { int32_t npeak; int32_t pad; double a, norm; const double* centers_host; /* [npeak][dim] */ } vb200_gaussmix_t;
-typedef struct { int32_t n; int32_t pad; double a, norm; const double* x0_host; /* [n] */ } vb200_ridge_t;
+typedef struct { int32_t n; int32_t mode; /* 0: axis-order sum as in ridge.py; 1: shifted-mean identity */ double a, norm; const double* x0_host; /* [n] */ } vb200_ridge_t;
 typedef struct { double a[VB200_MAXDIM]; double u[VB200_MAXDIM]; } vb200_genz_t;
 typedef struct { double T, m, xscale, c2, c4; int32_t nx0; int32_t pad; double x0list[7]; } vb200_pathint_t;
 

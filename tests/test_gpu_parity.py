@@ -130,6 +130,8 @@ def _cases():
         'poly2': (2 * [[0., 2.]], F.Poly(0.5, [1.0, 2.0], [2, 3]), dict(neval=4000)),
         'gauss4': ([[-1., 1.]] + 3 * [[0., 1.]], F.GaussMix([4 * [0.5]], 100., 1013.2118364296088), dict(neval=10000)),
         'ridge8': (8 * [[0., 1.]], F.Ridge(8, N=17), dict(neval=60000)),
+        'ridge8_shifted': (8 * [[0., 1.]], F.Ridge(8, N=21, shifted=True), dict(neval=60000)),
+        'ridge6_pad': (6 * [[0., 1.]], F.Ridge(6, N=9), dict(neval=20000)),
         'ridge4_nomap': (4 * [[0., 1.]], F.Ridge(4, N=5), dict(neval=5000, alpha=0.0)),
         'genz10_pp': (10 * [[0., 1.]], F.Genz('product_peak', 2 + 3 * rng.random(10), rng.random(10)), dict(neval=50000)),
         'genz10_osc': (10 * [[0., 1.]], F.Genz('oscillatory', rng.random(10), rng.random(10)), dict(neval=50000, beta=0.0)),
@@ -143,7 +145,7 @@ def _cases():
     }
 
 
-CASES = ['poly2', 'gauss4', 'ridge8', 'ridge4_nomap', 'genz10_pp', 'genz10_osc', 'genz3_corner', 'peaks20',
+CASES = ['poly2', 'gauss4', 'ridge8', 'ridge8_shifted', 'ridge6_pad', 'ridge4_nomap', 'genz10_pp', 'genz10_osc', 'genz3_corner', 'peaks20',
          'pathint10', 'pathint8_nocorr']
 
 

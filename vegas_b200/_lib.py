@@ -35,7 +35,7 @@ class GaussMixParams(ctypes.Structure):
 
 
 class RidgeParams(ctypes.Structure):
-    _fields_ = [('n', ctypes.c_int32), ('pad', ctypes.c_int32), ('a', ctypes.c_double),
+    _fields_ = [('n', ctypes.c_int32), ('mode', ctypes.c_int32), ('a', ctypes.c_double),
                 ('norm', ctypes.c_double), ('x0_host', ctypes.c_void_p)]
 
 

@@ -70,6 +70,56 @@ __device__ __forceinline__ double div_exact(double a, double b, double rb)
     return __fma_rn(e, rb, q);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// exp() for W independent arguments evaluated in lock-step, so that the W Horner chains interleave
+// in the FP64 pipe (a single exp is ~15 dependent DFMAs).  Cody-Waite reduction x = k ln2 + r,
+// |r| <= ln2/2, then a degree-11 near-minimax polynomial (Chebyshev fit, max rel. error 4.2e-18
+// before rounding; coefficients derived with mpmath, see tools/exp_coeffs.py), scaled by 2^k
+// through the exponent field.  |x| >= 708 (overflow / underflow / denormal results, inf, NaN)
+// takes the library exp(), so results there are unchanged.
+// ---------------------------------------------------------------------------------------------
+__constant__ double vb_exp_c[12] = {
+    2.51100492048186583e-08, 2.76326547225277896e-07, 2.75572408872298695e-06, 2.48014854415613131e-05,
+    1.98412698900764028e-04, 1.38888889523528631e-03, 8.33333333331958900e-03, 4.16666666664879531e-02,
+    1.66666666666666796e-01, 5.00000000000001887e-01, 1.0, 1.0};
+
+template <int W>
+__device__ __forceinline__ void vb_exp_n(const double (&x)[W], double (&e)[W])
+{
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: rounds to nearest integer
+    double t[W], r[W], p[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) t[j] = __fma_rn(x[j], 1.44269504088896339e+00, MAGIC);
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        double kf = t[j] - MAGIC;
+        r[j] = __fma_rn(kf, -6.93147180559945286e-01, x[j]);
+        r[j] = __fma_rn(kf, -2.31904681384629956e-17, r[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) p[j] = __fma_rn(vb_exp_c[0], r[j], vb_exp_c[1]);
+#pragma unroll
+    for (int i = 2; i < 12; ++i) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) p[j] = __fma_rn(p[j], r[j], vb_exp_c[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        int k = __double2loint(t[j]);
+        double v = __hiloint2double(__double2hiint(p[j]) + (k << 20), __double2loint(p[j]));
+        if ((__double2hiint(x[j]) & 0x7fffffff) >= 0x40862000) v = exp(x[j]);     // |x| >= 708: rare
+        e[j] = v;
+    }
+}
+
+__device__ __forceinline__ double vb_exp(double x)
+{
+    double a[1] = {x}, e[1];
+    vb_exp_n<1>(a, e);
+    return e[0];
+}
+
 // ---------------------------------------------------------------------------------------------
 // parameter blocks
 // ---------------------------------------------------------------------------------------------

@@ -57,44 +57,103 @@ struct FGaussMix {
 #pragma unroll
             for (int d = 0; d < D; ++d)
                 if (d < dim) { double t = x[d] - __ldg(c + d); dx2 += t * t; }
-            s += exp(-a * dx2);
+            s += vb_exp(-a * dx2);
         }
         f[0] = s * norm;
     }
 };
 
 // f = norm * mean_k exp(-a * sum_d (x_d - x0_k)^2)     (examples/ridge.py:18-24)
-// Same arithmetic as the numpy original: per term the D squared distances are summed in axis
-// order, then exp(-a*dx2); the N terms are averaged, then scaled.
+// mode 0: the numpy original's arithmetic -- per term the D squared distances are summed in axis
+//         order, then exp(-a*dx2); the N terms are averaged, then scaled.
+// mode 1: the same value through the exact identity sum_d (x_d-c)^2 = V + D (xbar-c)^2 with
+//         xbar = mean_d x_d, V = sum_d (x_d-xbar)^2 (a sum of non-negative terms: no cancellation);
+//         the argument is -(a V) - (sqrt(aD)(xbar-c))^2, two FP64 instructions per term instead of
+//         2D+1.  xs[k] = sqrt(a D) x0[k] is precomputed on the host.
+// W terms are evaluated in lock-step so their exp() chains interleave in the FP64 pipe.
+#define VB_RIDGE_W 4
 struct FRidge {
     static constexpr int NF = 1;
     const double* x0;   // [n] device
-    int n;
+    const double* xs;   // [n] device: sqrt(a*dim) * x0[k]   (mode 1)
+    int n, mode;
     double a, norm;
+
+    template <int D, bool CHECK>
+    __device__ __forceinline__ double sum_axis_order(const double (&x)[D], int dim) const
+    {
+        constexpr int W = VB_RIDGE_W;
+        double s[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) s[j] = 0.0;
+        int k = 0;
+        for (; k + W <= n; k += W) {
+            double c[W], q[W], e[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) { c[j] = __ldg(x0 + k + j); q[j] = 0.0; }
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                if (!CHECK || d < dim) {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) { double t = x[d] - c[j]; q[j] = fma(t, t, q[j]); }
+                }
+#pragma unroll
+            for (int j = 0; j < W; ++j) q[j] *= -a;
+            vb_exp_n<W>(q, e);
+#pragma unroll
+            for (int j = 0; j < W; ++j) s[j] += e[j];
+        }
+        for (; k < n; ++k) {
+            double c = __ldg(x0 + k), q = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                if (!CHECK || d < dim) { double t = x[d] - c; q = fma(t, t, q); }
+            s[0] += vb_exp(-a * q);
+        }
+        double tot = s[0];
+#pragma unroll
+        for (int j = 1; j < W; ++j) tot += s[j];
+        return tot;
+    }
+
+    template <int D>
+    __device__ __forceinline__ double sum_shifted(const double (&x)[D], int dim) const
+    {
+        constexpr int W = VB_RIDGE_W;
+        double xbar = 0.0, V = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) if (d < dim) xbar += x[d];
+        xbar /= (double)dim;
+#pragma unroll
+        for (int d = 0; d < D; ++d) if (d < dim) { double t = x[d] - xbar; V = fma(t, t, V); }
+        const double mV = -a * V, xb = sqrt(a * (double)dim) * xbar;
+        double s[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) s[j] = 0.0;
+        int k = 0;
+        for (; k + W <= n; k += W) {
+            double q[W], e[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) { double t = xb - __ldg(xs + k + j); q[j] = fma(-t, t, mV); }
+            vb_exp_n<W>(q, e);
+#pragma unroll
+            for (int j = 0; j < W; ++j) s[j] += e[j];
+        }
+        for (; k < n; ++k) { double t = xb - __ldg(xs + k); s[0] += vb_exp(fma(-t, t, mV)); }
+        double tot = s[0];
+#pragma unroll
+        for (int j = 1; j < W; ++j) tot += s[j];
+        return tot;
+    }
+
     template <int D>
     __device__ __forceinline__ void operator()(const double (&x)[D], int dim, double (&f)[1]) const
     {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int k = 0;
-        for (; k + 4 <= n; k += 4) {
-            double c0 = __ldg(x0 + k), c1 = __ldg(x0 + k + 1), c2 = __ldg(x0 + k + 2), c3 = __ldg(x0 + k + 3);
-            double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-#pragma unroll
-            for (int d = 0; d < D; ++d)
-                if (d < dim) {
-                    double t0 = x[d] - c0, t1 = x[d] - c1, t2 = x[d] - c2, t3 = x[d] - c3;
-                    q0 += t0 * t0; q1 += t1 * t1; q2 += t2 * t2; q3 += t3 * t3;
-                }
-            s0 += exp(-a * q0); s1 += exp(-a * q1); s2 += exp(-a * q2); s3 += exp(-a * q3);
-        }
-        for (; k < n; ++k) {
-            double c0 = __ldg(x0 + k), q0 = 0.0;
-#pragma unroll
-            for (int d = 0; d < D; ++d)
-                if (d < dim) { double t0 = x[d] - c0; q0 += t0 * t0; }
-            s0 += exp(-a * q0);
-        }
-        f[0] = ((s0 + s1) + (s2 + s3)) / (double)n * norm;
+        double tot;
+        if (mode == 1) tot = sum_shifted<D>(x, dim);
+        else if (dim == D) tot = sum_axis_order<D, false>(x, dim);
+        else tot = sum_axis_order<D, true>(x, dim);
+        f[0] = tot / (double)n * norm;
     }
 };
 

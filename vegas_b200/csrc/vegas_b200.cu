@@ -216,10 +216,13 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         const vb200_ridge_t* q = (const vb200_ridge_t*)params;
         if (q->n < 1 || !q->x0_host) return fail(-1, "ridge: n < 1 or no x0");
         size_t bytes = sizeof(double) * (size_t)q->n;
-        CK(c->fparams.ensure(bytes));
+        CK(c->fparams.ensure(2 * bytes));
+        std::vector<double> xs((size_t)q->n);
+        for (int k = 0; k < q->n; ++k) xs[k] = sqrt(q->a * (double)dim) * q->x0_host[k];
         CK(cudaMemcpy(c->fparams.p, q->x0_host, bytes, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy((char*)c->fparams.p + bytes, xs.data(), bytes, cudaMemcpyHostToDevice));
         FRidge f;
-        f.x0 = (const double*)c->fparams.p; f.n = q->n; f.a = q->a; f.norm = q->norm;
+        f.x0 = (const double*)c->fparams.p; f.xs = f.x0 + q->n; f.n = q->n; f.mode = q->mode; f.a = q->a; f.norm = q->norm;
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
         break;

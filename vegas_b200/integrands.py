@@ -71,8 +71,9 @@ class Ridge(DeviceIntegrand):
     ``f = mean_k exp(-a * sum_d (x_d - x0_k)^2) * (a/pi)^(D/2)``, ``x0 = linspace(lo, hi, N)``."""
     fid = _lib.F_RIDGE
 
-    def __init__(self, dim, N=1000, lo=0.4, hi=0.6, a=100.0):
+    def __init__(self, dim, N=1000, lo=0.4, hi=0.6, a=100.0, shifted=False):
         self.dim, self.N, self.a = int(dim), int(N), float(a)
+        self.shifted = bool(shifted)      # device arithmetic: axis-order sum (False) or the shifted-mean identity
         self.x0 = np.ascontiguousarray(np.linspace(lo, hi, self.N))
         self.norm = (self.a / np.pi) ** (self.dim / 2.)
 
@@ -80,7 +81,7 @@ class Ridge(DeviceIntegrand):
         if dim != self.dim:
             raise ValueError('Ridge: built for %d dimensions, integrator has %d' % (self.dim, dim))
         q = _lib.RidgeParams()
-        q.n, q.a, q.norm = self.N, self.a, self.norm
+        q.n, q.mode, q.a, q.norm = self.N, int(self.shifted), self.a, self.norm
         q.x0_host = self.x0.ctypes.data
         return q, self.x0
 
@@ -96,6 +97,9 @@ class Ridge(DeviceIntegrand):
         return out
 
     def flops_per_sample(self, c_exp):
+        """algorithmic fp64 flops of one evaluation (FMA = 2)"""
+        if self.shifted:
+            return self.N * (3 + 1 + c_exp) + 5 * self.dim + 4
         return self.N * (3 * self.dim + 2 + c_exp)
 
 
