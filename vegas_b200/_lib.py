@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libvegas_b200.so')
+LIB_PATH = os.environ.get('VB200_LIB') or os.path.join(_HERE, 'libvegas_b200.so')   # VB200_LIB: developer override for A/B builds
 
 MAXDIM = 32
 CHUNK = 256

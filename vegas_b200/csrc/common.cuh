@@ -8,7 +8,10 @@
 
 #define VB_MAXD 32          // compile-time bound on dimensions carried in kernel parameters
 #define VB_NT 256           // threads per CTA of the engine kernels
-#define VB_CH 256           // hypercubes per chunk (== VB_NT: one cube per thread in set-up)
+#define VB_CH 256           // hypercubes per chunk
+#ifndef VB_ENT
+#define VB_ENT 128          // threads per CTA of the engine kernel (VB_CH / VB_ENT cubes per thread in set-up)
+#endif
 #define VB_WARP_CUBE 64     // cubes with more samples than this are reduced by a whole warp
 #define VB_EPSILON (2.220446049250313e-16 * 1e4)   // reference EPSILON, _vegas.pyx:36
 
@@ -104,12 +107,17 @@ __device__ __forceinline__ void vb_exp_n(const double (&x)[W], double (&e)[W])
 #pragma unroll
         for (int j = 0; j < W; ++j) p[j] = __fma_rn(p[j], r[j], vb_exp_c[i]);
     }
+    bool rare = false;
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         int k = __double2loint(t[j]);
-        double v = __hiloint2double(__double2hiint(p[j]) + (k << 20), __double2loint(p[j]));
-        if ((__double2hiint(x[j]) & 0x7fffffff) >= 0x40862000) v = exp(x[j]);     // |x| >= 708: rare
-        e[j] = v;
+        e[j] = __hiloint2double(__double2hiint(p[j]) + (k << 20), __double2loint(p[j]));
+        rare |= (__double2hiint(x[j]) & 0x7fffffff) >= 0x40862000;
+    }
+    if (rare) {                                            // some |x| >= 708: one branch for all W
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            if ((__double2hiint(x[j]) & 0x7fffffff) >= 0x40862000) e[j] = exp(x[j]);
     }
 }
 
@@ -174,7 +182,8 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// fixed-tree block sum; result valid in thread 0.  red: >= VB_NT/32 doubles of shared memory.
+// fixed-tree block sum over NT threads; result valid in thread 0.  red: >= NT/32 doubles of smem.
+template <int NT = VB_NT>
 __device__ __forceinline__ double block_sum(double v, double* red)
 {
     v = warp_sum(v);
@@ -184,14 +193,15 @@ __device__ __forceinline__ double block_sum(double v, double* red)
     double t = 0.0;
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int w = 0; w < VB_NT / 32; ++w) t += red[w];
+        for (int w = 0; w < NT / 32; ++w) t += red[w];
     }
     return t;
 }
 
-// block-wide exclusive scan of one int per thread (VB_NT threads); returns exclusive prefix,
-// total through *total.  scratch: VB_NT/32 ints of shared memory.
-__device__ __forceinline__ long long block_exscan(int v, long long* scratch, long long* total)
+// block-wide exclusive scan of one value per thread (NT threads); returns the exclusive prefix,
+// the total through *total.  scratch: NT/32 long longs of shared memory.
+template <int NT = VB_NT>
+__device__ __forceinline__ long long block_exscan(long long v, long long* scratch, long long* total)
 {
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     long long x = v;
@@ -205,7 +215,7 @@ __device__ __forceinline__ long long block_exscan(int v, long long* scratch, lon
     __syncthreads();
     long long base = 0, tot = 0;
 #pragma unroll
-    for (int i = 0; i < VB_NT / 32; ++i) {
+    for (int i = 0; i < NT / 32; ++i) {
         long long s = scratch[i];
         if (i < w) base += s;
         tot += s;

@@ -32,7 +32,7 @@ static int launch_engine(const EngineP& p, const Src& src, LaunchCfg& cfg, int m
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
     if (e != cudaSuccess) return -(int)e - 1000;
     int bps = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, VB_NT, cfg.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, VB_ENT, cfg.smem);
     if (e != cudaSuccess) return -(int)e - 1000;
     if (bps < 1) bps = 1;
     cfg.blocks_per_sm_out = bps;
@@ -40,7 +40,7 @@ static int launch_engine(const EngineP& p, const Src& src, LaunchCfg& cfg, int m
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     if (st == VB_DRYRUN) return grid;
-    kern<<<grid, VB_NT, cfg.smem, st>>>(p, src);
+    kern<<<grid, VB_ENT, cfg.smem, st>>>(p, src);
     e = cudaGetLastError();
     if (e != cudaSuccess) return -(int)e - 1000;
     return grid;

@@ -1,8 +1,8 @@
 // engine.cuh -- the vegas+ iteration engine: one persistent kernel per iteration (or per batch).
 //
 // Work decomposition ("hypercube tiling"):
-//   chunk  = VB_CH consecutive hypercubes of this rank's share; chunks are dealt round-robin to
-//            the persistent CTAs (static => results do not depend on scheduling).
+//   chunk  = VB_CH consecutive hypercubes of this rank's share; the persistent CTAs claim chunks
+//            from an atomic counter, so they all finish together whatever the sample counts.
 //   tile   = maximal run of cubes inside a chunk whose samples fit the shared-memory staging
 //            buffer (cap samples).  Cubes larger than cap are staged through global scratch.
 //   phase 1 (thread per SAMPLE): Philox -> stratified y -> AdaptiveMap -> integrand -> w*f staged
@@ -40,6 +40,7 @@ struct EngineP {
     double* scratch;           // [gridDim.x][NF][scratch_stride]
     int64_t scratch_stride;
     int64_t chunk_begin, chunk_end;   // local chunk range of this launch
+    unsigned long long* work_counter; // zeroed before the launch: next chunk to claim
     int64_t cstride[VB_MAXD];  // cstride[d] = prod_{e<d} nstrat[e]
     // unfused path
     const double* fbuf;        // [rows][nf]
@@ -252,11 +253,14 @@ __device__ __forceinline__ void cube_epilogue(const EngineP& p, CubeAcc<NF>& A, 
 // the engine kernel
 // ---------------------------------------------------------------------------------------------
 template <class Src>
-__global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ EngineP p, const __grid_constant__ Src src)
+__global__ void __launch_bounds__(VB_ENT) k_engine(const __grid_constant__ EngineP p, const __grid_constant__ Src src)
 {
     constexpr int NF = Src::NF;
     constexpr int NV = NF * (NF + 1) / 2;
-    constexpr int NW = VB_NT / 32;
+    constexpr int NT = VB_ENT;
+    constexpr int NW = NT / 32;
+    constexpr int CPT = VB_CH / NT;                               // cubes per thread in set-up
+    static_assert(VB_CH % NT == 0, "chunk must be a multiple of the CTA size");
     extern __shared__ double smem[];
     double* wf_s = smem;                                          // [NF][cap]
     long long* ex_s = (long long*)(wf_s + (size_t)NF * p.cap);    // [VB_CH + 1]
@@ -266,6 +270,7 @@ __global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ Engine
     __shared__ double red_s[NW];
     __shared__ double bc_s[NF];
     __shared__ uint32_t base_s[VB_MAXD];
+    __shared__ long long next_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dim = p.map.dim;
@@ -273,27 +278,42 @@ __global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ Engine
     CubeAcc<NF> A;
     A.clear();
 
-    for (int64_t lc = p.chunk_begin + blockIdx.x; lc < p.chunk_end; lc += gridDim.x) {
+    // chunks are claimed dynamically (one atomic per chunk) so that CTAs finish together
+    for (;;) {
+        __syncthreads();                       // previous chunk fully consumed
+        if (tid == 0) next_s = p.chunk_begin + (long long)atomicAdd(p.work_counter, 1ull);
+        __syncthreads();
+        const int64_t lc = next_s;
+        if (lc >= p.chunk_end) break;
         const int64_t lh0 = lc * VB_CH;
         const int64_t h0 = local_to_global(p.st, lh0);
-        const bool valid = lh0 + tid < p.st.nlocal;
-        const int n_mine = valid ? alloc_neval(p.al, lh0 + tid) : 0;
-        __syncthreads();                       // previous chunk fully consumed
         if (tid < dim) base_s[tid] = (uint32_t)((h0 / p.cstride[tid]) % p.st.nstrat[tid]);
+        int n_mine[CPT];
+        long long mine = 0;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int c = tid * CPT + i;
+            n_mine[i] = (lh0 + c < p.st.nlocal) ? alloc_neval(p.al, lh0 + c) : 0;
+            mine += n_mine[i];
+        }
         long long total;
-        long long ex = block_exscan(n_mine, scan_s, &total);     // contains __syncthreads
-        ex_s[tid] = ex;
-        n_s[tid] = n_mine;
-        if (tid == VB_NT - 1) ex_s[VB_CH] = total;
-        {   // mixed-radix digits of cube h0+tid: base digits plus tid, with carries
-            uint32_t carry = (uint32_t)tid;
+        long long ex = block_exscan<NT>(mine, scan_s, &total);     // contains __syncthreads
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int c = tid * CPT + i;
+            ex_s[c] = ex;
+            n_s[c] = n_mine[i];
+            ex += n_mine[i];
+            // mixed-radix digits of cube h0+c: base digits plus c, with carries
+            uint32_t carry = (uint32_t)c;
             for (int d = 0; d < dim; ++d) {
                 uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
                 uint32_t qd = v / ns;
-                y0_s[tid * dim + d] = v - qd * ns;
+                y0_s[c * dim + d] = v - qd * ns;
                 carry = qd;
             }
         }
+        if (tid == NT - 1) ex_s[VB_CH] = total;
         __syncthreads();
         const int64_t chunk_row = p.chunk_off ? p.chunk_off[lc] - p.row0 : 0;
 
@@ -301,8 +321,18 @@ __global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ Engine
         while (c0 < VB_CH) {
             const long long base = ex_s[c0];
             if (base >= total) break;                              // only empty cubes remain
-            const int cnt = __syncthreads_count(tid >= c0 && ex_s[tid + 1] - base <= (long long)p.cap);
-            if (cnt == 0) {
+            // c1 = one past the last cube whose samples still fit the staging buffer (all threads
+            // search the same shared array: broadcast reads, no barrier)
+            int c1;
+            {
+                int lo = c0, hi = VB_CH + 1;                       // ex_s[lo]-base <= cap < ex_s[hi]-base (virtual)
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (ex_s[mid] - base <= (long long)p.cap) lo = mid; else hi = mid;
+                }
+                c1 = lo;
+            }
+            if (c1 == c0) {
                 // ---- giant cube c0: staged through global scratch, reduced by the whole CTA
                 const int n = n_s[c0];
                 const int64_t h = h0 + c0;
@@ -310,7 +340,7 @@ __global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ Engine
                 double S[NF];
 #pragma unroll
                 for (int s = 0; s < NF; ++s) S[s] = 0.0;
-                for (int k = tid; k < n; k += VB_NT) {
+                for (int k = tid; k < n; k += NT) {
                     double w[NF];
                     src.sample(p, n, h, (uint32_t)k, chunk_row + base + k, y0_s + c0 * dim, w);
 #pragma unroll
@@ -319,7 +349,7 @@ __global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ Engine
                 double m[NF];
 #pragma unroll
                 for (int s = 0; s < NF; ++s) {
-                    double t = block_sum(S[s], red_s);
+                    double t = block_sum<NT>(S[s], red_s);
                     if (tid == 0) bc_s[s] = t;
                 }
                 __syncthreads();
@@ -330,16 +360,16 @@ __global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ Engine
                 for (int s = 0; s < NF; ++s) sd[s] = 0.0;
 #pragma unroll
                 for (int v = 0; v < NV; ++v) q[v] = 0.0;
-                for (int k = tid; k < n; k += VB_NT) {
+                for (int k = tid; k < n; k += NT) {
                     double w[NF];
 #pragma unroll
                     for (int s = 0; s < NF; ++s) w[s] = gs[s * p.scratch_stride + k];
                     pass2_sample<NF>(w, m, correlate, sd, q);
                 }
 #pragma unroll
-                for (int s = 0; s < NF; ++s) sd[s] = block_sum(sd[s], red_s);
+                for (int s = 0; s < NF; ++s) sd[s] = block_sum<NT>(sd[s], red_s);
 #pragma unroll
-                for (int v = 0; v < NV; ++v) q[v] = block_sum(q[v], red_s);
+                for (int v = 0; v < NV; ++v) q[v] = block_sum<NT>(q[v], red_s);
                 if (tid == 0) {
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
                     cube_epilogue<NF>(p, A, sigf2, lh0 + c0, h, n, y0_s + c0 * dim);
@@ -348,11 +378,10 @@ __global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ Engine
                 c0 += 1;
                 continue;
             }
-            const int c1 = c0 + cnt;
             const int Tt = (int)(ex_s[c1] - base);
 
             // ---- phase 1: one thread per sample
-            for (int i = tid; i < Tt; i += VB_NT) {
+            for (int i = tid; i < Tt; i += NT) {
                 int lo = c0, hi = c1;
                 while (hi - lo > 1) {
                     int mid = (lo + hi) >> 1;
@@ -368,9 +397,8 @@ __global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ Engine
             __syncthreads();
 
             // ---- phase 2a: one thread per small cube, serial in the reference's order
-            {
-                const int c = c0 + tid;
-                const int n = (c < c1) ? n_s[c] : 0;
+            for (int c = c0 + tid; c < c1; c += NT) {
+                const int n = n_s[c];
                 if (n > 0 && n <= VB_WARP_CUBE) {
                     const int o = (int)(ex_s[c] - base);
                     double S[NF], m[NF], sd[NF], q[NV];
@@ -428,13 +456,12 @@ __global__ void __launch_bounds__(VB_NT) k_engine(const __grid_constant__ Engine
         }
     }
 
-    // ---- per-CTA partial sums (fixed tree), finished by k_finalize in CTA order
+    // ---- per-CTA partial sums (fixed tree inside the CTA), finished by k_finalize in CTA order
     constexpr int NACC = NF + NV + 1;
     double* out = p.partials + (size_t)blockIdx.x * NACC;
 #pragma unroll
-    for (int s = 0; s < NF; ++s) { double t = block_sum(A.mean[s], red_s); if (tid == 0) out[s] = t; }
+    for (int s = 0; s < NF; ++s) { double t = block_sum<NT>(A.mean[s], red_s); if (tid == 0) out[s] = t; }
 #pragma unroll
-    for (int v = 0; v < NV; ++v) { double t = block_sum(A.var[v], red_s); if (tid == 0) out[NF + v] = t; }
-    { double t = block_sum(A.sum_sigf, red_s); if (tid == 0) out[NF + NV] = t; }
+    for (int v = 0; v < NV; ++v) { double t = block_sum<NT>(A.var[v], red_s); if (tid == 0) out[NF + v] = t; }
+    { double t = block_sum<NT>(A.sum_sigf, red_s); if (tid == 0) out[NF + NV] = t; }
 }
-

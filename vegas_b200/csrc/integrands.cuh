@@ -71,7 +71,9 @@ struct FGaussMix {
 //         the argument is -(a V) - (sqrt(aD)(xbar-c))^2, two FP64 instructions per term instead of
 //         2D+1.  xs[k] = sqrt(a D) x0[k] is precomputed on the host.
 // W terms are evaluated in lock-step so their exp() chains interleave in the FP64 pipe.
-#define VB_RIDGE_W 4
+#ifndef VB_RIDGE_W
+#define VB_RIDGE_W 8
+#endif
 struct FRidge {
     static constexpr int NF = 1;
     const double* x0;   // [n] device
@@ -83,37 +85,41 @@ struct FRidge {
     __device__ __forceinline__ double sum_axis_order(const double (&x)[D], int dim) const
     {
         constexpr int W = VB_RIDGE_W;
-        double s[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j) s[j] = 0.0;
+        double s0 = 0.0, s1 = 0.0;
         int k = 0;
-        for (; k + W <= n; k += W) {
-            double c[W], q[W], e[W];
+        if (n >= W) {
+            double cn[W];                                   // centres of the NEXT group (prefetch)
 #pragma unroll
-            for (int j = 0; j < W; ++j) { c[j] = __ldg(x0 + k + j); q[j] = 0.0; }
+            for (int j = 0; j < W; ++j) cn[j] = __ldg(x0 + j);
+            for (; k + W <= n; k += W) {
+                double c[W], q[W], e[W];
 #pragma unroll
-            for (int d = 0; d < D; ++d)
-                if (!CHECK || d < dim) {
+                for (int j = 0; j < W; ++j) { c[j] = cn[j]; q[j] = 0.0; }
+                if (k + 2 * W <= n) {
 #pragma unroll
-                    for (int j = 0; j < W; ++j) { double t = x[d] - c[j]; q[j] = fma(t, t, q[j]); }
+                    for (int j = 0; j < W; ++j) cn[j] = __ldg(x0 + k + W + j);
                 }
 #pragma unroll
-            for (int j = 0; j < W; ++j) q[j] *= -a;
-            vb_exp_n<W>(q, e);
+                for (int d = 0; d < D; ++d)
+                    if (!CHECK || d < dim) {
 #pragma unroll
-            for (int j = 0; j < W; ++j) s[j] += e[j];
+                        for (int j = 0; j < W; ++j) { double t = x[d] - c[j]; q[j] = fma(t, t, q[j]); }
+                    }
+#pragma unroll
+                for (int j = 0; j < W; ++j) q[j] *= -a;
+                vb_exp_n<W>(q, e);
+#pragma unroll
+                for (int j = 0; j < W; j += 2) { s0 += e[j]; s1 += e[j + 1]; }
+            }
         }
         for (; k < n; ++k) {
             double c = __ldg(x0 + k), q = 0.0;
 #pragma unroll
             for (int d = 0; d < D; ++d)
                 if (!CHECK || d < dim) { double t = x[d] - c; q = fma(t, t, q); }
-            s[0] += vb_exp(-a * q);
+            s0 += vb_exp(-a * q);
         }
-        double tot = s[0];
-#pragma unroll
-        for (int j = 1; j < W; ++j) tot += s[j];
-        return tot;
+        return s0 + s1;
     }
 
     template <int D>

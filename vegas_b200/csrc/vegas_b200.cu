@@ -74,7 +74,7 @@ struct vb200_ctx {
     std::vector<char> functor;        // host copy of the functor struct
     DevBuf fparams;                   // device arrays the functor points to
     // scratch
-    DevBuf partials, scratch;
+    DevBuf partials, scratch, counter;
     int64_t launches = 0;
 };
 
@@ -109,7 +109,7 @@ extern "C" void vb200_destroy(vb200_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     c->grid.release(); c->chunk_tot.release(); c->chunk_off.release(); c->stats.release();
-    c->fparams.release(); c->partials.release(); c->scratch.release();
+    c->fparams.release(); c->partials.release(); c->scratch.release(); c->counter.release();
     delete c;
 }
 
@@ -493,6 +493,9 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
         CK(c->scratch.ensure(sizeof(double) * (size_t)grid * nf * (size_t)c->plan_max));
         p.scratch = (double*)c->scratch.p;
     }
+    CK(c->counter.ensure(sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), st));
+    p.work_counter = (unsigned long long*)c->counter.p;
     int g2 = fused ? do_launch_fused(c, p, cfg, max_grid, st) : launch_buffer(p, nf, cfg, max_grid, st);
     if (g2 < 0) return fail(-2, "engine: launch failed (%d: %s)", g2, cudaGetErrorString((cudaError_t)(-(g2 + 1000))));
     k_finalize<<<1, 64, 0, st>>>(p.partials, g2, nacc, acc);
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ Engine
         __syncthreads();
         if (tid < dim) base_s[tid] = (uint32_t)((h0 / p.cstride[tid]) % p.st.nstrat[tid]);
         long long total;
-        long long ex = block_exscan(n_mine, scan_s, &total);
+        long long ex = block_exscan<VB_NT>(n_mine, scan_s, &total);
         ex_s[tid] = ex;
         n_s[tid] = n_mine;
         if (tid == VB_NT - 1) ex_s[VB_CH] = total;
