@@ -1,0 +1,35 @@
+"""The cases of the golden fixtures: shared by make_golden.py (reference run) and the tests."""
+import numpy as np
+
+
+def integrand(name):
+    """numpy lbatch integrands, f(x[n, D]) -> f[n] or f[n, nf]"""
+    if name == 'gauss':
+        return lambda x: np.exp(-100. * np.sum((x - 0.5) ** 2, axis=1)) * 1013.2118364296088
+    if name == 'poly':
+        return lambda x: 0.5 + x[:, 0] ** 2 + 2. * x[:, 1] ** 3
+    if name == 'osc':
+        return lambda x: np.cos(2. + x.dot(np.arange(1, x.shape[1] + 1) * 0.7))
+    if name == 'vec':
+        def f(x):
+            g = np.exp(-30. * np.sum((x - 0.4) ** 2, axis=1))
+            return np.stack([g, g * x[:, 0], x[:, 1] ** 2], axis=1)
+        return f
+    if name == 'const':
+        return lambda x: 7. * np.ones(x.shape[0])
+    raise KeyError(name)
+
+
+CASES = {
+    # name: limits, integrand, Integrator kwargs, iterations, uniform seed
+    'gauss4': dict(limits=[[-1., 1.]] + 3 * [[0., 1.]], f='gauss', kw=dict(neval=3000), nitn=3, seed=11),
+    'poly2_beta0': dict(limits=2 * [[0., 2.]], f='poly', kw=dict(neval=1500, beta=0.0), nitn=3, seed=12),
+    'osc3_errors': dict(limits=3 * [[0., 1.]], f='osc', kw=dict(neval=2000, adapt_to_errors=True), nitn=3, seed=13),
+    'vec2': dict(limits=[[0., 1.], [0., 2.]], f='vec', kw=dict(neval=2500, alpha=0.3), nitn=3, seed=14),
+    'vec2_nocorr': dict(limits=[[0., 1.], [0., 2.]], f='vec', kw=dict(neval=2500, correlate_integrals=False),
+                        nitn=2, seed=15),
+    'gauss2_batches': dict(limits=2 * [[0., 1.]], f='gauss', kw=dict(neval=4000, min_neval_batch=700), nitn=3, seed=16),
+    'gauss2_bigcubes': dict(limits=2 * [[0., 1.]], f='gauss', kw=dict(neval=3000, nstrat=[3, 2]), nitn=3, seed=17),
+    'const1': dict(limits=[[0., 1.]], f='const', kw=dict(neval=100, alpha=0.0), nitn=3, seed=18),
+    'gauss3_noadapt': dict(limits=3 * [[0., 1.]], f='gauss', kw=dict(neval=2000, adapt=False), nitn=2, seed=19),
+}

@@ -1,0 +1,405 @@
+"""CPU tests of the host-side mirror of the reference API (no GPU needed): the integer set-up of
+``Integrator.set``, ``settings()``, pickling, ``AdaptiveMap`` construction / regrid (the library's
+host ``vb200_map_adapt``), the result accumulators, the C-ABI export list, and the block-cyclic
+sharding arithmetic.  Ported from the reference's own tests (tests/test_vegas.py, lines cited)."""
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+import vegas_b200 as vegas
+from vegas_b200 import _lib
+from vegas_b200._gv import gv
+from vegas_b200._integrator import _local_cubes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ----------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    """the shared library loads without a GPU and exports exactly what include/vegas_b200.h declares"""
+    hdr = open(os.path.join(ROOT, 'include', 'vegas_b200.h')).read()
+    declared = sorted(set(re.findall(r'\b(vb200_[a-z0-9_]+)\s*\(', hdr)))
+    assert declared and set(declared) == set(_lib.SYMBOLS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.vb200_abi_version() == 1
+    _lib.load()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(_lib.VegasB200Error):
+        _lib.Context()
+    integ = vegas.Integrator([[0, 1]])
+    with pytest.raises(_lib.VegasB200Error):
+        integ(lambda x: x[0])
+    m = vegas.AdaptiveMap([[0, 1]])
+    with pytest.raises(_lib.VegasB200Error):
+        m(np.array([[0.5]]))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'vegas_b200')):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src and 'vegas_oracle' not in src, fn
+
+
+# ----------------------------------------------------------------------------- AdaptiveMap (host parts)
+def test_map_init():
+    """tests/test_vegas.py:39-63"""
+    m = vegas.AdaptiveMap(grid=[[0, 1], [2, 4]])
+    np.testing.assert_allclose(m.grid, [[0, 1], [2, 4]])
+    np.testing.assert_allclose(m.inc, [[1], [2]])
+    np.testing.assert_allclose(m.ninc, [1, 1])
+    m = vegas.AdaptiveMap(grid=[[0, 1], [-2, 4]], ninc=2)
+    np.testing.assert_allclose(m.grid, [[0, 0.5, 1.], [-2., 1., 4.]])
+    np.testing.assert_allclose(m.inc, [[0.5, 0.5], [3., 3.]])
+    assert m.dim == 2
+    m = vegas.AdaptiveMap([[0, 0.4, 1], [-2, 0., 4]], ninc=4)
+    np.testing.assert_allclose(m.grid, [[0, 0.2, 0.4, 0.7, 1.], [-2., -1., 0., 2., 4.]])
+    np.testing.assert_allclose(m.inc, [[0.2, 0.2, 0.3, 0.3], [1, 1, 2, 2]])
+    np.testing.assert_allclose(m.ninc, [4, 4])
+    m = vegas.AdaptiveMap([[0, 1], [2, 2.5, 4]])
+    np.testing.assert_allclose(m.ninc, [1, 2])
+    np.testing.assert_allclose(m.grid[0, :2], [0, 1])
+    np.testing.assert_allclose(m.grid[1, :3], [2, 2.5, 4])
+    np.testing.assert_allclose(m.inc[0, :1], [1])
+    np.testing.assert_allclose(m.inc[1, :2], [.5, 1.5])
+    with pytest.raises(ValueError):
+        vegas.AdaptiveMap([[0]])
+
+
+def test_map_pickle_region_settings():
+    """tests/test_vegas.py:65-74, 114-129"""
+    m1 = vegas.AdaptiveMap(grid=[[0, 1, 3], [-2, 0, 6]])
+    m2 = pickle.loads(pickle.dumps(m1))
+    np.testing.assert_allclose(m2.grid, m1.grid)
+    np.testing.assert_allclose(m2.inc, m1.inc)
+    np.testing.assert_allclose(m1.region(0), [0, 3])
+    np.testing.assert_allclose(m1.region(), [[0, 3], [-2, 6]])
+    m = vegas.AdaptiveMap(grid=[[0, 1, 3], [-2, 0, 6]], ninc=4)
+    out = "    grid[ 0] = [ 0.   0.5  1.   2.   3. ]\n    grid[ 1] = [-2. -1.  0.  3.  6.]\n"
+    assert m.settings(5).replace(' ', '') == out.replace(' ', '')
+    out = "    grid[ 0] = [ 0.5  2. ]\n    grid[ 1] = [-1.  3.]\n"
+    assert m.settings(2).replace(' ', '') == out.replace(' ', '')
+
+
+def test_map_adapt_host_matches_golden():
+    """vb200_map_adapt (the product's host step) against the reference's adapt recorded in
+    tests/golden/ref_map.npz -- training sums taken from the fixture"""
+    G = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_map.npz'))
+    m = vegas.AdaptiveMap([[0, 2], [-1, 1]], ninc=[50, 33])
+    for i, alpha in enumerate((1.5, 0.5, -1.0)):
+        m.sum_f = np.array(G['train%d_sum_f' % i])
+        m.n_f = np.array(G['train%d_n_f' % i])
+        m.adapt(alpha=alpha)
+        g = G['train%d_grid' % i]
+        for d in range(2):
+            n = m.ninc[d] + 1
+            np.testing.assert_allclose(m.grid[d, :n], g[d, :n], rtol=1e-14, atol=1e-16)
+            np.testing.assert_array_equal(m.inc[d, :n - 1], m.grid[d, 1:n] - m.grid[d, :n - 1])
+    m.adapt(ninc=[20, 7])
+    for d, n in enumerate((21, 8)):
+        np.testing.assert_allclose(m.grid[d, :n], G['regrid'][d, :n], rtol=1e-14, atol=1e-16)
+    m.adapt(ninc=1)
+    np.testing.assert_allclose(m.grid, [[0, 2], [-1, 1]])
+    m.make_uniform(ninc=[4, 2])
+    np.testing.assert_allclose(m.grid[0], [0, 0.5, 1, 1.5, 2])
+
+
+# ----------------------------------------------------------------------------- Integrator set-up
+def test_integrator_init():
+    """tests/test_vegas.py:561-595"""
+    I = vegas.Integrator([[0., 1.], [-1., 1.]], neval=234, nitn=123, neval_frac=0.75)
+    assert I.neval == 234 and I.nitn == 123
+    for k in vegas.Integrator.defaults:
+        if k in ['neval', 'nitn']:
+            assert getattr(I, k) != vegas.Integrator.defaults[k]
+        elif k not in ['map', 'xparam']:
+            assert getattr(I, k) == vegas.Integrator.defaults[k]
+    np.testing.assert_allclose([I.map.grid[0, 0], I.map.grid[0, I.map.ninc[0]]], [0., 1.])
+    np.testing.assert_allclose([I.map.grid[1, 0], I.map.grid[1, I.map.ninc[1]]], [-1., 1.])
+    assert list(I.map.ninc) == [20, 20] and list(I.nstrat) == [5, 5]
+    I = vegas.Integrator([[0., 1.], [-1., 1.]], nstrat=[1, 1], neval=1000)
+    assert list(I.map.ninc) == [100, 100] and list(I.nstrat) == [1, 1]
+    assert I.neval == 1000 and I.min_neval_hcube == 1000
+    I = vegas.Integrator([[0., 1.], [-1., 1.]], nstrat=[10, 11], neval_frac=0.75)
+    assert list(I.map.ninc) == [80, 88] and list(I.nstrat) == [10, 11]
+    assert I.neval == 880 and I.min_neval_hcube == 2
+
+
+def test_integrator_set():
+    """tests/test_vegas.py:703-772"""
+    new_defaults = dict(
+        map=vegas.AdaptiveMap([[1, 2], [0, 1]]), neval=100, maxinc_axis=100, min_neval_batch=10,
+        max_neval_hcube=1e1, max_mem=229, nitn=100, alpha=0.35, beta=0.25, adapt_to_errors=True,
+        rtol=0.1, atol=0.2, analyzer=vegas.reporter(5))
+    I = vegas.Integrator([[1, 2]])
+    old = I.set(**new_defaults)
+    for k in new_defaults:
+        if k == 'map':
+            np.testing.assert_allclose([[I.map.grid[0, 0], I.map.grid[0, I.map.ninc[0]]],
+                                        [I.map.grid[1, 0], I.map.grid[1, I.map.ninc[1]]]], new_defaults['map'].grid)
+        else:
+            assert getattr(I, k) == new_defaults[k]
+    assert old['neval'] == 1000 and old['alpha'] == 0.5
+    I = vegas.Integrator([[1, 1.3, 2], [0, 1]], maxinc_axis=1000, neval_frac=0.75)
+    I.set(nstrat=[22, 13])
+    assert I.neval == 22 * 13 * 2 / 0.25 and I.min_neval_hcube == 2
+    I.set(nstrat=[7, 9], neval=2000)
+    assert I.neval == 2000 and list(I.nstrat) == [7, 9] and list(I.map.ninc) == [196, 198]
+    assert I.min_neval_hcube == 7
+    I.set(nstrat=[7, 9])
+    assert I.neval == 7 * 9 * 2 / 0.25 and I.min_neval_hcube == 2
+    with pytest.raises(ValueError):
+        I.set(nstrat=[7, 9], neval=20)
+    I.set(neval=3100)
+    assert list(I.nstrat) == [20, 19] and I.min_neval_hcube == 2
+    with pytest.raises(ValueError):
+        I.set(nstrat=[2, 3, 5])
+    I.set(neval=3500)
+    assert list(I.nstrat) == [21, 20]
+    with pytest.raises(ValueError):
+        I.set(nstrat=[10, 12], neval=120 * 4)
+    I.set(nstrat=[10, 12], neval=120 * 8)
+    assert I.neval == 120 * 8 and I.min_neval_hcube == 2
+    I.set(neval=3.5e8)
+    nstrat, ninc = np.array(I.nstrat), np.array(I.map.ninc)
+    assert np.all(np.round(nstrat / ninc) * ninc == nstrat)
+    I.set(neval=300)
+    nstrat, ninc = np.array(I.nstrat), np.array(I.map.ninc)
+    assert np.all(np.round(ninc / nstrat) * nstrat == ninc)
+    I.set(sigf=[1.])
+    assert len(I.sigf) != 1
+    with pytest.raises(AttributeError):
+        I.set(no_such_parameter=1)
+    I.set(nhcube_batch=10)          # legacy key: ignored
+
+
+def test_strata_match_golden_and_survey_sizes():
+    """integer outputs of set() for the BASELINE configs and the golden cases"""
+    from tests.golden.cases import CASES
+    for name, spec in CASES.items():
+        G = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_%s.npz' % name))
+        I = vegas.Integrator(spec['limits'], **spec['kw'])
+        assert list(I.nstrat) == list(G['nstrat']) and list(I.map.ninc) == list(G['ninc']), name
+        assert I.nhcube == int(G['nhcube']) and I.min_neval_hcube == int(G['min_neval_hcube']), name
+    I = vegas.Integrator(4 * [[0, 1]], neval=1e4)
+    assert list(I.nstrat) == [6, 6, 6, 5] and list(I.map.ninc) == [996, 996, 996, 1000] and I.nhcube == 1080
+    I = vegas.Integrator(8 * [[0, 1]], neval=1e8)
+    assert list(I.nstrat) == [8, 8, 8, 8, 8, 7, 7, 7] and I.nhcube == 11239424 and I.min_neval_hcube == 2
+    I = vegas.Integrator(10 * [[0, 1]], neval=1e9)
+    assert list(I.nstrat) == [7, 7, 7, 7, 6, 6, 6, 6, 6, 6] and I.nhcube == 112021056
+    with pytest.raises(MemoryError):
+        vegas.Integrator(20 * [[0, 1]], neval=1e10)
+    I = vegas.Integrator(20 * [[0, 1]], neval=1e10, nstrat=5 * [60] + 15 * [1], max_mem=2e10)
+    assert I.nhcube == 777600000 and I.min_neval_hcube == 3
+
+
+def test_settings_strings():
+    """tests/test_vegas.py:597-673"""
+    head = [
+        "Integrator Settings:",
+        "    {neval} (approx) integrand evaluations in each of 123 iterations",
+        "    number of: strata/axis = [{nstrat0} {nstrat1}]",
+        "               increments/axis = [{ninc0} {ninc1}]",
+        "               h-cubes = {nhcube}  processors = 1",
+        "               evaluations/batch >= {min_neval_batch:.2g}",
+        "               {min_neval_hcube} <= evaluations/h-cube <= {max_neval_hcube:.2g}",
+        "    minimize_mem = False  adapt_to_errors = False  adapt = True",
+        "    accuracy: relative = 0  absolute = 0",
+        "    damping: alpha = {alpha}  beta= {beta}",
+        ""]
+    tails = [
+        ([[0., 1.], [-1., 1.]], ["    axis    integration limits", "    --------------------------",
+                                 "       0            (0.0, 1.0)", "       1           (-1.0, 1.0)\n"]),
+        (dict(x=[[0., 1.]], y=[-1., 1.]), ["    key/index    axis    integration limits",
+                                            "    ---------------------------------------",
+                                            "          x 0       0            (0.0, 1.0)",
+                                            "            y       1           (-1.0, 1.0)\n"]),
+        ([[[0., 1.]], [[-1., 1.]]], ["    key/index    axis    integration limits",
+                                     "    ---------------------------------------",
+                                     "          0,0       0            (0.0, 1.0)",
+                                     "          1,0       1           (-1.0, 1.0)\n"]),
+    ]
+    for limits, tail in tails:
+        I = vegas.Integrator(limits, neval=254, nitn=123, neval_frac=0.75)
+        out = '\n'.join(head + tail).format(
+            neval=I.neval, nstrat0=I.nstrat[0], nstrat1=I.nstrat[1], ninc0=I.map.ninc[0], ninc1=I.map.ninc[1],
+            nhcube=I.nhcube, min_neval_hcube=I.min_neval_hcube, alpha=I.alpha, beta=I.beta,
+            min_neval_batch=I.min_neval_batch, max_neval_hcube=float(I.max_neval_hcube))
+        assert out == I.settings()
+
+
+def test_integrator_pickle():
+    """tests/test_vegas.py:675-701"""
+    I1 = vegas.Integrator([[0., 1.], [-1., 1.]], neval=234)
+    I2 = pickle.loads(pickle.dumps(I1))
+    assert isinstance(I2, vegas.Integrator)
+    for k in vegas.Integrator.defaults:
+        if k == 'map':
+            np.testing.assert_allclose(I1.map.ninc, I2.map.ninc)
+            for d in range(I1.dim):
+                n = I1.map.ninc[d] + 1
+                np.testing.assert_allclose(I1.map.grid[d, :n] + 1e-8, I2.map.grid[d, :n] + 1e-8, rtol=0.01)
+        elif k != 'ran_array_generator':
+            assert getattr(I1, k) == getattr(I2, k)
+    assert list(I2.nstrat) == list(I1.nstrat) and len(I2.sigf) == len(I1.sigf)
+    I3 = vegas.Integrator(I1, alpha=0.1)
+    assert I3.alpha == 0.1 and list(I3.nstrat) == list(I1.nstrat) and I3.neval == I1.neval
+
+
+# ----------------------------------------------------------------------------- results
+def test_ravg_known_answers():
+    """tests/test_vegas.py:216-236"""
+    a = vegas.RAvg()
+    a.add(gv.gvar(1, 1))
+    a.add(gv.gvar(2, 2))
+    a.add(gv.gvar(3, 3))
+    np.testing.assert_allclose(a.mean, 1.346938775510204)
+    np.testing.assert_allclose(a.sdev, 0.8571428571428571)
+    assert a.dof == 2
+    np.testing.assert_allclose(a.chi2, 0.5306122448979592)
+    np.testing.assert_allclose(a.Q, 0.7669711269557102)
+    assert str(a) == '1.35(86)'
+    s = ["itn   integral        wgt average     chi2/dof        Q",
+         "-------------------------------------------------------",
+         "  1   1.0(1.0)        1.0(1.0)            0.00     1.00",
+         "  2   2.0(2.0)        1.20(89)            0.20     0.65",
+         "  3   3.0(3.0)        1.35(86)            0.27     0.77", ""]
+    assert a.summary() == '\n'.join(s)
+    b = pickle.loads(pickle.dumps(a))
+    assert str(b) == '1.35(86)' and b.dof == 2
+    a.extend(b)
+    assert a.nitn == 6
+    u = vegas.RAvg(weighted=False)
+    for m, s in ((1, 1), (2, 2), (3, 3)):
+        u.add(gv.gvar(m, s))
+    np.testing.assert_allclose(u.mean, 2.0)
+    np.testing.assert_allclose(u.sdev, (14. / 9.) ** 0.5)
+
+
+def test_ravgarray_ravgdict_known_answers():
+    """tests/test_vegas.py:312-361"""
+    a = vegas.RAvgArray((1, 2))
+    a.add([[gv.gvar(1, 1), gv.gvar(10, 10)]])
+    a.add([[gv.gvar(2, 2), gv.gvar(20, 20)]])
+    a.add([[gv.gvar(3, 3), gv.gvar(30, 30)]])
+    assert a.shape == (1, 2)
+    np.testing.assert_allclose(a[0, 0].mean, 1.346938775510204)
+    np.testing.assert_allclose(a[0, 0].sdev, 0.8571428571428571)
+    assert a.dof == 4
+    np.testing.assert_allclose(a.chi2, 2 * 0.5306122448979592)
+    np.testing.assert_allclose(a.Q, 0.900374555485)
+    assert str(a[0, 0]) == '1.35(86)' and str(a[0, 1]) == '13.5(8.6)'
+    s = ["itn   integral        wgt average     chi2/dof        Q",
+         "-------------------------------------------------------",
+         "  1   1.0(1.0)        1.0(1.0)            0.00     1.00",
+         "  2   2.0(2.0)        1.20(89)            0.20     0.82",
+         "  3   3.0(3.0)        1.35(86)            0.27     0.90", ""]
+    assert a.summary() == '\n'.join(s)
+    d = vegas.RAvgDict(dict(s=1.0, a=[[2.0, 3.0]]))
+    d.add(dict(s=gv.gvar(1, 1), a=[[gv.gvar(1, 1), gv.gvar(10, 10)]]))
+    d.add(dict(s=gv.gvar(2, 2), a=[[gv.gvar(2, 2), gv.gvar(20, 20)]]))
+    d.add(dict(s=gv.gvar(3, 3), a=[[gv.gvar(3, 3), gv.gvar(30, 30)]]))
+    assert d['a'].shape == (1, 2)
+    np.testing.assert_allclose(d['a'][0, 0].mean, 1.346938775510204)
+    assert str(d['a'][0, 1]) == '13.5(8.6)' and str(d['s']) == '1.35(86)'
+    assert d.dof == 6
+    np.testing.assert_allclose(d.chi2, 3 * 0.5306122448979592)
+    np.testing.assert_allclose(d.Q, 0.953162484587)
+
+
+# ----------------------------------------------------------------------------- integrand adapters
+def test_integrand_adapter_shapes():
+    """tests/test_vegas.py:840-969 (subset): every integrand kind is normalised to eval(x[n,D]) -> f[n,size]"""
+    m = vegas.AdaptiveMap([[0, 1], [0, 2]])
+    xs = np.array([0.3, 0.7])
+    x = np.array([[0.1, 0.2], [0.3, 0.4], [0.5, 0.6]])
+
+    def scalar(x):
+        return x[0] + x[1]
+
+    def scalar_arr(x):
+        return [x[0], x[1], x[0] * x[1]]
+
+    def scalar_dict(x):
+        return dict(a=x[0], b=[x[1], x[0] * x[1]])
+
+    @vegas.lbatchintegrand
+    def lb(x):
+        return x[:, 0] + x[:, 1]
+
+    @vegas.rbatchintegrand
+    def rb(x):
+        return dict(a=x[0], b=[x[1], x[0] * x[1]])
+
+    class C(vegas.LBatchIntegrand):
+        def __call__(self, x):
+            return np.stack([x[:, 0], x[:, 1]], axis=1).reshape(-1, 1, 2)
+
+    v = vegas.VegasIntegrand(scalar, m, False, xs, False)
+    assert v.shape == () and v.size == 1
+    np.testing.assert_allclose(v.eval(x)[:, 0], x.sum(axis=1))
+    v = vegas.VegasIntegrand(scalar_arr, m, False, xs, False)
+    assert v.shape == (3,) and v.eval(x).shape == (3, 3)
+    v = vegas.VegasIntegrand(scalar_dict, m, False, xs, False)
+    assert v.shape is None and v.size == 3
+    np.testing.assert_allclose(v.eval(x), np.stack([x[:, 0], x[:, 1], x[:, 0] * x[:, 1]], axis=1))
+    v = vegas.VegasIntegrand(lb, m, False, xs, False)
+    assert v.shape == () and v.eval(x).shape == (3, 1)
+    v = vegas.VegasIntegrand(rb, m, False, xs, False)
+    assert v.shape is None and v.size == 3
+    np.testing.assert_allclose(v.eval(x), np.stack([x[:, 0], x[:, 1], x[:, 0] * x[:, 1]], axis=1))
+    r = v.format_result(np.array([1., 2., 3.]), np.diag([1., 4., 9.]))
+    assert str(r['a']) == '1.0(1.0)' and r['b'].shape == (2,)
+    v = vegas.VegasIntegrand(C(), m, False, xs, False)
+    assert v.shape == (1, 2) and v.eval(x).shape == (3, 2)
+    with pytest.raises(ValueError):
+        vegas.VegasIntegrand(C, m, False, xs, False)
+    # dictionary-valued arguments
+    I = vegas.Integrator(dict(u=[0., 1.], w=[[0., 1.], [0., 2.]]))
+
+    def fd(xd):
+        return xd['u'] * xd['w'][0] + xd['w'][1]
+    v = I._make_std_integrand(fd)
+    np.testing.assert_allclose(v.eval(np.array([[0.5, 0.2, 1.0]]))[0, 0], 0.5 * 0.2 + 1.0)
+
+
+def test_device_integrand_twins_are_consistent():
+    F = vegas.integrands
+    rng = np.random.default_rng(1)
+    x = rng.random((50, 8))
+    np.testing.assert_allclose(F.Ridge(8, N=7)(x), F.Ridge(8, N=7, shifted=True)(x))
+    p = F.PathIntegral(T=4., ndT=8, x0list=np.linspace(0, 2, 6))
+    out = p(x - 0.5)
+    assert list(out) == ['exp(-E0*T)', 'exp(-E0*T) * psi(x0)**2'] and out['exp(-E0*T) * psi(x0)**2'].shape == (50, 6)
+    # Genz closed forms against brute-force quadrature in 2-D
+    t = (np.arange(400) + 0.5) / 400
+    X = np.stack(np.meshgrid(t, t, indexing='ij'), axis=-1).reshape(-1, 2)
+    for kind in F.Genz.KINDS:
+        g = F.Genz(kind, [1.3, 2.1], [0.4, 0.7])
+        np.testing.assert_allclose(g(X).mean(), g.exact(), rtol=3e-3, err_msg=kind)
+
+
+# ----------------------------------------------------------------------------- sharding arithmetic
+@pytest.mark.parametrize('nh,slab,world', [(1080, 256, 2), (11239424, 16384, 8), (777, 256, 4), (256, 256, 3), (5, 256, 2)])
+def test_block_cyclic_partition_covers_every_cube_once(nh, slab, world):
+    seen = np.zeros(nh, np.int32)
+    for r in range(world):
+        idx = _local_cubes(nh, slab, r, world)
+        seen[idx] += 1
+        # matches the library's count
+        L = _lib.load()
+        out = ctypes.c_int64()
+        h = ctypes.c_void_p()
+    assert np.all(seen == 1)

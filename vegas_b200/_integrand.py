@@ -27,7 +27,7 @@ class LBatchIntegrand(object):
         return self.fcn(*args, **kargs)
 
     def __getattr__(self, attr):
-        if attr == 'fcn':
+        if attr == 'fcn' or self.fcn is self:
             raise AttributeError(attr)
         return getattr(self.fcn, attr)
 
@@ -44,7 +44,7 @@ class RBatchIntegrand(object):
         return self.fcn(*args, **kargs)
 
     def __getattr__(self, attr):
-        if attr == 'fcn':
+        if attr == 'fcn' or self.fcn is self:
             raise AttributeError(attr)
         return getattr(self.fcn, attr)
 

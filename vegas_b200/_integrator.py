@@ -620,14 +620,7 @@ class Integrator(object):
     def _set_neval_stats(self, total, nmax, adaptive):
         rank, world = self._rank_world()
         if world > 1:
-            import torch
-            t = torch.tensor([total, -nmax], dtype=torch.int64, device=self._ctx.device)
-            dist = _dist()
-            tot = t[:1].clone()
-            dist.all_reduce(tot)
-            mx = t[1:].clone()
-            dist.all_reduce(mx, op=dist.ReduceOp.MIN)
-            total, nmax = int(tot.item()), -int(mx.item())
+            total, nmax = allreduce_neval_stats(total, nmax, self._ctx.device)
         self.last_neval = int(total)
         # pyx:1682,1699-1702: both ends start at min_neval_hcube
         hi = max(self.min_neval_hcube, nmax) if adaptive else self.min_neval_hcube
@@ -689,11 +682,7 @@ class Integrator(object):
             if self._timing is not None:
                 ev[2].record()
             if world > 1:
-                dist = _dist()
-                dist.all_reduce(acc)
-                dist.all_reduce(sum_f)
-                dist.all_reduce(n_f)
-                dist.all_reduce(status, op=dist.ReduceOp.MAX)
+                allreduce_iteration(acc, sum_f, n_f, status)
             if self._timing is not None:
                 ev[3].record()
                 self._timing.append((ev, total))
@@ -763,6 +752,29 @@ class Integrator(object):
     def gpu_launches(self):
         """kernels launched by this integrator's context so far"""
         return self._ctx.launch_count() if self._ctx is not None else 0
+
+
+def allreduce_iteration(acc, sum_f, n_f, status):
+    """The one exchange step of an iteration when the hypercube range is sharded: sum the
+    per-rank partial sums [mean, var, sum_sigf], the training histogram (fp64 sums, integer
+    counts) and the NaN flag over the process group (NCCL over NVLink on GPUs; gloo in the CPU
+    tests).  In place; every rank ends with identical values."""
+    dist = _dist()
+    dist.all_reduce(acc)
+    dist.all_reduce(sum_f)
+    dist.all_reduce(n_f)
+    dist.all_reduce(status, op=dist.ReduceOp.MAX)
+
+
+def allreduce_neval_stats(total, nmax, device):
+    """(sum of samples, max samples per hypercube) over the ranks"""
+    import torch
+    dist = _dist()
+    tot = torch.tensor([total], dtype=torch.int64, device=device)
+    mx = torch.tensor([nmax], dtype=torch.int64, device=device)
+    dist.all_reduce(tot)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    return int(tot.item()), int(mx.item())
 
 
 def _local_cubes(nhcube, slab, rank, world):
