@@ -82,6 +82,7 @@ class Integrator(object):
         self._launches = 0
         self._trace = None      # test hook: called with the raw per-iteration sums before adapt
         self._timing = None     # bench hook: list receiving per-iteration CUDA-event pairs
+        self._unfused_events = []   # bench hook: (events around sample / callback / reduce, rows) per batch
         for k, v in self.engine_defaults.items():
             setattr(self, k, v)
         for k in list(kargs):
@@ -734,7 +735,12 @@ class Integrator(object):
             x = torch.empty((rows, self.dim), dtype=torch.float64, device=ctx.device)
             wgt = torch.empty(rows, dtype=torch.float64, device=ctx.device)
             jac1d = torch.empty_like(x) if self.uses_jac else None
+            if self._timing is not None:
+                tev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                tev[0].record()
             ctx.sample(pitn, c0, c1, x, wgt, jac1d=jac1d)
+            if self._timing is not None:
+                tev[1].record()
             if on_device:
                 fx = std.eval(x, jac=jac1d)
             else:
@@ -745,7 +751,12 @@ class Integrator(object):
             if fx.shape != (rows, nf):
                 raise ValueError('integrand returned shape %s for %d points, expected %s'
                                  % (tuple(fx.shape), rows, (rows, nf)))
+            if self._timing is not None:
+                tev[2].record()
             ctx.reduce(pitn, self.beta, flags, c0, c1, fx, nf, wgt, self._sigf_dev, acc, sum_f, n_f, hs, status)
+            if self._timing is not None:
+                tev[3].record()
+                self._unfused_events.append((tev, rows))
             self._launches += 3
 
     @property
