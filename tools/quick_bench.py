@@ -15,5 +15,7 @@ r = integ(f, nitn=4)
 torch.cuda.synchronize()
 kms = [ev[1].elapsed_time(ev[2]) for ev, _ in integ._timing]
 tot = sum(t for _, t in integ._timing)
-print('%s N=%d shifted=%d neval=%.0e: kernel %.2f ms/itn  %.4e samples/s  result %s' % (
-    os.environ.get('VB200_LIB', 'default'), N, shifted, neval, np.mean(kms), tot / (sum(kms) * 1e-3), r))
+from vegas_b200 import _lib
+pk = _lib.fp64_peak(0, 20000)[0]
+print('[fp64 peak %.1f TF/s, launch %s] %s N=%d shifted=%d neval=%.0e: kernel %.2f ms/itn  %.4e samples/s  result %s' % (
+    pk, integ._ctx.last_launch(), os.environ.get('VB200_LIB', 'default'), N, shifted, neval, np.mean(kms), tot / (sum(kms) * 1e-3), r))

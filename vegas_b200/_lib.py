@@ -22,6 +22,7 @@ SYMBOLS = (
     'vb200_set_map', 'vb200_set_strata', 'vb200_set_integrand', 'vb200_plan', 'vb200_chunk_offsets',
     'vb200_iterate_fused', 'vb200_sample', 'vb200_reduce', 'vb200_map', 'vb200_invmap', 'vb200_jac1d',
     'vb200_add_training_data', 'vb200_map_adapt', 'vb200_uniforms', 'vb200_fp64_peak', 'vb200_launch_count',
+    'vb200_last_launch',
 )
 
 
@@ -92,6 +93,7 @@ def load():
     L.vb200_fp64_peak.argtypes = [i32, i32, ctypes.POINTER(f64), ctypes.POINTER(f64)]
     L.vb200_launch_count.argtypes = [vp]
     L.vb200_launch_count.restype = i64
+    L.vb200_last_launch.argtypes = [vp, pi64]
     for name in SYMBOLS:
         if name not in ('vb200_last_error', 'vb200_destroy', 'vb200_launch_count'):
             getattr(L, name).restype = i32
@@ -207,6 +209,12 @@ class Context(object):
 
     def launch_count(self):
         return self.L.vb200_launch_count(self.h)
+
+    def last_launch(self):
+        """geometry of the most recent engine launch"""
+        out = (ctypes.c_int64 * 4)()
+        check(self.L.vb200_last_launch(self.h, out))
+        return dict(grid=out[0], ctas_per_sm=out[1], smem_bytes=out[2], hist_window_bins=out[3])
 
 
 def map_adapt(grid, ninc, sum_f, n_f, alpha, new_ninc):

@@ -42,6 +42,10 @@ struct EngineP {
     int64_t chunk_begin, chunk_end;   // local chunk range of this launch
     unsigned long long* work_counter; // zeroed before the launch: next chunk to claim
     int64_t cstride[VB_MAXD];  // cstride[d] = prod_{e<d} nstrat[e]
+    // shared-memory windows of the training histogram (0 bins on an axis: global atomics there)
+    int wcap[VB_MAXD];         // bins of axis d's window
+    int woff[VB_MAXD];         // offset of axis d's window in the shared arrays
+    int wtot;                  // total window bins (0: no shared histogram)
     // unfused path
     const double* fbuf;        // [rows][nf]
     const double* wbuf;        // [rows]
@@ -57,27 +61,145 @@ __device__ __forceinline__ int bin_of(const EngineP& p, int d, uint32_t y0, doub
 {
     double y = div_exact((double)y0 + u, p.st.dns[d], p.st.rns[d]);
     if (y_out) *y_out = y;
-    int iy = __double2int_rd(__dmul_rn(y, (double)p.map.ninc[d]));
+    int iy = min(__double2int_rd(__dmul_rn(y, (double)p.map.ninc[d])), p.map.ninc[d] - 1);
     return (y > 0.0 && y < 1.0) ? iy : -1;
 }
 
-__device__ __forceinline__ void hist_add(const EngineP& p, int d, int bin, double v)
+// first training bin that samples of stratum `digit` on axis d can fall into.  Same arithmetic as
+// bin_of with u = 0, and bin_of is monotonic in (y0 + u): every sample of strata [a, b] on this
+// axis lands in bins [bin_floor(a), bin_floor(b + 1)].
+__device__ __forceinline__ int bin_floor(const EngineP& p, int d, int digit)
 {
+    double y = div_exact((double)digit, p.st.dns[d], p.st.rns[d]);
+    return min(__double2int_rd(__dmul_rn(y, (double)p.map.ninc[d])), p.map.ninc[d] - 1);
+}
+
+// The training histogram (AdaptiveMap.add_training_data, _vegas.pyx:421-464) is accumulated in
+// shared memory: a chunk of consecutive hypercubes only touches a window of bins on each axis
+// (all of them on the fastest-running axes, one or two strata on the others).  The CTA keeps one
+// window per axis, [lo[d], lo[d] + wcap[d]), and flushes it to the global histogram with fp64 /
+// u64 atomics only when a newly claimed chunk needs a different window.  Bins outside the window
+// (axes whose window did not fit, chunks that wrap around an axis) go straight to global memory.
+struct HistW {
+    double* sum;        // [wtot]
+    unsigned* cnt;      // [wtot]
+    const int* lo;      // [dim] first bin of the current window
+    uint32_t sum_sa;    // the same arrays as shared-state-space addresses (explicit .shared atomics:
+    uint32_t cnt_sa;    //  through generic pointers the compiler emits the slower generic ATOM forms)
+};
+
+#define VB_NO_SLOT 0xffffffffu
+#ifndef VB_HIST_GROUP
+#define VB_HIST_GROUP 4
+#endif
+
+__device__ __forceinline__ void hist_global(const EngineP& p, int d, int bin, double v)
+{
+    atomicAdd(p.sum_f + (size_t)d * p.hstride + bin, v);
+    atomicAdd(p.n_f + (size_t)d * p.hstride + bin, 1ull);
+}
+
+// count the sample in its window slot and return the shared address of the slot's fp64 sum, or
+// VB_NO_SLOT after sending it to the global histogram (bin outside the window) / skipping it (bin < 0)
+__device__ __forceinline__ uint32_t hist_slot(const EngineP& p, const HistW& H, int d, int bin, double v)
+{
+    if (bin < 0) return VB_NO_SLOT;
+    const unsigned r = (unsigned)(bin - H.lo[d]);
+    if (r < (unsigned)p.wcap[d]) {
+        const unsigned i = (unsigned)p.woff[d] + r;
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(H.cnt_sa + 4u * i) : "memory");
+        return H.sum_sa + 8u * i;
+    }
+    hist_global(p, d, bin, v);
+    return VB_NO_SLOT;
+}
+
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t sa)
+{
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(sa) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long cas_shared_u64(uint32_t sa, unsigned long long cmp, unsigned long long val)
+{
+    unsigned long long old;
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(sa), "l"(cmp), "l"(val) : "memory");
+    return old;
+}
+
+// fp64 adds of v to W shared slots in lock-step: there is no native shared-memory fp64 add, so
+// each is a compare-and-swap loop; running the W loops side by side overlaps their round trips.
+template <int W>
+__device__ __forceinline__ void hist_sum_slots(uint32_t (&sa)[W], double v)
+{
+    unsigned long long old[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) old[j] = sa[j] != VB_NO_SLOT ? lds_u64(sa[j]) : 0ull;
+    bool pending;
+    do {
+        unsigned long long seen[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            if (sa[j] != VB_NO_SLOT)
+                seen[j] = cas_shared_u64(sa[j], old[j], (unsigned long long)__double_as_longlong(__longlong_as_double((long long)old[j]) + v));
+        pending = false;
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            if (sa[j] != VB_NO_SLOT) {
+                if (seen[j] == old[j]) sa[j] = VB_NO_SLOT;
+                else { old[j] = seen[j]; pending = true; }
+            }
+    } while (pending);
+}
+
+__device__ __forceinline__ void hist_add(const EngineP& p, const HistW& H, int d, int bin, double v)
+{
+#ifdef VB_HIST_GENERIC
     if (bin >= 0) {
-        atomicAdd(p.sum_f + (size_t)d * p.hstride + bin, v);
-        atomicAdd(p.n_f + (size_t)d * p.hstride + bin, 1ull);
+        const unsigned r = (unsigned)(bin - H.lo[d]);
+        if (r < (unsigned)p.wcap[d]) {
+            atomicAdd(H.sum + p.woff[d] + r, v);
+            atomicAdd(H.cnt + p.woff[d] + r, 1u);
+        } else hist_global(p, d, bin, v);
+    }
+#else
+    uint32_t sa[1] = {hist_slot(p, H, d, bin, v)};
+    if (sa[0] != VB_NO_SLOT) hist_sum_slots<1>(sa, v);
+#endif
+}
+
+// add the windows of the axes with need[d] != 0 (all axes when need == nullptr) to the global
+// histogram and clear them; called by the whole CTA between barriers
+template <int NT>
+__device__ __forceinline__ void hist_flush(const EngineP& p, const HistW& H, const int* need)
+{
+    for (int d = 0; d < p.map.dim; ++d) {
+        const int cap = p.wcap[d];
+        if (cap == 0 || (need && !need[d])) continue;
+        const int lo = H.lo[d], off = p.woff[d];
+        for (int i = threadIdx.x; i < cap; i += NT) {
+            const unsigned c = H.cnt[off + i];
+            if (c) {
+                atomicAdd(p.sum_f + (size_t)d * p.hstride + lo + i, H.sum[off + i]);
+                atomicAdd(p.n_f + (size_t)d * p.hstride + lo + i, (unsigned long long)c);
+                H.sum[off + i] = 0.0;
+                H.cnt[off + i] = 0u;
+            }
+        }
     }
 }
 
 // training point of a whole cube (adapt_to_errors, _vegas.pyx:2187-2193): y of its LAST sample
-static __device__ __noinline__ void train_cube(const EngineP& p, int64_t h, uint32_t klast, const uint32_t* y0, double v)
+static __device__ __noinline__ void train_cube(const EngineP& p, const HistW& H, int64_t h, uint32_t klast,
+                                               const uint32_t* y0, double v)
 {
     for (int pr = 0; 2 * pr < p.map.dim; ++pr) {
         double ua, ub;
         philox_pair(p.key, p.itn, h, klast, pr, ua, ub);
-        hist_add(p, 2 * pr, bin_of(p, 2 * pr, y0[2 * pr], ua, nullptr), fabs(v));
+        hist_add(p, H, 2 * pr, bin_of(p, 2 * pr, y0[2 * pr], ua, nullptr), fabs(v));
         if (2 * pr + 1 < p.map.dim)
-            hist_add(p, 2 * pr + 1, bin_of(p, 2 * pr + 1, y0[2 * pr + 1], ub, nullptr), fabs(v));
+            hist_add(p, H, 2 * pr + 1, bin_of(p, 2 * pr + 1, y0[2 * pr + 1], ub, nullptr), fabs(v));
     }
 }
 
@@ -88,8 +210,9 @@ static __device__ __noinline__ void train_cube(const EngineP& p, int64_t h, uint
 template <class F, int D>
 struct FusedSrc {
     static constexpr int NF = F::NF;
+    static constexpr int MINB = (D <= 10 && F::NF == 1) ? 3 : 2;                  // resident CTAs per SM the register budget is set for
     F f;
-    __device__ __forceinline__ void sample(const EngineP& p, int n, int64_t h, uint32_t k,
+    __device__ __forceinline__ void sample(const EngineP& p, const HistW& H, int n, int64_t h, uint32_t k,
                                            int64_t /*row*/, const uint32_t* y0, double (&wf)[NF]) const
     {
         const int dim = p.map.dim;
@@ -105,23 +228,19 @@ struct FusedSrc {
                 for (int e = 0; e < 2; ++e) {
                     const int d = 2 * pr + e;
                     if (d < D && d < dim) {
-                        double y;
-                        int b = bin_of(p, d, y0[d], u[e], &y);
+                        // branch-free so that the grid loads of all axes are in flight together
                         const int ni = p.map.ninc[d];
                         const double* g = p.map.grid + (size_t)d * p.map.gstride;
-                        double t = __dmul_rn(y, (double)ni);
-                        int iy = __double2int_rd(t);
-                        if (iy < ni) {
-                            double g0 = __ldg(g + iy), g1 = __ldg(g + iy + 1);
-                            double inc = g1 - g0;
-                            x[d] = __dadd_rn(g0, __dmul_rn(inc, __dsub_rn(t, (double)iy)));   // no FMA: bit-identical to pyx:354
-                            jac *= inc * (double)ni;
-                        } else {
-                            double g0 = __ldg(g + ni - 1), g1 = __ldg(g + ni);
-                            x[d] = g1;
-                            jac *= (g1 - g0) * (double)ni;
-                        }
-                        bin[d] = b;
+                        const double y = div_exact((double)y0[d] + u[e], p.st.dns[d], p.st.rns[d]);
+                        const double t = __dmul_rn(y, (double)ni);
+                        const int iy = __double2int_rd(t);
+                        const int ic = min(iy, ni - 1);
+                        const double g0 = __ldg(g + ic), g1 = __ldg(g + ic + 1);
+                        const double inc = g1 - g0;
+                        const double xin = __dadd_rn(g0, __dmul_rn(inc, __dsub_rn(t, (double)iy)));   // no FMA: bit-identical to pyx:354
+                        x[d] = iy < ni ? xin : g1;                                                     // pyx:357-359
+                        jac *= inc * (double)ni;
+                        bin[d] = (y > 0.0 && y < 1.0) ? ic : -1;                                      // pyx:460
                     }
                 }
             }
@@ -136,9 +255,22 @@ struct FusedSrc {
         if (p.flags & VBF_TRAIN) {
             double a = wf[0] * (double)n;
             double fdv2 = a * a;
+            constexpr int G = VB_HIST_GROUP;                      // axes whose CAS loops run side by side
+#ifdef VB_HIST_GENERIC
 #pragma unroll
-            for (int d = 0; d < D; ++d)
-                if (d < dim) hist_add(p, d, bin[d], fdv2);
+            for (int d = 0; d < D; ++d) if (d < dim) hist_add(p, H, d, bin[d], fdv2);
+#else
+#pragma unroll
+            for (int d0 = 0; d0 < D; d0 += G) {
+                if (d0 < dim) {
+                    uint32_t sa[G];
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+                        sa[j] = (d0 + j < D && d0 + j < dim) ? hist_slot(p, H, d0 + j, bin[d0 + j < D ? d0 + j : 0], fdv2) : VB_NO_SLOT;
+                    hist_sum_slots<G>(sa, fdv2);
+                }
+            }
+#endif
         }
     }
 };
@@ -148,7 +280,8 @@ struct FusedSrc {
 template <int NF_>
 struct BufferSrc {
     static constexpr int NF = NF_;
-    __device__ __forceinline__ void sample(const EngineP& p, int n, int64_t h, uint32_t k,
+    static constexpr int MINB = NF_ <= 4 ? 4 : 3;
+    __device__ __forceinline__ void sample(const EngineP& p, const HistW& H, int n, int64_t h, uint32_t k,
                                            int64_t row, const uint32_t* y0, double (&wf)[NF]) const
     {
         double wgt = p.wbuf[row];
@@ -166,9 +299,9 @@ struct BufferSrc {
             for (int pr = 0; 2 * pr < p.map.dim; ++pr) {
                 double ua, ub;
                 philox_pair(p.key, p.itn, h, k, pr, ua, ub);
-                hist_add(p, 2 * pr, bin_of(p, 2 * pr, y0[2 * pr], ua, nullptr), fdv2);
+                hist_add(p, H, 2 * pr, bin_of(p, 2 * pr, y0[2 * pr], ua, nullptr), fdv2);
                 if (2 * pr + 1 < p.map.dim)
-                    hist_add(p, 2 * pr + 1, bin_of(p, 2 * pr + 1, y0[2 * pr + 1], ub, nullptr), fdv2);
+                    hist_add(p, H, 2 * pr + 1, bin_of(p, 2 * pr + 1, y0[2 * pr + 1], ub, nullptr), fdv2);
             }
         }
     }
@@ -238,22 +371,29 @@ __device__ __forceinline__ double cube_finish(CubeAcc<NF>& A, int n, const doubl
 }
 
 template <int NF>
-__device__ __forceinline__ void cube_epilogue(const EngineP& p, CubeAcc<NF>& A, double sigf2, int64_t lh,
-                                              int64_t h, int n, const uint32_t* y0)
+__device__ __forceinline__ void cube_epilogue(const EngineP& p, const HistW& H, CubeAcc<NF>& A, double sigf2,
+                                              int64_t lh, int64_t h, int n, const uint32_t* y0)
 {
     if (p.flags & VBF_UPDATE_SIGF) {
         double sg = pow(sigf2, p.beta_half);
         p.sigf_out[lh] = sg;
         A.sum_sigf += sg;
     }
-    if (p.flags & VBF_TRAIN_ERRORS) train_cube(p, h, (uint32_t)(n - 1), y0, sigf2);
+    if (p.flags & VBF_TRAIN_ERRORS) train_cube(p, H, h, (uint32_t)(n - 1), y0, sigf2);
 }
 
 // ---------------------------------------------------------------------------------------------
 // the engine kernel
 // ---------------------------------------------------------------------------------------------
+#ifdef VB_NO_MINB
+#define VB_LB __launch_bounds__(VB_ENT)
+#elif defined(VB_FORCE_MINB)
+#define VB_LB __launch_bounds__(VB_ENT, VB_FORCE_MINB)
+#else
+#define VB_LB __launch_bounds__(VB_ENT, Src::MINB)
+#endif
 template <class Src>
-__global__ void __launch_bounds__(VB_ENT) k_engine(const __grid_constant__ EngineP p, const __grid_constant__ Src src)
+__global__ void VB_LB k_engine(const __grid_constant__ EngineP p, const __grid_constant__ Src src)
 {
     constexpr int NF = Src::NF;
     constexpr int NV = NF * (NF + 1) / 2;
@@ -271,12 +411,22 @@ __global__ void __launch_bounds__(VB_ENT) k_engine(const __grid_constant__ Engin
     __shared__ double bc_s[NF];
     __shared__ uint32_t base_s[VB_MAXD];
     __shared__ long long next_s;
+    __shared__ int wlo_s[VB_MAXD], wnew_s[VB_MAXD], wneed_s[VB_MAXD];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dim = p.map.dim;
     const bool correlate = (p.flags & VBF_CORRELATE) != 0;
     CubeAcc<NF> A;
     A.clear();
+    HistW H;
+    H.sum = (double*)(y0_s + (size_t)VB_CH * dim);                // [wtot]   (8-byte aligned: VB_CH*dim*4)
+    H.cnt = (unsigned*)(H.sum + p.wtot);                          // [wtot]
+    H.lo = wlo_s;
+    H.sum_sa = (uint32_t)__cvta_generic_to_shared(H.sum);
+    H.cnt_sa = (uint32_t)__cvta_generic_to_shared(H.cnt);
+    for (int i = tid; i < p.wtot; i += NT) { H.sum[i] = 0.0; H.cnt[i] = 0u; }
+    if (tid < VB_MAXD) wlo_s[tid] = 0;
+    long long since_flush = 0;                                    // samples added since the last full flush
 
     // chunks are claimed dynamically (one atomic per chunk) so that CTAs finish together
     for (;;) {
@@ -287,6 +437,36 @@ __global__ void __launch_bounds__(VB_ENT) k_engine(const __grid_constant__ Engin
         if (lc >= p.chunk_end) break;
         const int64_t lh0 = lc * VB_CH;
         const int64_t h0 = local_to_global(p.st, lh0);
+        if (p.wtot > 0) {
+            // ---- move the histogram windows to this chunk's strata (flush the ones that change)
+            const bool force = since_flush > 0x40000000LL;         // keep the u32 counts far from overflow
+            if (tid < dim) {
+                const int d = tid;
+                int need = 0, lo_bin = 0;
+                if (p.wcap[d] > 0) {
+                    const int64_t a = h0 / p.cstride[d], b = (h0 + VB_CH - 1) / p.cstride[d];
+                    const int64_t ns = p.st.nstrat[d];
+                    int dlo = 0, dhi = (int)ns - 1;
+                    if (b - a + 1 < ns) {
+                        dlo = (int)(a % ns);
+                        const int e = (int)(b % ns);
+                        if (e >= dlo) dhi = e;                     // else the chunk wraps: keep [dlo, ns-1]
+                    }
+                    lo_bin = bin_floor(p, d, dlo);
+                    int hi_bin = bin_floor(p, d, dhi + 1);
+                    if (hi_bin > lo_bin + p.wcap[d] - 1) hi_bin = lo_bin + p.wcap[d] - 1;
+                    const int cur = wlo_s[d];
+                    need = (force || lo_bin < cur || hi_bin >= cur + p.wcap[d]) ? 1 : 0;
+                }
+                wneed_s[d] = need;
+                wnew_s[d] = lo_bin;
+            }
+            __syncthreads();
+            hist_flush<NT>(p, H, wneed_s);
+            __syncthreads();
+            if (tid < dim && wneed_s[tid]) wlo_s[tid] = wnew_s[tid];
+            if (force) since_flush = 0;
+        }
         if (tid < dim) base_s[tid] = (uint32_t)((h0 / p.cstride[tid]) % p.st.nstrat[tid]);
         int n_mine[CPT];
         long long mine = 0;
@@ -314,6 +494,7 @@ __global__ void __launch_bounds__(VB_ENT) k_engine(const __grid_constant__ Engin
             }
         }
         if (tid == NT - 1) ex_s[VB_CH] = total;
+        since_flush += total;
         __syncthreads();
         const int64_t chunk_row = p.chunk_off ? p.chunk_off[lc] - p.row0 : 0;
 
@@ -340,11 +521,15 @@ __global__ void __launch_bounds__(VB_ENT) k_engine(const __grid_constant__ Engin
                 double S[NF];
 #pragma unroll
                 for (int s = 0; s < NF; ++s) S[s] = 0.0;
-                for (int k = tid; k < n; k += NT) {
-                    double w[NF];
-                    src.sample(p, n, h, (uint32_t)k, chunk_row + base + k, y0_s + c0 * dim, w);
+                for (int kb = 0; kb < n; kb += NT) {
+                    const int k = kb + tid;
+                    if (k < n) {
+                        double w[NF];
+                        src.sample(p, H, n, h, (uint32_t)k, chunk_row + base + k, y0_s + c0 * dim, w);
 #pragma unroll
-                    for (int s = 0; s < NF; ++s) { gs[s * p.scratch_stride + k] = w[s]; S[s] += w[s]; }
+                        for (int s = 0; s < NF; ++s) { gs[s * p.scratch_stride + k] = w[s]; S[s] += w[s]; }
+                    }
+                    __syncwarp();
                 }
                 double m[NF];
 #pragma unroll
@@ -372,7 +557,7 @@ __global__ void __launch_bounds__(VB_ENT) k_engine(const __grid_constant__ Engin
                 for (int v = 0; v < NV; ++v) q[v] = block_sum<NT>(q[v], red_s);
                 if (tid == 0) {
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
-                    cube_epilogue<NF>(p, A, sigf2, lh0 + c0, h, n, y0_s + c0 * dim);
+                    cube_epilogue<NF>(p, H, A, sigf2, lh0 + c0, h, n, y0_s + c0 * dim);
                 }
                 __syncthreads();
                 c0 += 1;
@@ -381,18 +566,22 @@ __global__ void __launch_bounds__(VB_ENT) k_engine(const __grid_constant__ Engin
             const int Tt = (int)(ex_s[c1] - base);
 
             // ---- phase 1: one thread per sample
-            for (int i = tid; i < Tt; i += NT) {
-                int lo = c0, hi = c1;
-                while (hi - lo > 1) {
-                    int mid = (lo + hi) >> 1;
-                    if ((int)(ex_s[mid] - base) <= i) lo = mid; else hi = mid;
-                }
-                const int c = lo;
-                const int k = i - (int)(ex_s[c] - base);
-                double w[NF];
-                src.sample(p, n_s[c], h0 + c, (uint32_t)k, chunk_row + base + i, y0_s + c * dim, w);
+            for (int ib = 0; ib < Tt; ib += NT) {                  // warp-uniform trip count
+                const int i = ib + tid;
+                if (i < Tt) {
+                    int lo = c0, hi = c1;
+                    while (hi - lo > 1) {
+                        int mid = (lo + hi) >> 1;
+                        if ((int)(ex_s[mid] - base) <= i) lo = mid; else hi = mid;
+                    }
+                    const int c = lo;
+                    const int k = i - (int)(ex_s[c] - base);
+                    double w[NF];
+                    src.sample(p, H, n_s[c], h0 + c, (uint32_t)k, chunk_row + base + i, y0_s + c * dim, w);
 #pragma unroll
-                for (int s = 0; s < NF; ++s) wf_s[(size_t)s * p.cap + i] = w[s];
+                    for (int s = 0; s < NF; ++s) wf_s[(size_t)s * p.cap + i] = w[s];
+                }
+                __syncwarp();                                      // lanes leave the histogram CAS loops at different times
             }
             __syncthreads();
 
@@ -418,7 +607,7 @@ __global__ void __launch_bounds__(VB_ENT) k_engine(const __grid_constant__ Engin
                         pass2_sample<NF>(w, m, correlate, sd, q);
                     }
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
-                    cube_epilogue<NF>(p, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
+                    cube_epilogue<NF>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
                 }
             }
             // ---- phase 2b: one warp per large cube
@@ -448,13 +637,15 @@ __global__ void __launch_bounds__(VB_ENT) k_engine(const __grid_constant__ Engin
                 for (int v = 0; v < NV; ++v) q[v] = warp_sum(q[v]);
                 if (lane == 0) {
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
-                    cube_epilogue<NF>(p, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
+                    cube_epilogue<NF>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
                 }
             }
             __syncthreads();
             c0 = c1;
         }
     }
+
+    if (p.wtot > 0) hist_flush<NT>(p, H, nullptr);               // the loop exits through a barrier
 
     // ---- per-CTA partial sums (fixed tree inside the CTA), finished by k_finalize in CTA order
     constexpr int NACC = NF + NV + 1;

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -52,6 +53,9 @@ struct DevBuf {
 struct vb200_ctx {
     int device = 0;
     int sm_count = 0;
+    size_t smem_per_sm = 0, smem_per_block_optin = 0;
+    int last_grid = 0, last_bps = 0, last_wtot = 0;      // geometry of the most recent engine launch
+    int64_t last_smem = 0;
     uint64_t seed = 0;
     PhiloxKey key;
     // map
@@ -96,6 +100,8 @@ extern "C" int vb200_create(vb200_ctx** out, int device)
     vb200_ctx* c = new vb200_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    c->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    c->smem_per_block_optin = prop.sharedMemPerBlockOptin;
     philox_make_key(0, c->key);
     memset(&c->map, 0, sizeof c->map);
     memset(&c->st, 0, sizeof c->st);
@@ -447,17 +453,69 @@ static int fill_engine(vb200_ctx* c, EngineP& p, uint32_t itn, double beta, int 
     return 0;
 }
 
-static void size_cfg(vb200_ctx* c, int nf, LaunchCfg& cfg)
+static int env_int(const char* name, int dflt)
 {
-    int cap = 4096;
-    const int lim = (64 * 1024) / (8 * nf);
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// shared memory of the engine kernel apart from the histogram windows
+static size_t base_smem(vb200_ctx* c, int nf, int cap)
+{
+    size_t b = sizeof(double) * (size_t)nf * cap + sizeof(long long) * (VB_CH + 1) + sizeof(int) * VB_CH +
+               sizeof(uint32_t) * (size_t)VB_CH * c->map.dim;
+    return (b + 15) & ~(size_t)15;
+}
+
+static void size_cfg(vb200_ctx* c, int nf, LaunchCfg& cfg, int wtot)
+{
+    int cap = env_int("VB200_CAP", 2048);
+    const int lim = (32 * 1024) / (8 * nf);
     if (cap > lim) cap = lim;
+    if (cap < 256) cap = 256;
     cfg.sm_count = c->sm_count;
     cfg.cap = cap;
-    cfg.smem = sizeof(double) * (size_t)nf * cap + sizeof(long long) * (VB_CH + 1) + sizeof(int) * VB_CH +
-               sizeof(uint32_t) * (size_t)VB_CH * c->map.dim;
+    cfg.smem = base_smem(c, nf, cap) + (sizeof(double) + sizeof(unsigned)) * (size_t)wtot;
     cfg.smem = (cfg.smem + 15) & ~(size_t)15;
     cfg.blocks_per_sm_out = 0;
+}
+
+// Windows of the training histogram kept in shared memory (engine.cuh, HistW).  On axis d a chunk
+// of VB_CH consecutive hypercubes spans at most `nd` strata; the window must hold their bins.
+// Axes are admitted smallest window first until `budget_bins` is used up (the others fall back to
+// global atomics); what is left upgrades partial windows to the full axis, fastest-running axis
+// first, so they are never flushed.
+static void plan_windows(vb200_ctx* c, EngineP& p, long long budget_bins)
+{
+    const int dim = c->map.dim;
+    p.wtot = 0;
+    for (int d = 0; d < VB_MAXD; ++d) { p.wcap[d] = 0; p.woff[d] = 0; }
+    if (!(p.flags & (VBF_TRAIN | VBF_TRAIN_ERRORS)) || budget_bins <= 0) return;
+    long long need[VB_MAXD];
+    int order[VB_MAXD];
+    for (int d = 0; d < dim; ++d) {
+        const long long ns = c->st.nstrat[d], ni = c->map.ninc[d], cs = c->cstride[d];
+        long long nd;
+        if (cs >= VB_CH) nd = (cs % VB_CH == 0) ? 1 : 2;
+        else nd = (VB_CH + cs - 1) / cs + ((VB_CH % cs == 0) ? 0 : 1);
+        need[d] = (nd >= ns) ? ni : (nd * ni + ns - 1) / ns + 1;
+        if (need[d] > ni) need[d] = ni;
+        order[d] = d;
+    }
+    for (int i = 1; i < dim; ++i)                                   // insertion sort by need (stable)
+        for (int j = i; j > 0 && need[order[j]] < need[order[j - 1]]; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+    long long used = 0;
+    for (int i = 0; i < dim; ++i) {
+        const int d = order[i];
+        if (used + need[d] <= budget_bins) { p.wcap[d] = (int)need[d]; used += need[d]; }
+    }
+    for (int d = 0; d < dim; ++d) {
+        const long long ni = c->map.ninc[d];
+        if (p.wcap[d] > 0 && p.wcap[d] < ni && used + (ni - p.wcap[d]) <= budget_bins) { used += ni - p.wcap[d]; p.wcap[d] = (int)ni; }
+    }
+    int off = 0;
+    for (int d = 0; d < dim; ++d) { p.woff[d] = off; off += p.wcap[d]; }
+    p.wtot = off;
 }
 
 typedef int (*launch_fn)(vb200_ctx*, const EngineP&, LaunchCfg&, int, cudaStream_t);
@@ -476,15 +534,36 @@ static int do_launch_fused(vb200_ctx* c, const EngineP& p, LaunchCfg& cfg, int m
 
 static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc, cudaStream_t st)
 {
-    LaunchCfg cfg;
-    size_cfg(c, nf, cfg);
-    p.cap = cfg.cap;
     const int64_t nch = p.chunk_end - p.chunk_begin;
     if (nch <= 0) return 0;
     const int max_grid = (int)(nch < 0x7fffffff ? nch : 0x7fffffff);
-    int grid = fused ? do_launch_fused(c, p, cfg, max_grid, VB_DRYRUN) : launch_buffer(p, nf, cfg, max_grid, VB_DRYRUN);
+    auto launch = [&](LaunchCfg& cfg, cudaStream_t s) {
+        return fused ? do_launch_fused(c, p, cfg, max_grid, s) : launch_buffer(p, nf, cfg, max_grid, s);
+    };
+    // pass 1: residency without the histogram windows (registers / staging buffer decide)
+    LaunchCfg cfg;
+    plan_windows(c, p, 0);
+    size_cfg(c, nf, cfg, 0);
+    p.cap = cfg.cap;
+    int grid = launch(cfg, VB_DRYRUN);
     if (grid == -22) return fail(-4, "engine: no kernel compiled for dim=%d nf=%d integrand=%d", p.map.dim, nf, c->fid);
     if (grid < 0) return fail(-2, "engine: occupancy query failed (%d)", grid);
+    // pass 2: give the windows the shared memory that this residency leaves unused
+    {
+        const int bps = cfg.blocks_per_sm_out > 0 ? cfg.blocks_per_sm_out : 1;
+        long long per_cta = (long long)c->smem_per_sm / bps - 1024;           // 1 KB reserved per CTA
+        if (per_cta > (long long)c->smem_per_block_optin) per_cta = (long long)c->smem_per_block_optin;
+        long long budget = (per_cta - (long long)cfg.smem - 64) / (long long)(sizeof(double) + sizeof(unsigned));
+        const int cap_bins = env_int("VB200_HIST_BINS", 1 << 30);
+        if (budget > cap_bins) budget = cap_bins;
+        plan_windows(c, p, budget);
+        if (p.wtot > 0) {
+            size_cfg(c, nf, cfg, p.wtot);
+            int g2 = launch(cfg, VB_DRYRUN);
+            if (g2 < 0) return fail(-2, "engine: occupancy query failed (%d)", g2);
+            grid = g2;
+        }
+    }
     const int nacc = nf + nf * (nf + 1) / 2 + 1;
     CK(c->partials.ensure(sizeof(double) * (size_t)grid * nacc));
     p.partials = (double*)c->partials.p;
@@ -496,8 +575,9 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     CK(c->counter.ensure(sizeof(unsigned long long)));
     CK(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), st));
     p.work_counter = (unsigned long long*)c->counter.p;
-    int g2 = fused ? do_launch_fused(c, p, cfg, max_grid, st) : launch_buffer(p, nf, cfg, max_grid, st);
+    int g2 = launch(cfg, st);
     if (g2 < 0) return fail(-2, "engine: launch failed (%d: %s)", g2, cudaGetErrorString((cudaError_t)(-(g2 + 1000))));
+    c->last_grid = g2; c->last_bps = cfg.blocks_per_sm_out; c->last_smem = (int64_t)cfg.smem; c->last_wtot = p.wtot;
     k_finalize<<<1, 64, 0, st>>>(p.partials, g2, nacc, acc);
     c->launches += 2;
     CK(cudaGetLastError());
@@ -813,6 +893,13 @@ extern "C" int vb200_add_training_data(vb200_ctx* c, const double* y, const doub
 }
 
 extern "C" int64_t vb200_launch_count(vb200_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int vb200_last_launch(vb200_ctx* c, int64_t out[4])
+{
+    if (!c || !out) return fail(-1, "vb200_last_launch: null argument");
+    out[0] = c->last_grid; out[1] = c->last_bps; out[2] = c->last_smem; out[3] = c->last_wtot;
+    return 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // FP64 FMA throughput probe (the roofline denominator for the fused kernel)
