@@ -121,8 +121,8 @@ int  vb200_uniforms(vb200_ctx* ctx, uint32_t itn, int64_t chunk_begin, int64_t c
 int     vb200_fp64_peak(int device, int iters, double* tflops_out, double* ms_out);
 int64_t vb200_launch_count(vb200_ctx* ctx);
 /* geometry of the most recent engine launch: {CTAs, CTAs per SM, dynamic shared memory bytes per
- * CTA, bins of the shared-memory training-histogram windows} */
-int     vb200_last_launch(vb200_ctx* ctx, int64_t out[4]);
+ * CTA, bins of the shared-memory training-histogram windows, threads per CTA, hypercubes per chunk} */
+int     vb200_last_launch(vb200_ctx* ctx, int64_t out[6]);
 
 #ifdef __cplusplus
 }

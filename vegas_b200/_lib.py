@@ -212,9 +212,10 @@ class Context(object):
 
     def last_launch(self):
         """geometry of the most recent engine launch"""
-        out = (ctypes.c_int64 * 4)()
+        out = (ctypes.c_int64 * 6)()
         check(self.L.vb200_last_launch(self.h, out))
-        return dict(grid=out[0], ctas_per_sm=out[1], smem_bytes=out[2], hist_window_bins=out[3])
+        return dict(grid=out[0], ctas_per_sm=out[1], smem_bytes=out[2], window_bins=out[3], threads=out[4],
+                    chunk_cubes=out[5])
 
 
 def map_adapt(grid, ninc, sum_f, n_f, alpha, new_ninc):

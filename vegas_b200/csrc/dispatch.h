@@ -1,52 +1,146 @@
 // dispatch.h -- launchers of the templated engine kernel, one translation unit per integrand
 // family so the instantiations compile in parallel.
 #pragma once
+#include <stdlib.h>
+
 #include "engine.cuh"
 #include "integrands.cuh"
 
-// Each launcher picks the instantiation for the padded dimension D >= dim, sizes the persistent
-// grid from the occupancy calculator, launches on `stream` and returns the grid size (>0) or a
-// negative error.  `functor` points to the host copy of the family's functor struct.
+// Each launcher picks the instantiation for the padded dimension D >= dim (and the light or heavy
+// geometry), sizes shared memory, histogram windows and the persistent grid for it, launches on
+// `stream` and returns the grid size (>0) or a negative error.  `functor` points to the host copy
+// of the family's functor struct.
 struct LaunchCfg {
+    // in
     int sm_count;
-    int cap;          // staged samples per tile
-    size_t smem;      // dynamic shared memory bytes
-    int blocks_per_sm_out;
+    size_t smem_per_sm, smem_optin;   // device limits
+    bool light;                       // use the one-big-CTA-per-SM geometry (fused sources only)
+    // out
+    int nt, ch;                       // CTA size and cubes per chunk of the chosen instantiation
+    int cap;                          // staged samples per tile
+    size_t smem;                      // dynamic shared memory bytes
+    int blocks_per_sm;
+    int wtot;                         // bins of the shared-memory histogram windows
+    int64_t nchunks;                  // chunks of `ch` cubes in the launch
 };
 
-int launch_fused_poly(const EngineP& p, const void* functor, LaunchCfg& cfg, int max_grid, cudaStream_t st);
-int launch_fused_gaussmix(const EngineP& p, const void* functor, LaunchCfg& cfg, int max_grid, cudaStream_t st);
-int launch_fused_ridge(const EngineP& p, const void* functor, LaunchCfg& cfg, int max_grid, cudaStream_t st);
-int launch_fused_genz(const EngineP& p, const void* functor, LaunchCfg& cfg, int max_grid, cudaStream_t st);
-int launch_fused_pathint(const EngineP& p, const void* functor, int nx0, LaunchCfg& cfg, int max_grid, cudaStream_t st);
-int launch_buffer(const EngineP& p, int nf, LaunchCfg& cfg, int max_grid, cudaStream_t st);
+int launch_fused_poly(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st);
+int launch_fused_gaussmix(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st);
+int launch_fused_ridge(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st);
+int launch_fused_genz(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st);
+int launch_fused_pathint(const EngineP& p, const void* functor, int nx0, LaunchCfg& cfg, cudaStream_t st);
+int launch_buffer(const EngineP& p, int nf, LaunchCfg& cfg, cudaStream_t st);
 
-// dry-run variants: only compute the grid size (blocks/SM * SMs) so the caller can size scratch
-// before the real launch.  Implemented by passing st == (cudaStream_t)-1.
+// dry-run variants: only compute the geometry (cfg outputs, grid size) so the caller can size
+// scratch before the real launch.  Implemented by passing st == (cudaStream_t)-1.
 #define VB_DRYRUN ((cudaStream_t)(intptr_t)-1)
 
-template <class Src>
-static int launch_engine(const EngineP& p, const Src& src, LaunchCfg& cfg, int max_grid, cudaStream_t st)
+static inline int vb_env_int(const char* name, int dflt)
 {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// Windows of the training histogram (and, for GRIDW sources, of the map's grid) kept in shared
+// memory (engine.cuh, HistW).  On axis d a chunk of `ch` consecutive hypercubes spans at most `nd`
+// strata; the window must hold their bins.  Axes are admitted smallest window first until
+// `budget_bins` is used up (the others fall back to global memory); what is left upgrades partial
+// windows to the full axis, fastest-running axis first, so they are never flushed.
+static inline void vb_plan_windows(EngineP& p, int ch, long long budget_bins, bool always)
+{
+    const int dim = p.map.dim;
+    p.wtot = 0;
+    for (int d = 0; d < VB_MAXD; ++d) { p.wcap[d] = 0; p.woff[d] = 0; }
+    if ((!always && !(p.flags & (VBF_TRAIN | VBF_TRAIN_ERRORS))) || budget_bins <= 0) return;
+    long long need[VB_MAXD];
+    int order[VB_MAXD];
+    for (int d = 0; d < dim; ++d) {
+        const long long ns = p.st.nstrat[d], ni = p.map.ninc[d], cs = p.cstride[d];
+        long long nd;
+        if (cs >= ch) nd = (cs % ch == 0) ? 1 : 2;
+        else nd = (ch + cs - 1) / cs + ((ch % cs == 0) ? 0 : 1);
+        need[d] = (nd >= ns) ? ni : (nd * ni + ns - 1) / ns + 1;
+        if (need[d] > ni) need[d] = ni;
+        order[d] = d;
+    }
+    for (int i = 1; i < dim; ++i)                                   // insertion sort by need (stable)
+        for (int j = i; j > 0 && need[order[j]] < need[order[j - 1]]; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+    long long used = 0;
+    for (int i = 0; i < dim; ++i) {
+        const int d = order[i];
+        if (used + need[d] <= budget_bins) { p.wcap[d] = (int)need[d]; used += need[d]; }
+    }
+    for (int d = 0; d < dim; ++d) {
+        const long long ni = p.map.ninc[d];
+        if (p.wcap[d] > 0 && p.wcap[d] < ni && used + (ni - p.wcap[d]) <= budget_bins) { used += ni - p.wcap[d]; p.wcap[d] = (int)ni; }
+    }
+    int off = 0;
+    for (int d = 0; d < dim; ++d) { p.woff[d] = off; off += p.wcap[d]; }
+    p.wtot = off;
+}
+
+template <class Src>
+static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cudaStream_t st)
+{
+    constexpr int NF = Src::NF, NT = Src::NT, CH = Src::CH;
+    constexpr int DIGB = (int)sizeof(typename Src::dig_t);
     auto kern = k_engine<Src>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    EngineP p = p_in;
+    const int dim = p.map.dim;
+    cfg.nt = NT; cfg.ch = CH;
+    // staging capacity: ~16 samples per thread, at most 32 KB (heavy) / 64 KB (light)
+    int cap = vb_env_int(CH == VB_CH ? "VB200_CAP" : "VB200_LCAP", 16 * NT);
+    const int lim = ((CH == VB_CH ? 32 : 64) * 1024) / (8 * NF);
+    if (cap > lim) cap = lim;
+    if (cap < 256) cap = 256;
+    cfg.cap = p.cap = cap;
+    if (CH != VB_CH) {
+        // super-chunks: only whole-range launches (the fused path); slabs must be whole chunks
+        if (p.chunk_begin != 0 || p.chunk_off != nullptr) return -23;
+        if (p.st.world > 1 && p.st.slab % CH != 0) return -23;
+        p.chunk_end = (p.st.nlocal + CH - 1) / CH;
+    }
+    cfg.nchunks = p.chunk_end - p.chunk_begin;
+    const int max_grid = (int)(cfg.nchunks < 0x7fffffff ? cfg.nchunks : 0x7fffffff);
+    // pass 1: residency without the windows (registers / staging buffer decide)
+    vb_plan_windows(p, CH, 0, false);
+    size_t smem0 = engine_smem_bytes(NF, cap, CH, dim, 0, Src::GRIDW, DIGB);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    const long long dyn_max = (long long)cfg.smem_optin - (long long)fa.sharedSizeBytes;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max);
     if (e != cudaSuccess) return -(int)e - 1000;
     int bps = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, VB_ENT, cfg.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, NT, smem0);
     if (e != cudaSuccess) return -(int)e - 1000;
-    if (bps < 1) bps = 1;
-    cfg.blocks_per_sm_out = bps;
+    if (bps < 1) return -24;                                        // does not fit at all
+    // pass 2: give the windows the shared memory that this residency leaves unused
+    long long per_cta = (long long)cfg.smem_per_sm / bps - 1024;    // 1 KB reserved per CTA
+    per_cta -= (long long)fa.sharedSizeBytes;
+    if (per_cta > dyn_max) per_cta = dyn_max;
+    const long long per_bin = sizeof(double) + sizeof(unsigned) + (Src::GRIDW ? sizeof(double) : 0);
+    long long budget = (per_cta - (long long)smem0 - 256) / per_bin;
+    const int cap_bins = vb_env_int("VB200_HIST_BINS", 1 << 30);
+    if (budget > cap_bins) budget = cap_bins;
+    vb_plan_windows(p, CH, budget, Src::GRIDW);
+    cfg.wtot = p.wtot;
+    cfg.smem = engine_smem_bytes(NF, cap, CH, dim, p.wtot, Src::GRIDW, DIGB);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, NT, cfg.smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    if (bps < 1) return -24;
+    cfg.blocks_per_sm = bps;
     int grid = bps * cfg.sm_count;
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     if (st == VB_DRYRUN) return grid;
-    kern<<<grid, VB_ENT, cfg.smem, st>>>(p, src);
+    kern<<<grid, NT, cfg.smem, st>>>(p, src);
     e = cudaGetLastError();
     if (e != cudaSuccess) return -(int)e - 1000;
     return grid;
 }
 
-// padded-dimension dispatch
+// padded-dimension dispatch; light geometry first when asked for and compiled in
 #define VB_DISPATCH_D(F, fobj, LIST_MACRO)                                                     \
     do {                                                                                       \
         const int dim_ = p.map.dim;                                                            \
@@ -54,4 +148,6 @@ static int launch_engine(const EngineP& p, const Src& src, LaunchCfg& cfg, int m
         return -22;                                                                            \
     } while (0)
 #define VB_CASE_D(F, fobj, DD)                                                                 \
-    if (dim_ <= DD) { FusedSrc<F, DD> s_{fobj}; return launch_engine(p, s_, cfg, max_grid, st); }
+    if (dim_ <= DD) { FusedSrc<F, DD> s_{fobj}; return launch_engine(p, s_, cfg, st); }
+#define VB_CASE_L(F, fobj, DD)                                                                 \
+    if (cfg.light && dim_ <= DD) { FusedSrc<F, DD, true> s_{fobj}; return launch_engine(p, s_, cfg, st); }

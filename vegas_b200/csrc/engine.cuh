@@ -14,6 +14,7 @@
 // Reference: Integrator._random_batch (_vegas.pyx:1692-1759) + Integrator.__call__
 // (_vegas.pyx:2136-2197).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 #define VBF_UPDATE_SIGF   1   // adaptive stratification: write sigf, accumulate sum_sigf
@@ -46,6 +47,7 @@ struct EngineP {
     int wcap[VB_MAXD];         // bins of axis d's window
     int woff[VB_MAXD];         // offset of axis d's window in the shared arrays
     int wtot;                  // total window bins (0: no shared histogram)
+    double dni[VB_MAXD];       // (double) map.ninc[d]
     // unfused path
     const double* fbuf;        // [rows][nf]
     const double* wbuf;        // [rows]
@@ -80,12 +82,17 @@ __device__ __forceinline__ int bin_floor(const EngineP& p, int d, int digit)
 // window per axis, [lo[d], lo[d] + wcap[d]), and flushes it to the global histogram with fp64 /
 // u64 atomics only when a newly claimed chunk needs a different window.  Bins outside the window
 // (axes whose window did not fit, chunks that wrap around an axis) go straight to global memory.
+extern __shared__ double vb_smem[];        // dynamic shared memory of the engine kernel
+static __shared__ int vb_wlo_s[VB_MAXD];   // first bin of the current window of each axis
+// (file-scope declarations so that every access compiles to LDS / ATOMS: through generic pointers
+//  carried in a struct the compiler falls back to generic loads and the slower generic ATOM forms)
+
 struct HistW {
     double* sum;        // [wtot]
     unsigned* cnt;      // [wtot]
-    const int* lo;      // [dim] first bin of the current window
-    uint32_t sum_sa;    // the same arrays as shared-state-space addresses (explicit .shared atomics:
-    uint32_t cnt_sa;    //  through generic pointers the compiler emits the slower generic ATOM forms)
+    int gw_off;         // index in vb_smem of the windows' grid nodes: axis d at gw_off + woff[d] + d .. + wcap[d] (GRIDW sources)
+    uint32_t sum_sa;    // sum / cnt as shared-state-space addresses for the explicit .shared atomics
+    uint32_t cnt_sa;
 };
 
 #define VB_NO_SLOT 0xffffffffu
@@ -104,13 +111,26 @@ __device__ __forceinline__ void hist_global(const EngineP& p, int d, int bin, do
 __device__ __forceinline__ uint32_t hist_slot(const EngineP& p, const HistW& H, int d, int bin, double v)
 {
     if (bin < 0) return VB_NO_SLOT;
-    const unsigned r = (unsigned)(bin - H.lo[d]);
+    const unsigned r = (unsigned)(bin - vb_wlo_s[d]);
     if (r < (unsigned)p.wcap[d]) {
         const unsigned i = (unsigned)p.woff[d] + r;
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(H.cnt_sa + 4u * i) : "memory");
         return H.sum_sa + 8u * i;
     }
     hist_global(p, d, bin, v);
+    return VB_NO_SLOT;
+}
+
+// same for the code FusedSrc::sample keeps per axis: r < 2^31: slot r of the axis' window;
+// VB_NO_SLOT: no training point (y on the boundary); else 2^31 | bin for the global histogram
+__device__ __forceinline__ uint32_t hist_slot_code(const EngineP& p, const HistW& H, int d, unsigned code, double v)
+{
+    if (code < 0x80000000u) {
+        const unsigned i = (unsigned)p.woff[d] + code;
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(H.cnt_sa + 4u * i) : "memory");
+        return H.sum_sa + 8u * i;
+    }
+    if (code != VB_NO_SLOT) hist_global(p, d, (int)(code & 0x7fffffffu), v);
     return VB_NO_SLOT;
 }
 
@@ -157,7 +177,7 @@ __device__ __forceinline__ void hist_add(const EngineP& p, const HistW& H, int d
 {
 #ifdef VB_HIST_GENERIC
     if (bin >= 0) {
-        const unsigned r = (unsigned)(bin - H.lo[d]);
+        const unsigned r = (unsigned)(bin - vb_wlo_s[d]);
         if (r < (unsigned)p.wcap[d]) {
             atomicAdd(H.sum + p.woff[d] + r, v);
             atomicAdd(H.cnt + p.woff[d] + r, 1u);
@@ -177,7 +197,7 @@ __device__ __forceinline__ void hist_flush(const EngineP& p, const HistW& H, con
     for (int d = 0; d < p.map.dim; ++d) {
         const int cap = p.wcap[d];
         if (cap == 0 || (need && !need[d])) continue;
-        const int lo = H.lo[d], off = p.woff[d];
+        const int lo = vb_wlo_s[d], off = p.woff[d];
         for (int i = threadIdx.x; i < cap; i += NT) {
             const unsigned c = H.cnt[off + i];
             if (c) {
@@ -191,8 +211,9 @@ __device__ __forceinline__ void hist_flush(const EngineP& p, const HistW& H, con
 }
 
 // training point of a whole cube (adapt_to_errors, _vegas.pyx:2187-2193): y of its LAST sample
+template <class dig_t>
 static __device__ __noinline__ void train_cube(const EngineP& p, const HistW& H, int64_t h, uint32_t klast,
-                                               const uint32_t* y0, double v)
+                                               const dig_t* y0, double v)
 {
     for (int pr = 0; 2 * pr < p.map.dim; ++pr) {
         double ua, ub;
@@ -207,17 +228,34 @@ static __device__ __noinline__ void train_cube(const EngineP& p, const HistW& H,
 // sample sources
 // ---------------------------------------------------------------------------------------------
 // Fused: everything from the Philox counter to w*f happens in registers.
-template <class F, int D>
+// Two geometries:
+//   heavy (LIGHT = false): 128-thread CTAs, several per SM, 256-cube chunks, wide register budget --
+//                          for integrands whose own loop dominates (the N = 1000 ridge);
+//   light (LIGHT = true):  ONE big CTA per SM (VB_LNT threads, VB_LCH-cube chunks) so that all warps
+//                          of the SM share one set of histogram windows AND a shared-memory copy of
+//                          the map's grid nodes for those windows -- for cheap integrands, where the
+//                          sampler itself is the work and occupancy / smem locality decide.
+#ifndef VB_LNT
+#define VB_LNT 640
+#endif
+#ifndef VB_LCH
+#define VB_LCH 1280
+#endif
+template <class F, int D, bool LIGHT = false>
 struct FusedSrc {
     static constexpr int NF = F::NF;
-    static constexpr int MINB = (D <= 10 && F::NF == 1) ? 3 : 2;                  // resident CTAs per SM the register budget is set for
+    static constexpr int NT = LIGHT ? VB_LNT : VB_ENT;             // threads per CTA
+    static constexpr int CH = LIGHT ? VB_LCH : VB_CH;              // hypercubes per chunk
+    static constexpr int MINB = LIGHT ? 1 : ((D <= 10 && F::NF == 1) ? 3 : 2);   // resident CTAs per SM the register budget is set for
+    static constexpr bool GRIDW = LIGHT;                           // grid windows in shared memory
+    typedef typename std::conditional<LIGHT, uint16_t, uint32_t>::type dig_t;   // stratum digits of a cube
     F f;
     __device__ __forceinline__ void sample(const EngineP& p, const HistW& H, int n, int64_t h, uint32_t k,
-                                           int64_t /*row*/, const uint32_t* y0, double (&wf)[NF]) const
+                                           int64_t /*row*/, const dig_t* y0, double (&wf)[NF]) const
     {
         const int dim = p.map.dim;
         double x[D];
-        int bin[D];
+        unsigned code[D];     // training slot of axis d, see hist_slot_code
         double jac = 1.0;
 #pragma unroll
         for (int pr = 0; pr < (D + 1) / 2; ++pr) {
@@ -228,19 +266,26 @@ struct FusedSrc {
                 for (int e = 0; e < 2; ++e) {
                     const int d = 2 * pr + e;
                     if (d < D && d < dim) {
-                        // branch-free so that the grid loads of all axes are in flight together
                         const int ni = p.map.ninc[d];
-                        const double* g = p.map.grid + (size_t)d * p.map.gstride;
                         const double y = div_exact((double)y0[d] + u[e], p.st.dns[d], p.st.rns[d]);
-                        const double t = __dmul_rn(y, (double)ni);
+                        const double t = __dmul_rn(y, p.dni[d]);
                         const int iy = __double2int_rd(t);
                         const int ic = min(iy, ni - 1);
-                        const double g0 = __ldg(g + ic), g1 = __ldg(g + ic + 1);
+                        const unsigned r = (unsigned)(ic - vb_wlo_s[d]);
+                        const bool inw = r < (unsigned)p.wcap[d];
+                        const double* gp = p.map.grid + (size_t)d * p.map.gstride + ic;
+                        double g0, g1;
+                        if (GRIDW && __builtin_expect(inw, 1)) {
+                            const double* w = vb_smem + (H.gw_off + p.woff[d] + d) + r;
+                            g0 = w[0]; g1 = w[1];
+                        } else {
+                            g0 = __ldg(gp); g1 = __ldg(gp + 1);
+                        }
                         const double inc = g1 - g0;
                         const double xin = __dadd_rn(g0, __dmul_rn(inc, __dsub_rn(t, (double)iy)));   // no FMA: bit-identical to pyx:354
                         x[d] = iy < ni ? xin : g1;                                                     // pyx:357-359
-                        jac *= inc * (double)ni;
-                        bin[d] = (y > 0.0 && y < 1.0) ? ic : -1;                                      // pyx:460
+                        jac *= inc * p.dni[d];
+                        code[d] = !(y > 0.0 && y < 1.0) ? VB_NO_SLOT : (inw ? r : (0x80000000u | (unsigned)ic));   // pyx:460
                     }
                 }
             }
@@ -256,21 +301,16 @@ struct FusedSrc {
             double a = wf[0] * (double)n;
             double fdv2 = a * a;
             constexpr int G = VB_HIST_GROUP;                      // axes whose CAS loops run side by side
-#ifdef VB_HIST_GENERIC
-#pragma unroll
-            for (int d = 0; d < D; ++d) if (d < dim) hist_add(p, H, d, bin[d], fdv2);
-#else
 #pragma unroll
             for (int d0 = 0; d0 < D; d0 += G) {
                 if (d0 < dim) {
                     uint32_t sa[G];
 #pragma unroll
                     for (int j = 0; j < G; ++j)
-                        sa[j] = (d0 + j < D && d0 + j < dim) ? hist_slot(p, H, d0 + j, bin[d0 + j < D ? d0 + j : 0], fdv2) : VB_NO_SLOT;
+                        sa[j] = (d0 + j < D && d0 + j < dim) ? hist_slot_code(p, H, d0 + j, code[d0 + j < D ? d0 + j : 0], fdv2) : VB_NO_SLOT;
                     hist_sum_slots<G>(sa, fdv2);
                 }
             }
-#endif
         }
     }
 };
@@ -280,9 +320,12 @@ struct FusedSrc {
 template <int NF_>
 struct BufferSrc {
     static constexpr int NF = NF_;
+    static constexpr int NT = VB_ENT, CH = VB_CH;
     static constexpr int MINB = NF_ <= 4 ? 4 : 3;
+    static constexpr bool GRIDW = false;
+    typedef uint32_t dig_t;
     __device__ __forceinline__ void sample(const EngineP& p, const HistW& H, int n, int64_t h, uint32_t k,
-                                           int64_t row, const uint32_t* y0, double (&wf)[NF]) const
+                                           int64_t row, const dig_t* y0, double (&wf)[NF]) const
     {
         double wgt = p.wbuf[row];
         bool bad = false;
@@ -370,9 +413,9 @@ __device__ __forceinline__ double cube_finish(CubeAcc<NF>& A, int n, const doubl
     return fabs((dn * q[0] - sd[0] * sd[0]) / dn1);
 }
 
-template <int NF>
+template <int NF, class dig_t>
 __device__ __forceinline__ void cube_epilogue(const EngineP& p, const HistW& H, CubeAcc<NF>& A, double sigf2,
-                                              int64_t lh, int64_t h, int n, const uint32_t* y0)
+                                              int64_t lh, int64_t h, int n, const dig_t* y0)
 {
     if (p.flags & VBF_UPDATE_SIGF) {
         double sg = pow(sigf2, p.beta_half);
@@ -385,47 +428,56 @@ __device__ __forceinline__ void cube_epilogue(const EngineP& p, const HistW& H, 
 // ---------------------------------------------------------------------------------------------
 // the engine kernel
 // ---------------------------------------------------------------------------------------------
-#ifdef VB_NO_MINB
-#define VB_LB __launch_bounds__(VB_ENT)
-#elif defined(VB_FORCE_MINB)
-#define VB_LB __launch_bounds__(VB_ENT, VB_FORCE_MINB)
-#else
-#define VB_LB __launch_bounds__(VB_ENT, Src::MINB)
-#endif
-template <class Src>
-__global__ void VB_LB k_engine(const __grid_constant__ EngineP p, const __grid_constant__ Src src)
+// dynamic shared memory of k_engine<Src> (the host sizes the launch with the same function)
+__host__ __device__ inline size_t engine_smem_bytes(int nf, int cap, int ch, int dim, int wtot, bool gridw, int digbytes)
 {
+    size_t b = sizeof(double) * (size_t)nf * cap            // wf_s   staged w*f
+             + sizeof(long long) * (size_t)(ch + 1)         // ex_s   exclusive scan of the cubes' sample counts
+             + sizeof(double) * (size_t)wtot                // H.sum
+             + (gridw ? sizeof(double) * (size_t)(wtot + dim) : 0)   // grid nodes of the windows
+             + sizeof(int) * (size_t)ch                     // n_s
+             + sizeof(unsigned) * (size_t)wtot              // H.cnt
+             + (size_t)digbytes * ch * dim;                 // y0_s   stratum digits
+    return (b + 15) & ~(size_t)15;
+}
+
+template <class Src>
+__global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_constant__ EngineP p, const __grid_constant__ Src src)
+{
+    typedef typename Src::dig_t dig_t;
     constexpr int NF = Src::NF;
     constexpr int NV = NF * (NF + 1) / 2;
-    constexpr int NT = VB_ENT;
+    constexpr int NT = Src::NT;
+    constexpr int CH = Src::CH;
     constexpr int NW = NT / 32;
-    constexpr int CPT = VB_CH / NT;                               // cubes per thread in set-up
-    static_assert(VB_CH % NT == 0, "chunk must be a multiple of the CTA size");
-    extern __shared__ double smem[];
-    double* wf_s = smem;                                          // [NF][cap]
-    long long* ex_s = (long long*)(wf_s + (size_t)NF * p.cap);    // [VB_CH + 1]
-    int* n_s = (int*)(ex_s + VB_CH + 1);                          // [VB_CH]
-    uint32_t* y0_s = (uint32_t*)(n_s + VB_CH);                    // [VB_CH][dim]
+    constexpr int CPT = CH / NT;                                  // cubes per thread in set-up
+    static_assert(CH % NT == 0 && CH % VB_CH == 0, "chunk must be a multiple of the CTA size and of the ABI chunk");
+    double* wf_s = vb_smem;                                       // [NF][cap]
+    long long* ex_s = (long long*)(wf_s + (size_t)NF * p.cap);    // [CH + 1]
+    HistW H;
+    H.sum = (double*)(ex_s + CH + 1);                             // [wtot]
+    double* gw_s = H.sum + p.wtot;                                // [wtot + dim] (GRIDW)
+    int* n_s = (int*)(gw_s + (Src::GRIDW ? p.wtot + p.map.dim : 0));   // [CH]
+    H.cnt = (unsigned*)(n_s + CH);                                // [wtot]
+    dig_t* y0_s = (dig_t*)(H.cnt + p.wtot);                       // [CH][dim]
     __shared__ long long scan_s[NW];
     __shared__ double red_s[NW];
     __shared__ double bc_s[NF];
     __shared__ uint32_t base_s[VB_MAXD];
     __shared__ long long next_s;
-    __shared__ int wlo_s[VB_MAXD], wnew_s[VB_MAXD], wneed_s[VB_MAXD];
+    __shared__ int wnew_s[VB_MAXD], wneed_s[VB_MAXD];
+    int* const wlo_s = vb_wlo_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int dim = p.map.dim;
     const bool correlate = (p.flags & VBF_CORRELATE) != 0;
     CubeAcc<NF> A;
     A.clear();
-    HistW H;
-    H.sum = (double*)(y0_s + (size_t)VB_CH * dim);                // [wtot]   (8-byte aligned: VB_CH*dim*4)
-    H.cnt = (unsigned*)(H.sum + p.wtot);                          // [wtot]
-    H.lo = wlo_s;
+    H.gw_off = (int)(gw_s - vb_smem);
     H.sum_sa = (uint32_t)__cvta_generic_to_shared(H.sum);
     H.cnt_sa = (uint32_t)__cvta_generic_to_shared(H.cnt);
     for (int i = tid; i < p.wtot; i += NT) { H.sum[i] = 0.0; H.cnt[i] = 0u; }
-    if (tid < VB_MAXD) wlo_s[tid] = 0;
+    if (tid < VB_MAXD) wlo_s[tid] = -0x40000000;                   // no window yet: the first chunk installs them
     long long since_flush = 0;                                    // samples added since the last full flush
 
     // chunks are claimed dynamically (one atomic per chunk) so that CTAs finish together
@@ -435,16 +487,16 @@ __global__ void VB_LB k_engine(const __grid_constant__ EngineP p, const __grid_c
         __syncthreads();
         const int64_t lc = next_s;
         if (lc >= p.chunk_end) break;
-        const int64_t lh0 = lc * VB_CH;
+        const int64_t lh0 = lc * CH;
         const int64_t h0 = local_to_global(p.st, lh0);
         if (p.wtot > 0) {
-            // ---- move the histogram windows to this chunk's strata (flush the ones that change)
+            // ---- move the windows to this chunk's strata (flush the histogram of the ones that change)
             const bool force = since_flush > 0x40000000LL;         // keep the u32 counts far from overflow
             if (tid < dim) {
                 const int d = tid;
                 int need = 0, lo_bin = 0;
                 if (p.wcap[d] > 0) {
-                    const int64_t a = h0 / p.cstride[d], b = (h0 + VB_CH - 1) / p.cstride[d];
+                    const int64_t a = h0 / p.cstride[d], b = (h0 + CH - 1) / p.cstride[d];
                     const int64_t ns = p.st.nstrat[d];
                     int dlo = 0, dhi = (int)ns - 1;
                     if (b - a + 1 < ns) {
@@ -465,6 +517,16 @@ __global__ void VB_LB k_engine(const __grid_constant__ EngineP p, const __grid_c
             hist_flush<NT>(p, H, wneed_s);
             __syncthreads();
             if (tid < dim && wneed_s[tid]) wlo_s[tid] = wnew_s[tid];
+            if (Src::GRIDW) {
+                // grid nodes lo .. lo + wcap of the moved windows (nodes past the axis end repeat the last one)
+                for (int d = 0; d < dim; ++d) {
+                    if (!wneed_s[d]) continue;
+                    const int lo = wnew_s[d], ni = p.map.ninc[d];
+                    const double* g = p.map.grid + (size_t)d * p.map.gstride;
+                    double* w = gw_s + p.woff[d] + d;
+                    for (int i = tid; i <= p.wcap[d]; i += NT) w[i] = __ldg(g + min(lo + i, ni));
+                }
+            }
             if (force) since_flush = 0;
         }
         if (tid < dim) base_s[tid] = (uint32_t)((h0 / p.cstride[tid]) % p.st.nstrat[tid]);
@@ -489,24 +551,24 @@ __global__ void VB_LB k_engine(const __grid_constant__ EngineP p, const __grid_c
             for (int d = 0; d < dim; ++d) {
                 uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
                 uint32_t qd = v / ns;
-                y0_s[c * dim + d] = v - qd * ns;
+                y0_s[c * dim + d] = (dig_t)(v - qd * ns);
                 carry = qd;
             }
         }
-        if (tid == NT - 1) ex_s[VB_CH] = total;
+        if (tid == NT - 1) ex_s[CH] = total;
         since_flush += total;
         __syncthreads();
         const int64_t chunk_row = p.chunk_off ? p.chunk_off[lc] - p.row0 : 0;
 
         int c0 = 0;
-        while (c0 < VB_CH) {
+        while (c0 < CH) {
             const long long base = ex_s[c0];
             if (base >= total) break;                              // only empty cubes remain
             // c1 = one past the last cube whose samples still fit the staging buffer (all threads
             // search the same shared array: broadcast reads, no barrier)
             int c1;
             {
-                int lo = c0, hi = VB_CH + 1;                       // ex_s[lo]-base <= cap < ex_s[hi]-base (virtual)
+                int lo = c0, hi = CH + 1;                       // ex_s[lo]-base <= cap < ex_s[hi]-base (virtual)
                 while (hi - lo > 1) {
                     int mid = (lo + hi) >> 1;
                     if (ex_s[mid] - base <= (long long)p.cap) lo = mid; else hi = mid;
@@ -557,7 +619,7 @@ __global__ void VB_LB k_engine(const __grid_constant__ EngineP p, const __grid_c
                 for (int v = 0; v < NV; ++v) q[v] = block_sum<NT>(q[v], red_s);
                 if (tid == 0) {
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
-                    cube_epilogue<NF>(p, H, A, sigf2, lh0 + c0, h, n, y0_s + c0 * dim);
+                    cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c0, h, n, y0_s + c0 * dim);
                 }
                 __syncthreads();
                 c0 += 1;
@@ -607,7 +669,7 @@ __global__ void VB_LB k_engine(const __grid_constant__ EngineP p, const __grid_c
                         pass2_sample<NF>(w, m, correlate, sd, q);
                     }
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
-                    cube_epilogue<NF>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
+                    cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
                 }
             }
             // ---- phase 2b: one warp per large cube
@@ -637,7 +699,7 @@ __global__ void VB_LB k_engine(const __grid_constant__ EngineP p, const __grid_c
                 for (int v = 0; v < NV; ++v) q[v] = warp_sum(q[v]);
                 if (lane == 0) {
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
-                    cube_epilogue<NF>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
+                    cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
                 }
             }
             __syncthreads();

@@ -1,10 +1,10 @@
-// fused_gaussmix.cu -- engine instantiations for the FGaussMix device functor.
+// fused_gaussmix.cu -- engine instantiations for the FGaussMix device functor (heavy geometry).
 #include "dispatch.h"
 
 #define LIST_(F, f) VB_CASE_D(F, f, 2) VB_CASE_D(F, f, 4) VB_CASE_D(F, f, 6) VB_CASE_D(F, f, 8) \
     VB_CASE_D(F, f, 10) VB_CASE_D(F, f, 12) VB_CASE_D(F, f, 16) VB_CASE_D(F, f, 20)
 
-int launch_fused_gaussmix(const EngineP& p, const void* functor, LaunchCfg& cfg, int max_grid, cudaStream_t st)
+int launch_fused_gaussmix_heavy(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st)
 {
     const FGaussMix& f = *(const FGaussMix*)functor;
     VB_DISPATCH_D(FGaussMix, f, LIST_);

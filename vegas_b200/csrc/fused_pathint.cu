@@ -4,17 +4,17 @@
 #define LIST_(F, f) VB_CASE_D(F, f, 8) VB_CASE_D(F, f, 10) VB_CASE_D(F, f, 12) VB_CASE_D(F, f, 16)
 
 template <int NX0>
-static int launch_nx0(const EngineP& p, const void* functor, LaunchCfg& cfg, int max_grid, cudaStream_t st)
+static int launch_nx0(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st)
 {
     const FPathInt<NX0>& f = *(const FPathInt<NX0>*)functor;
     VB_DISPATCH_D(FPathInt<NX0>, f, LIST_);
 }
 
-int launch_fused_pathint(const EngineP& p, const void* functor, int nx0, LaunchCfg& cfg, int max_grid, cudaStream_t st)
+int launch_fused_pathint(const EngineP& p, const void* functor, int nx0, LaunchCfg& cfg, cudaStream_t st)
 {
     switch (nx0) {
-    case 0: return launch_nx0<0>(p, functor, cfg, max_grid, st);
-    case 6: return launch_nx0<6>(p, functor, cfg, max_grid, st);
+    case 0: return launch_nx0<0>(p, functor, cfg, st);
+    case 6: return launch_nx0<6>(p, functor, cfg, st);
     default: return -22;
     }
 }

@@ -1,10 +1,10 @@
-// fused_poly.cu -- engine instantiations for the FPoly device functor.
+// fused_poly.cu -- engine instantiations for the FPoly device functor (heavy geometry).
 #include "dispatch.h"
 
 #define LIST_(F, f) VB_CASE_D(F, f, 2) VB_CASE_D(F, f, 4) VB_CASE_D(F, f, 6) VB_CASE_D(F, f, 8) \
     VB_CASE_D(F, f, 10) VB_CASE_D(F, f, 12) VB_CASE_D(F, f, 16) VB_CASE_D(F, f, 20)
 
-int launch_fused_poly(const EngineP& p, const void* functor, LaunchCfg& cfg, int max_grid, cudaStream_t st)
+int launch_fused_poly_heavy(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st)
 {
     const FPoly& f = *(const FPoly*)functor;
     VB_DISPATCH_D(FPoly, f, LIST_);

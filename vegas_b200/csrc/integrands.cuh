@@ -163,6 +163,25 @@ struct FRidge {
     }
 };
 
+// The same ridge for n < 8 terms without the 8-wide lock-step machinery (and its registers): the
+// light engine geometry uses it.  Arithmetic identical to FRidge's tail loop (mode 0).
+struct FRidgeLight : FRidge {
+    template <int D>
+    __device__ __forceinline__ void operator()(const double (&x)[D], int dim, double (&f)[1]) const
+    {
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double c = __ldg(x0 + k);
+            double q = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                if (d < dim) { double t = x[d] - c; q = fma(t, t, q); }
+            s += vb_exp(-a * q);
+        }
+        f[0] = s / (double)n * norm;
+    }
+};
+
 // ---- Genz (1984) test family on the unit cube; a = difficulty, u = shift ------------------------
 struct FGenz {
     static constexpr int NF = 1;

@@ -54,7 +54,8 @@ struct vb200_ctx {
     int device = 0;
     int sm_count = 0;
     size_t smem_per_sm = 0, smem_per_block_optin = 0;
-    int last_grid = 0, last_bps = 0, last_wtot = 0;      // geometry of the most recent engine launch
+    int last_grid = 0, last_bps = 0, last_wtot = 0, last_nt = 0, last_ch = 0;
+    bool light_hint = false;                              // the integrand is cheap: prefer the light engine geometry      // geometry of the most recent engine launch
     int64_t last_smem = 0;
     uint64_t seed = 0;
     PhiloxKey key;
@@ -193,6 +194,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
     CK(cudaSetDevice(c->device));
     const int dim = c->map.dim;
     c->fid = -1;
+    c->light_hint = false;
     switch (id) {
     case VB200_F_POLY: {
         if (nbytes != sizeof(vb200_poly_t)) return fail(-1, "poly: params size %zu != %zu", nbytes, sizeof(vb200_poly_t));
@@ -202,6 +204,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         for (int d = 0; d < VB_MAXD; ++d) { f.c[d] = q->c[d]; f.p[d] = q->p[d]; }
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
+        c->light_hint = true;
         break;
     }
     case VB200_F_GAUSS_MIX: {
@@ -215,6 +218,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         f.centers = (const double*)c->fparams.p; f.npeak = q->npeak; f.a = q->a; f.norm = q->norm;
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
+        c->light_hint = q->npeak <= 4;
         break;
     }
     case VB200_F_RIDGE: {
@@ -231,6 +235,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         f.x0 = (const double*)c->fparams.p; f.xs = f.x0 + q->n; f.n = q->n; f.mode = q->mode; f.a = q->a; f.norm = q->norm;
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
+        c->light_hint = q->n < 8 && q->mode == 0;          // FRidgeLight == FRidge's tail loop
         break;
     }
     case VB200_F_GENZ_OSC: case VB200_F_GENZ_PRODPEAK: case VB200_F_GENZ_CORNER:
@@ -242,6 +247,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         for (int d = 0; d < VB_MAXD; ++d) { f.a[d] = q->a[d]; f.u[d] = q->u[d]; }
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
+        c->light_hint = true;
         break;
     }
     case VB200_F_PATHINT: {
@@ -449,121 +455,42 @@ static int fill_engine(vb200_ctx* c, EngineP& p, uint32_t itn, double beta, int 
     p.beta_half = beta / 2.;
     p.sigf_out = sigf; p.sum_f = sum_f; p.n_f = (unsigned long long*)n_f; p.hstride = (int)hstride;
     p.status = status;
-    for (int d = 0; d < VB_MAXD; ++d) p.cstride[d] = c->cstride[d];
+    for (int d = 0; d < VB_MAXD; ++d) { p.cstride[d] = c->cstride[d]; p.dni[d] = (double)c->map.ninc[d]; }
     return 0;
 }
 
-static int env_int(const char* name, int dflt)
-{
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
-// shared memory of the engine kernel apart from the histogram windows
-static size_t base_smem(vb200_ctx* c, int nf, int cap)
-{
-    size_t b = sizeof(double) * (size_t)nf * cap + sizeof(long long) * (VB_CH + 1) + sizeof(int) * VB_CH +
-               sizeof(uint32_t) * (size_t)VB_CH * c->map.dim;
-    return (b + 15) & ~(size_t)15;
-}
-
-static void size_cfg(vb200_ctx* c, int nf, LaunchCfg& cfg, int wtot)
-{
-    int cap = env_int("VB200_CAP", 2048);
-    const int lim = (32 * 1024) / (8 * nf);
-    if (cap > lim) cap = lim;
-    if (cap < 256) cap = 256;
-    cfg.sm_count = c->sm_count;
-    cfg.cap = cap;
-    cfg.smem = base_smem(c, nf, cap) + (sizeof(double) + sizeof(unsigned)) * (size_t)wtot;
-    cfg.smem = (cfg.smem + 15) & ~(size_t)15;
-    cfg.blocks_per_sm_out = 0;
-}
-
-// Windows of the training histogram kept in shared memory (engine.cuh, HistW).  On axis d a chunk
-// of VB_CH consecutive hypercubes spans at most `nd` strata; the window must hold their bins.
-// Axes are admitted smallest window first until `budget_bins` is used up (the others fall back to
-// global atomics); what is left upgrades partial windows to the full axis, fastest-running axis
-// first, so they are never flushed.
-static void plan_windows(vb200_ctx* c, EngineP& p, long long budget_bins)
-{
-    const int dim = c->map.dim;
-    p.wtot = 0;
-    for (int d = 0; d < VB_MAXD; ++d) { p.wcap[d] = 0; p.woff[d] = 0; }
-    if (!(p.flags & (VBF_TRAIN | VBF_TRAIN_ERRORS)) || budget_bins <= 0) return;
-    long long need[VB_MAXD];
-    int order[VB_MAXD];
-    for (int d = 0; d < dim; ++d) {
-        const long long ns = c->st.nstrat[d], ni = c->map.ninc[d], cs = c->cstride[d];
-        long long nd;
-        if (cs >= VB_CH) nd = (cs % VB_CH == 0) ? 1 : 2;
-        else nd = (VB_CH + cs - 1) / cs + ((VB_CH % cs == 0) ? 0 : 1);
-        need[d] = (nd >= ns) ? ni : (nd * ni + ns - 1) / ns + 1;
-        if (need[d] > ni) need[d] = ni;
-        order[d] = d;
-    }
-    for (int i = 1; i < dim; ++i)                                   // insertion sort by need (stable)
-        for (int j = i; j > 0 && need[order[j]] < need[order[j - 1]]; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
-    long long used = 0;
-    for (int i = 0; i < dim; ++i) {
-        const int d = order[i];
-        if (used + need[d] <= budget_bins) { p.wcap[d] = (int)need[d]; used += need[d]; }
-    }
-    for (int d = 0; d < dim; ++d) {
-        const long long ni = c->map.ninc[d];
-        if (p.wcap[d] > 0 && p.wcap[d] < ni && used + (ni - p.wcap[d]) <= budget_bins) { used += ni - p.wcap[d]; p.wcap[d] = (int)ni; }
-    }
-    int off = 0;
-    for (int d = 0; d < dim; ++d) { p.woff[d] = off; off += p.wcap[d]; }
-    p.wtot = off;
-}
-
-typedef int (*launch_fn)(vb200_ctx*, const EngineP&, LaunchCfg&, int, cudaStream_t);
-
-static int do_launch_fused(vb200_ctx* c, const EngineP& p, LaunchCfg& cfg, int max_grid, cudaStream_t st)
+static int do_launch_fused(vb200_ctx* c, const EngineP& p, LaunchCfg& cfg, cudaStream_t st)
 {
     const void* f = c->functor.data();
     switch (c->fid) {
-    case VB200_F_POLY: return launch_fused_poly(p, f, cfg, max_grid, st);
-    case VB200_F_GAUSS_MIX: return launch_fused_gaussmix(p, f, cfg, max_grid, st);
-    case VB200_F_RIDGE: return launch_fused_ridge(p, f, cfg, max_grid, st);
-    case VB200_F_PATHINT: return launch_fused_pathint(p, f, c->nx0, cfg, max_grid, st);
-    default: return launch_fused_genz(p, f, cfg, max_grid, st);
+    case VB200_F_POLY: return launch_fused_poly(p, f, cfg, st);
+    case VB200_F_GAUSS_MIX: return launch_fused_gaussmix(p, f, cfg, st);
+    case VB200_F_RIDGE: return launch_fused_ridge(p, f, cfg, st);
+    case VB200_F_PATHINT: cfg.light = false; return launch_fused_pathint(p, f, c->nx0, cfg, st);
+    default: return launch_fused_genz(p, f, cfg, st);
     }
 }
 
 static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc, cudaStream_t st)
 {
-    const int64_t nch = p.chunk_end - p.chunk_begin;
-    if (nch <= 0) return 0;
-    const int max_grid = (int)(nch < 0x7fffffff ? nch : 0x7fffffff);
-    auto launch = [&](LaunchCfg& cfg, cudaStream_t s) {
-        return fused ? do_launch_fused(c, p, cfg, max_grid, s) : launch_buffer(p, nf, cfg, max_grid, s);
-    };
-    // pass 1: residency without the histogram windows (registers / staging buffer decide)
+    if (p.chunk_end - p.chunk_begin <= 0) return 0;
     LaunchCfg cfg;
-    plan_windows(c, p, 0);
-    size_cfg(c, nf, cfg, 0);
-    p.cap = cfg.cap;
-    int grid = launch(cfg, VB_DRYRUN);
+    memset(&cfg, 0, sizeof cfg);
+    cfg.sm_count = c->sm_count;
+    cfg.smem_per_sm = c->smem_per_sm;
+    cfg.smem_optin = c->smem_per_block_optin;
+    // light geometry (one big CTA per SM): cheap integrand, digits fit 16 bits, and enough big chunks
+    // to keep every SM busy; VB200_LIGHT=0/1 overrides the work-size test (developer switch)
+    bool light = fused && c->light_hint;
+    for (int d = 0; d < c->map.dim; ++d) if (c->st.nstrat[d] > 65535) light = false;
+    const int force = vb_env_int("VB200_LIGHT", -1);
+    if (force == 0) light = false;
+    if (force != 1 && c->st.nlocal < (int64_t)VB_LCH * 4 * c->sm_count) light = false;
+    cfg.light = light;
+    auto launch = [&](cudaStream_t s) { return fused ? do_launch_fused(c, p, cfg, s) : launch_buffer(p, nf, cfg, s); };
+    int grid = launch(VB_DRYRUN);
     if (grid == -22) return fail(-4, "engine: no kernel compiled for dim=%d nf=%d integrand=%d", p.map.dim, nf, c->fid);
     if (grid < 0) return fail(-2, "engine: occupancy query failed (%d)", grid);
-    // pass 2: give the windows the shared memory that this residency leaves unused
-    {
-        const int bps = cfg.blocks_per_sm_out > 0 ? cfg.blocks_per_sm_out : 1;
-        long long per_cta = (long long)c->smem_per_sm / bps - 1024;           // 1 KB reserved per CTA
-        if (per_cta > (long long)c->smem_per_block_optin) per_cta = (long long)c->smem_per_block_optin;
-        long long budget = (per_cta - (long long)cfg.smem - 64) / (long long)(sizeof(double) + sizeof(unsigned));
-        const int cap_bins = env_int("VB200_HIST_BINS", 1 << 30);
-        if (budget > cap_bins) budget = cap_bins;
-        plan_windows(c, p, budget);
-        if (p.wtot > 0) {
-            size_cfg(c, nf, cfg, p.wtot);
-            int g2 = launch(cfg, VB_DRYRUN);
-            if (g2 < 0) return fail(-2, "engine: occupancy query failed (%d)", g2);
-            grid = g2;
-        }
-    }
     const int nacc = nf + nf * (nf + 1) / 2 + 1;
     CK(c->partials.ensure(sizeof(double) * (size_t)grid * nacc));
     p.partials = (double*)c->partials.p;
@@ -575,9 +502,10 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     CK(c->counter.ensure(sizeof(unsigned long long)));
     CK(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), st));
     p.work_counter = (unsigned long long*)c->counter.p;
-    int g2 = launch(cfg, st);
+    int g2 = launch(st);
     if (g2 < 0) return fail(-2, "engine: launch failed (%d: %s)", g2, cudaGetErrorString((cudaError_t)(-(g2 + 1000))));
-    c->last_grid = g2; c->last_bps = cfg.blocks_per_sm_out; c->last_smem = (int64_t)cfg.smem; c->last_wtot = p.wtot;
+    c->last_grid = g2; c->last_bps = cfg.blocks_per_sm; c->last_smem = (int64_t)cfg.smem; c->last_wtot = cfg.wtot;
+    c->last_nt = cfg.nt; c->last_ch = cfg.ch;
     k_finalize<<<1, 64, 0, st>>>(p.partials, g2, nacc, acc);
     c->launches += 2;
     CK(cudaGetLastError());
@@ -894,10 +822,11 @@ extern "C" int vb200_add_training_data(vb200_ctx* c, const double* y, const doub
 
 extern "C" int64_t vb200_launch_count(vb200_ctx* c) { return c ? c->launches : 0; }
 
-extern "C" int vb200_last_launch(vb200_ctx* c, int64_t out[4])
+extern "C" int vb200_last_launch(vb200_ctx* c, int64_t out[6])
 {
     if (!c || !out) return fail(-1, "vb200_last_launch: null argument");
     out[0] = c->last_grid; out[1] = c->last_bps; out[2] = c->last_smem; out[3] = c->last_wtot;
+    out[4] = c->last_nt; out[5] = c->last_ch;
     return 0;
 }
 
