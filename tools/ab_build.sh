@@ -8,7 +8,7 @@ out=build/ab_$name
 mkdir -p $out
 FL="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC $flags"
 pids=()
-for f in vegas_b200 fused_poly fused_gaussmix fused_ridge fused_genz fused_pathint reduce_buffer; do
+for f in $(cd vegas_b200/csrc && ls *.cu | sed "s/.cu//"); do
   nvcc $FL -c vegas_b200/csrc/$f.cu -o $out/$f.o & pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done

@@ -84,6 +84,7 @@ __device__ __forceinline__ int bin_floor(const EngineP& p, int d, int digit)
 // (axes whose window did not fit, chunks that wrap around an axis) go straight to global memory.
 extern __shared__ double vb_smem[];        // dynamic shared memory of the engine kernel
 static __shared__ int vb_wlo_s[VB_MAXD];   // first bin of the current window of each axis
+static __shared__ double vb_scratch_s[32];  // per-lane scratch slots (see hist_sum_slots4)
 // (file-scope declarations so that every access compiles to LDS / ATOMS: through generic pointers
 //  carried in a struct the compiler falls back to generic loads and the slower generic ATOM forms)
 
@@ -96,9 +97,6 @@ struct HistW {
 };
 
 #define VB_NO_SLOT 0xffffffffu
-#ifndef VB_HIST_GROUP
-#define VB_HIST_GROUP 4
-#endif
 
 __device__ __forceinline__ void hist_global(const EngineP& p, int d, int bin, double v)
 {
@@ -148,6 +146,155 @@ __device__ __forceinline__ unsigned long long cas_shared_u64(uint32_t sa, unsign
     return old;
 }
 
+// fp64 adds of v to 4 shared slots (VB_NO_SLOT: none) in lock-step.  There is no native
+// shared-memory fp64 add, so each is a compare-and-swap loop; running the 4 loops side by side
+// overlaps their round trips.  Written in PTX: the C++ form of this loop compiles to ~4x the
+// instructions (64-bit compares through 32-bit halves, register shuffling, v rematerialised).
+// Lanes leave the loop at different times: callers re-converge with __syncwarp().
+__device__ __forceinline__ void hist_sum_slots4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, double v)
+{
+    // No predicated ld/atom here (ptxas answers those with ~0.5 KB of spills in this kernel): a slot
+    // that is finished, or was never there, is redirected to this lane's scratch slot, where the
+    // compare-and-swap is harmless.
+    const uint32_t dummy = (uint32_t)__cvta_generic_to_shared(vb_scratch_s) + 8u * (threadIdx.x & 31);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p0, p1, p2, p3, t0, t1, t2, t3, q;\n\t"
+        ".reg .b32 a0, a1, a2, a3;\n\t"
+        ".reg .b64 o0, o1, o2, o3, s0, s1, s2, s3;\n\t"
+        ".reg .f64 f0, f1, f2, f3;\n\t"
+        "setp.ne.u32 p0, %0, 0xffffffff;\n\t"
+        "setp.ne.u32 p1, %1, 0xffffffff;\n\t"
+        "setp.ne.u32 p2, %2, 0xffffffff;\n\t"
+        "setp.ne.u32 p3, %3, 0xffffffff;\n\t"
+        "selp.b32 a0, %0, %5, p0;\n\t"
+        "selp.b32 a1, %1, %5, p1;\n\t"
+        "selp.b32 a2, %2, %5, p2;\n\t"
+        "selp.b32 a3, %3, %5, p3;\n\t"
+        "ld.shared.b64 o0, [a0];\n\t"
+        "ld.shared.b64 o1, [a1];\n\t"
+        "ld.shared.b64 o2, [a2];\n\t"
+        "ld.shared.b64 o3, [a3];\n"
+        "VB_CAS_LOOP:\n\t"
+        "mov.b64 f0, o0;\n\t"
+        "mov.b64 f1, o1;\n\t"
+        "mov.b64 f2, o2;\n\t"
+        "mov.b64 f3, o3;\n\t"
+        "add.rn.f64 f0, f0, %4;\n\t"
+        "add.rn.f64 f1, f1, %4;\n\t"
+        "add.rn.f64 f2, f2, %4;\n\t"
+        "add.rn.f64 f3, f3, %4;\n\t"
+        "mov.b64 s0, f0;\n\t"
+        "mov.b64 s1, f1;\n\t"
+        "mov.b64 s2, f2;\n\t"
+        "mov.b64 s3, f3;\n\t"
+        "atom.shared.cas.b64 s0, [a0], o0, s0;\n\t"
+        "atom.shared.cas.b64 s1, [a1], o1, s1;\n\t"
+        "atom.shared.cas.b64 s2, [a2], o2, s2;\n\t"
+        "atom.shared.cas.b64 s3, [a3], o3, s3;\n\t"
+        "setp.ne.b64 t0, s0, o0;\n\t"
+        "setp.ne.b64 t1, s1, o1;\n\t"
+        "setp.ne.b64 t2, s2, o2;\n\t"
+        "setp.ne.b64 t3, s3, o3;\n\t"
+        "and.pred p0, p0, t0;\n\t"
+        "and.pred p1, p1, t1;\n\t"
+        "and.pred p2, p2, t2;\n\t"
+        "and.pred p3, p3, t3;\n\t"
+        "mov.b64 o0, s0;\n\t"
+        "mov.b64 o1, s1;\n\t"
+        "mov.b64 o2, s2;\n\t"
+        "mov.b64 o3, s3;\n\t"
+        "selp.b32 a0, a0, %5, p0;\n\t"
+        "selp.b32 a1, a1, %5, p1;\n\t"
+        "selp.b32 a2, a2, %5, p2;\n\t"
+        "selp.b32 a3, a3, %5, p3;\n\t"
+        "or.pred q, p0, p1;\n\t"
+        "or.pred q, q, p2;\n\t"
+        "or.pred q, q, p3;\n\t"
+        "@q bra VB_CAS_LOOP;\n\t"
+        "}\n"
+        :: "r"(a0), "r"(a1), "r"(a2), "r"(a3), "d"(v), "r"(dummy) : "memory");
+}
+
+__device__ __forceinline__ void hist_sum_slots2(uint32_t a0, uint32_t a1, double v)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p0, p1, q;\n\t"
+        ".reg .b64 o0, o1, s0, s1;\n\t"
+        ".reg .f64 n0, n1, f0, f1;\n\t"
+        "setp.ne.u32 p0, %0, 0xffffffff;\n\t"
+        "setp.ne.u32 p1, %1, 0xffffffff;\n\t"
+        "@p0 ld.shared.b64 o0, [%0];\n\t"
+        "@p1 ld.shared.b64 o1, [%1];\n"
+        "VB_CAS_LOOP2:\n\t"
+        "@p0 mov.b64 f0, o0;\n\t"
+        "@p1 mov.b64 f1, o1;\n\t"
+        "@p0 add.rn.f64 n0, f0, %2;\n\t"
+        "@p1 add.rn.f64 n1, f1, %2;\n\t"
+        "@p0 mov.b64 s0, n0;\n\t"
+        "@p1 mov.b64 s1, n1;\n\t"
+        "@p0 atom.shared.cas.b64 s0, [%0], o0, s0;\n\t"
+        "@p1 atom.shared.cas.b64 s1, [%1], o1, s1;\n\t"
+        "@p0 setp.ne.b64 p0, s0, o0;\n\t"
+        "@p1 setp.ne.b64 p1, s1, o1;\n\t"
+        "@p0 mov.b64 o0, s0;\n\t"
+        "@p1 mov.b64 o1, s1;\n\t"
+        "or.pred q, p0, p1;\n\t"
+        "@q bra VB_CAS_LOOP2;\n\t"
+        "}\n"
+        :: "r"(a0), "r"(a1), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ void hist_sum_slot1_ptx(uint32_t a0, double v)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p0;\n\t"
+        ".reg .b64 o0, s0;\n\t"
+        ".reg .f64 n0, f0;\n\t"
+        "setp.ne.u32 p0, %0, 0xffffffff;\n\t"
+        "@p0 ld.shared.b64 o0, [%0];\n"
+        "VB_CAS_LOOP1:\n\t"
+        "@p0 mov.b64 f0, o0;\n\t"
+        "@p0 add.rn.f64 n0, f0, %1;\n\t"
+        "@p0 mov.b64 s0, n0;\n\t"
+        "@p0 atom.shared.cas.b64 s0, [%0], o0, s0;\n\t"
+        "@p0 setp.ne.b64 p0, s0, o0;\n\t"
+        "@p0 mov.b64 o0, s0;\n\t"
+        "@p0 bra VB_CAS_LOOP1;\n\t"
+        "}\n"
+        :: "r"(a0), "d"(v) : "memory");
+}
+
+// one slot, branches instead of predicated instructions
+__device__ __forceinline__ void hist_sum_slot1_bra(uint32_t a0, double v)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p0;\n\t"
+        ".reg .b64 o0, s0;\n\t"
+        ".reg .f64 n0, f0;\n\t"
+        "setp.eq.u32 p0, %0, 0xffffffff;\n\t"
+        "@p0 bra VB_CAS_DONE;\n\t"
+        "ld.shared.b64 o0, [%0];\n"
+        "VB_CAS_LOOPB:\n\t"
+        "mov.b64 f0, o0;\n\t"
+        "add.rn.f64 n0, f0, %1;\n\t"
+        "mov.b64 s0, n0;\n\t"
+        "atom.shared.cas.b64 s0, [%0], o0, s0;\n\t"
+        "setp.ne.b64 p0, s0, o0;\n\t"
+        "mov.b64 o0, s0;\n\t"
+        "@p0 bra VB_CAS_LOOPB;\n"
+        "VB_CAS_DONE:\n\t"
+        "}\n"
+        :: "r"(a0), "d"(v) : "memory");
+}
+
+#ifndef VB_HIST_W
+#define VB_HIST_W 4
+#endif
+
 // fp64 adds of v to W shared slots in lock-step: there is no native shared-memory fp64 add, so
 // each is a compare-and-swap loop; running the W loops side by side overlaps their round trips.
 template <int W>
@@ -173,9 +320,28 @@ __device__ __forceinline__ void hist_sum_slots(uint32_t (&sa)[W], double v)
     } while (pending);
 }
 
+
+// one slot: plain loop
+__device__ __forceinline__ void hist_sum_slot1(uint32_t sa, double v)
+{
+    unsigned long long old = lds_u64(sa), seen;
+    for (;;) {
+        seen = cas_shared_u64(sa, old, (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)old), v)));
+        if (seen == old) break;
+        old = seen;
+    }
+}
+
+// one training point; callers sit in a warp-uniform loop that ends with __syncwarp()
 __device__ __forceinline__ void hist_add(const EngineP& p, const HistW& H, int d, int bin, double v)
 {
-#ifdef VB_HIST_GENERIC
+    const uint32_t sa = hist_slot(p, H, d, bin, v);
+    if (sa != VB_NO_SLOT) hist_sum_slot1(sa, v);
+}
+
+// the same through the compiler's own atomics: for call sites in divergent code (phase 2)
+__device__ __forceinline__ void hist_add_divergent(const EngineP& p, const HistW& H, int d, int bin, double v)
+{
     if (bin >= 0) {
         const unsigned r = (unsigned)(bin - vb_wlo_s[d]);
         if (r < (unsigned)p.wcap[d]) {
@@ -183,10 +349,6 @@ __device__ __forceinline__ void hist_add(const EngineP& p, const HistW& H, int d
             atomicAdd(H.cnt + p.woff[d] + r, 1u);
         } else hist_global(p, d, bin, v);
     }
-#else
-    uint32_t sa[1] = {hist_slot(p, H, d, bin, v)};
-    if (sa[0] != VB_NO_SLOT) hist_sum_slots<1>(sa, v);
-#endif
 }
 
 // add the windows of the axes with need[d] != 0 (all axes when need == nullptr) to the global
@@ -218,9 +380,9 @@ static __device__ __noinline__ void train_cube(const EngineP& p, const HistW& H,
     for (int pr = 0; 2 * pr < p.map.dim; ++pr) {
         double ua, ub;
         philox_pair(p.key, p.itn, h, klast, pr, ua, ub);
-        hist_add(p, H, 2 * pr, bin_of(p, 2 * pr, y0[2 * pr], ua, nullptr), fabs(v));
+        hist_add_divergent(p, H, 2 * pr, bin_of(p, 2 * pr, y0[2 * pr], ua, nullptr), fabs(v));
         if (2 * pr + 1 < p.map.dim)
-            hist_add(p, H, 2 * pr + 1, bin_of(p, 2 * pr + 1, y0[2 * pr + 1], ub, nullptr), fabs(v));
+            hist_add_divergent(p, H, 2 * pr + 1, bin_of(p, 2 * pr + 1, y0[2 * pr + 1], ub, nullptr), fabs(v));
     }
 }
 
@@ -236,10 +398,10 @@ static __device__ __noinline__ void train_cube(const EngineP& p, const HistW& H,
 //                          the map's grid nodes for those windows -- for cheap integrands, where the
 //                          sampler itself is the work and occupancy / smem locality decide.
 #ifndef VB_LNT
-#define VB_LNT 640
+#define VB_LNT 512
 #endif
 #ifndef VB_LCH
-#define VB_LCH 1280
+#define VB_LCH 1024
 #endif
 template <class F, int D, bool LIGHT = false>
 struct FusedSrc {
@@ -299,16 +461,35 @@ struct FusedSrc {
         if (bad) p.status[0] = 1;
         if (p.flags & VBF_TRAIN) {
             double a = wf[0] * (double)n;
-            double fdv2 = a * a;
-            constexpr int G = VB_HIST_GROUP;                      // axes whose CAS loops run side by side
+            double fdv2 = __dmul_rn(a, a);
+            // 4 axes at a time: their CAS loops run side by side
 #pragma unroll
-            for (int d0 = 0; d0 < D; d0 += G) {
+            for (int d0 = 0; d0 < D; d0 += 4) {
                 if (d0 < dim) {
-                    uint32_t sa[G];
+                    uint32_t sa[4];
 #pragma unroll
-                    for (int j = 0; j < G; ++j)
+                    for (int j = 0; j < 4; ++j)
                         sa[j] = (d0 + j < D && d0 + j < dim) ? hist_slot_code(p, H, d0 + j, code[d0 + j < D ? d0 + j : 0], fdv2) : VB_NO_SLOT;
-                    hist_sum_slots<G>(sa, fdv2);
+#if VB_HIST_W == 0
+                    hist_sum_slots<4>(sa, fdv2);
+#elif VB_HIST_W == 4
+                    hist_sum_slots4(sa[0], sa[1], sa[2], sa[3], fdv2);
+#elif VB_HIST_W == 2
+                    hist_sum_slots2(sa[0], sa[1], fdv2);
+                    hist_sum_slots2(sa[2], sa[3], fdv2);
+#elif VB_HIST_W == 5
+                    hist_sum_slot1_bra(sa[0], fdv2);
+                    hist_sum_slot1_bra(sa[1], fdv2);
+                    hist_sum_slot1_bra(sa[2], fdv2);
+                    hist_sum_slot1_bra(sa[3], fdv2);
+#elif VB_HIST_W == 6
+                    (void)sa;
+#else
+                    hist_sum_slot1_ptx(sa[0], fdv2);
+                    hist_sum_slot1_ptx(sa[1], fdv2);
+                    hist_sum_slot1_ptx(sa[2], fdv2);
+                    hist_sum_slot1_ptx(sa[3], fdv2);
+#endif
                 }
             }
         }
