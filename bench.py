@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 DIM = 8
 RIDGE_N = 1000
 NEVAL_PER_GPU = int(1e8)
-C_EXP = 30            # fp64 flops charged per exp(): CUDA's exp = 14 DFMA + 2 DADD (SASS count)
+C_EXP = 18            # fp64 flops charged per exp(): the table-driven vb_exp_n executes 8 DFMA + 1 DADD + 1 DMUL
 METRIC = 'fp64 integrand samples/sec, 8-D ridge (N=%d), vegas+ beta=0.75' % RIDGE_N
 
 

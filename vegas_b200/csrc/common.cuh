@@ -75,17 +75,25 @@ __device__ __forceinline__ double div_exact(double a, double b, double rb)
 
 
 // ---------------------------------------------------------------------------------------------
-// exp() for W independent arguments evaluated in lock-step, so that the W Horner chains interleave
-// in the FP64 pipe (a single exp is ~15 dependent DFMAs).  Cody-Waite reduction x = k ln2 + r,
-// |r| <= ln2/2, then a degree-11 near-minimax polynomial (Chebyshev fit, max rel. error 4.2e-18
-// before rounding; coefficients derived with mpmath, see tools/exp_coeffs.py), scaled by 2^k
-// through the exponent field.  |x| >= 708 (overflow / underflow / denormal results, inf, NaN)
-// takes the library exp(), so results there are unchanged.
+// exp() for W independent arguments evaluated in lock-step, so that the W dependent chains
+// interleave in the FP64 pipe.  Table-driven: x * 128/ln2 = 128 k + j + f, |f| <= 1/2;
+// r = x - (128 k + j) ln2/128 (two-step Cody-Waite, |r| <= ln2/256);
+// exp(x) = 2^k * T[j] * P(r) with T[j] = 2^(j/128) correctly rounded (128 doubles staged in shared
+// memory by the kernel prologue: per-lane indices would serialise in the constant cache) and P a
+// degree-5 near-minimax polynomial (relative error 1.7e-20).  10 FP64 instructions (8 DFMA, 1 DADD,
+// 1 DMUL) against 16 in CUDA's exp(); error <= 1.5 ulp.  Constants: tools/exp_table.py.
+// |x| >= 708 (overflow / underflow / denormal results, inf, NaN) takes the library exp().
 // ---------------------------------------------------------------------------------------------
-__constant__ double vb_exp_c[12] = {
-    2.51100492048186583e-08, 2.76326547225277896e-07, 2.75572408872298695e-06, 2.48014854415613131e-05,
-    1.98412698900764028e-04, 1.38888889523528631e-03, 8.33333333331958900e-03, 4.16666666664879531e-02,
-    1.66666666666666796e-01, 5.00000000000001887e-01, 1.0, 1.0};
+#include "exp_table.inc"
+__constant__ double vb_exp_c[6] = VB_EXP_POLY;
+__device__ const double vb_exp_tab_g[128] = VB_EXP_TABLE;
+static __shared__ double vb_exp_tab_s[128];
+
+// called by all threads of a CTA (>= 128 of them) before the first vb_exp*(); needs a barrier after
+__device__ __forceinline__ void vb_exp_init()
+{
+    if (threadIdx.x < 128) vb_exp_tab_s[threadIdx.x] = vb_exp_tab_g[threadIdx.x];
+}
 
 template <int W>
 __device__ __forceinline__ void vb_exp_n(const double (&x)[W], double (&e)[W])
@@ -93,25 +101,26 @@ __device__ __forceinline__ void vb_exp_n(const double (&x)[W], double (&e)[W])
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: rounds to nearest integer
     double t[W], r[W], p[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) t[j] = __fma_rn(x[j], 1.44269504088896339e+00, MAGIC);
+    for (int j = 0; j < W; ++j) t[j] = __fma_rn(x[j], VB_EXP_INVL, MAGIC);
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         double kf = t[j] - MAGIC;
-        r[j] = __fma_rn(kf, -6.93147180559945286e-01, x[j]);
-        r[j] = __fma_rn(kf, -2.31904681384629956e-17, r[j]);
+        r[j] = __fma_rn(kf, -VB_EXP_LHEAD, x[j]);
+        r[j] = __fma_rn(kf, -VB_EXP_LTAIL, r[j]);
     }
 #pragma unroll
     for (int j = 0; j < W; ++j) p[j] = __fma_rn(vb_exp_c[0], r[j], vb_exp_c[1]);
 #pragma unroll
-    for (int i = 2; i < 12; ++i) {
+    for (int i = 2; i < 6; ++i) {
 #pragma unroll
         for (int j = 0; j < W; ++j) p[j] = __fma_rn(p[j], r[j], vb_exp_c[i]);
     }
     bool rare = false;
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        int k = __double2loint(t[j]);
-        e[j] = __hiloint2double(__double2hiint(p[j]) + (k << 20), __double2loint(p[j]));
+        const int n = __double2loint(t[j]);             // 128 k + j (two's complement in the low word)
+        p[j] = __dmul_rn(p[j], vb_exp_tab_s[n & 127]);
+        e[j] = __hiloint2double(__double2hiint(p[j]) + ((n >> 7) << 20), __double2loint(p[j]));
         rare |= (__double2hiint(x[j]) & 0x7fffffff) >= 0x40862000;
     }
     if (rare) {                                            // some |x| >= 708: one branch for all W

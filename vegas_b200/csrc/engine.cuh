@@ -657,6 +657,8 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     H.gw_off = (int)(gw_s - vb_smem);
     H.sum_sa = (uint32_t)__cvta_generic_to_shared(H.sum);
     H.cnt_sa = (uint32_t)__cvta_generic_to_shared(H.cnt);
+    static_assert(NT >= 128, "vb_exp_init needs 128 threads");
+    vb_exp_init();                                                // visible after the first barrier of the chunk loop
     for (int i = tid; i < p.wtot; i += NT) { H.sum[i] = 0.0; H.cnt[i] = 0u; }
     if (tid < VB_MAXD) wlo_s[tid] = -0x40000000;                   // no window yet: the first chunk installs them
     long long since_flush = 0;                                    // samples added since the last full flush
