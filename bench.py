@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 DIM = 8
 RIDGE_N = 1000
 NEVAL_PER_GPU = int(1e8)
+NCU_DRAM_BYTES_PER_LAUNCH = 129.46e6   # 91.42 MB read + 38.04 MB written: ncu capture of one launch at the bench configuration (profiles/prof_ridge1000_r01.summary.txt)
 C_EXP = 18            # fp64 flops charged per exp(): the table-driven vb_exp_n executes 8 DFMA + 1 DADD + 1 DMUL
 METRIC = 'fp64 integrand samples/sec, 8-D ridge (N=%d), vegas+ beta=0.75' % RIDGE_N
 
@@ -65,7 +66,7 @@ def reference_arm(steps, warmup, neval=None, nproc=None):
     its multiprocessing nproc mode on all host cores; falls back to the C restatement
     (oracle port, 1 core) if the compiled reference did not travel"""
     cores = nproc or os.cpu_count() or 1
-    neval = int(neval or 2e5)
+    neval = int(neval or 1e6)
     f = RidgeNumpy()
     kind = 'reference'
     try:
@@ -202,9 +203,17 @@ def ours(args):
     # ---- roofline of the fused kernel (this rank's launches)
     flops_per_sample = (9 * DIM + 10) + f.flops_per_sample(C_EXP)
     ach = float(np.sum(local_samples)) * flops_per_sample / (float(np.sum(kern_ms)) * 1e-3) / 1e12
-    roofline = dict(bound='fp64', achieved=ach, peak=fp64_peak, unit='TFLOP/s', frac=ach / fp64_peak, traffic=None,
-                    kernel='k_engine<FusedSrc<FRidge,8>>', kernel_ms=float(np.mean(kern_ms)),
-                    flops_per_sample=flops_per_sample,
+    geom = integ._ctx.last_launch()
+    roofline = dict(bound='fp64', achieved=ach, peak=fp64_peak, unit='TFLOP/s', frac=ach / fp64_peak,
+                    traffic=NCU_DRAM_BYTES_PER_LAUNCH if args.ridge_n == RIDGE_N else None,
+                    traffic_source='ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch at this '
+                                   'configuration (profiles/prof_ridge1000_r01.summary.txt); the kernel is FP64-bound, HBM '
+                                   'traffic is the sigf stream (8 B read + 8 B written per hypercube)',
+                    kernel='k_engine<FusedSrc<FRidge,8,false>>', kernel_ms=float(np.mean(kern_ms)),
+                    launch=geom, flops_per_sample=flops_per_sample,
+                    flops_note='9*D+10 engine + N*(3*D+2+C_exp) integrand, C_exp=%d (8 DFMA + 1 DADD + 1 DMUL executed by '
+                               'the table-driven exp); a ridge term is 28 FP64 instructions for %d flops, so 100%% FP64-pipe '
+                               'occupancy corresponds to frac=%.3f' % (C_EXP, 3 * DIM + 2 + C_EXP, (3 * DIM + 2 + C_EXP) / 56.),
                     peak_source='measured live: vb200_fp64_peak DFMA probe (MEASURED_PEAKS.json has no FP64 entry); '
                                 'nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2')
     out = dict(metric=METRIC, value=value, unit='samples/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
@@ -222,8 +231,9 @@ def ours(args):
         out['clocks'] = sampler.summary()
         if world == 1 and not args.no_cpu:
             # separate process: the reference forks a multiprocessing pool, which must not inherit CUDA
-            cp = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2',
-                                 '--warmup', '1', '--cpu-neval', '100000'], capture_output=True, text=True)
+            # bounded sample: 1 + 3 iterations of neval=1e6 (~10-15 s on 16 cores; the GPU arm runs 1e8)
+            cp = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '3',
+                                 '--warmup', '1', '--cpu-neval', '1000000'], capture_output=True, text=True)
             try:
                 out['cpu_baseline'] = json.loads(cp.stdout.strip().splitlines()[-1])['cpu_baseline']
             except Exception:
@@ -252,7 +262,7 @@ def variants(vegas, _lib, fp64_peak):
         fl = (9 * DIM + 10) + f.flops_per_sample(C_EXP)
         out['ridge_N%d%s' % (n, '_shifted' if shifted else '')] = dict(value=float(r.sum_neval) / (ms * 1e-3), unit='samples/s',
                                     roofline_frac=float(r.sum_neval) * fl / (kms * 1e-3) / 1e12 / fp64_peak,
-                                    flops_per_sample=fl, result=str(r))
+                                    flops_per_sample=fl, result=str(r), launch=integ._ctx.last_launch())
     return out
 
 
@@ -264,7 +274,7 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--ridge-n', type=int, default=RIDGE_N)
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--cpu-neval', type=int, default=200000)
+    ap.add_argument('--cpu-neval', type=int, default=1000000)
     ap.add_argument('--variants', action='store_true', default=True)
     ap.add_argument('--no-variants', dest='variants', action='store_false')
     args = ap.parse_args()

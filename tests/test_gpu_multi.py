@@ -1,0 +1,80 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the hypercube range sharded over two
+ranks (NCCL all-reduce of the per-iteration sums) must reproduce the single-GPU iteration --
+integers exactly, fp64 sums to 1e-12 (only the order of the partial sums differs), because the
+Philox stream is a pure function of (seed, iteration, hypercube, sample)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+LIMITS = 4 * [[0., 1.]]
+KW = dict(neval=400000, seed=4242)
+NITN = 3
+
+
+def _run(mpi, light):
+    import vegas_b200 as vegas
+    if light:
+        os.environ['VB200_LIGHT'] = '1'
+    f = vegas.integrands.Ridge(dim=4, N=3)
+    integ = vegas.Integrator(LIMITS, mpi=mpi, **KW)
+    recs = []
+    integ._trace = lambda rec: recs.append(dict(rec))
+    r = integ(f, nitn=NITN)
+    return recs, float(r.mean), float(r.sdev), np.array(integ.sigf), np.array(integ.map.grid), integ._ctx.last_launch()
+
+
+def _worker(rank, world, port, light, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    out = _run(True, light)
+    q.put((rank,) + out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('light', [False, True])
+def test_two_gpus_match_one(light):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000) + int(light)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, light, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    one = _run(False, light)
+    os.environ.pop('VB200_LIGHT', None)
+    for o in outs:
+        recs, mean, sdev, sigf, grid, geom = o[1:]
+        assert len(recs) == NITN
+        for a, b in zip(recs, one[0]):
+            assert a['last_neval'] == b['last_neval']
+            np.testing.assert_allclose(a['mean'], b['mean'], rtol=1e-12)
+            np.testing.assert_allclose(a['var'], b['var'], rtol=1e-11)
+            np.testing.assert_allclose(a['sum_sigf'], b['sum_sigf'], rtol=1e-12)
+            assert np.array_equal(a['n_f'], b['n_f'])
+            np.testing.assert_allclose(a['sum_f'], b['sum_f'], rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(mean, one[1], rtol=1e-12)
+        np.testing.assert_allclose(sigf, one[3], rtol=1e-8, atol=1e-300)
+        np.testing.assert_allclose(grid, one[4], rtol=1e-10, atol=1e-14)
+        if light:
+            assert geom['threads'] > 128, geom                 # the light geometry really ran on the shards
+    assert np.array_equal(outs[0][5], outs[1][5])              # identical grids on both ranks

@@ -459,7 +459,8 @@ class Integrator(object):
         if world == 1:
             return _lib.CHUNK
         per = -(-int(self.nhcube) // (world * 8))
-        per = -(-per // _lib.CHUNK) * _lib.CHUNK
+        unit = 4 * _lib.CHUNK if per >= 4 * _lib.CHUNK else _lib.CHUNK    # whole 1024-cube chunks of the light geometry
+        per = -(-per // unit) * unit
         return int(max(_lib.CHUNK, min(64 * _lib.CHUNK, per)))
 
     def _engine(self):
