@@ -43,7 +43,7 @@ def run_engine_iterations(limits, f, nitn, neval, seed, fused=True, **kw):
         rec = out[-1]
         rec.update(neval_hcube=nh.cpu().numpy().astype(np.int64), sigf_in=sigf_in, sum_sigf_in=sum_sigf_in,
                    grid_in=grid_in, sigf_out=integ.sigf.copy(), grid_out=integ.map.grid.copy(),
-                   ninc=np.array(integ.map.ninc), nstrat=np.array(integ.nstrat),
+                   ninc=np.array(integ.map.ninc), nstrat=np.array(integ.nstrat), launch=integ._ctx.last_launch(),
                    range=tuple(int(v) for v in integ.neval_hcube_range))
     return out
 

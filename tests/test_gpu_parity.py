@@ -315,3 +315,90 @@ def test_large_cubes_and_giant_cube_paths():
         eng = run_engine_iterations(2 * [[0., 1.]], f, nitn=2, seed=9, **kw)
         ora = run_oracle_iterations(2 * [[0., 1.]], f, nitn=2, seed=9, engine=eng, **kw)
         compare_iterations(eng, ora, rtol=1e-11, var_rtol=1e-9)
+
+
+# ----------------------------------------------------------------------------- light geometry
+@pytest.mark.parametrize('name', ['poly2', 'gauss4', 'ridge4_nomap', 'genz10_pp', 'genz10_osc', 'genz3_corner'])
+def test_light_geometry_vs_oracle(name, monkeypatch):
+    """the one-big-CTA-per-SM geometry (512 threads, 1024-cube chunks, grid + histogram windows in
+    shared memory), forced on problems that would normally be too small for it, vs the oracle"""
+    monkeypatch.setenv('VB200_LIGHT', '1')
+    limits, f, kw = _cases()[name]
+    eng = run_engine_iterations(limits, f, nitn=3, seed=4000 + len(name), **kw)
+    assert all(r['launch']['threads'] == 512 and r['launch']['chunk_cubes'] == 1024 for r in eng), eng[0]['launch']
+    ora = run_oracle_iterations(limits, f, nitn=3, seed=4000 + len(name), engine=eng, **kw)
+    compare_iterations(eng, ora, rtol=RTOL, var_rtol=1e-10)
+
+
+def test_light_equals_heavy(monkeypatch):
+    """both geometries consume the same Philox stream: integer results identical, sums to 1e-12"""
+    limits, f, kw = _cases()['genz10_pp']
+    monkeypatch.setenv('VB200_LIGHT', '0')
+    a = run_engine_iterations(limits, f, nitn=2, seed=6, **kw)
+    monkeypatch.setenv('VB200_LIGHT', '1')
+    b = run_engine_iterations(limits, f, nitn=2, seed=6, **kw)
+    assert a[0]['launch']['threads'] == 128 and b[0]['launch']['threads'] == 512
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra['neval_hcube'], rb['neval_hcube'])
+        assert np.array_equal(ra['n_f'], rb['n_f'])
+        np.testing.assert_allclose(ra['mean'], rb['mean'], rtol=1e-12)
+        np.testing.assert_allclose(ra['var'], rb['var'], rtol=1e-10)
+        np.testing.assert_allclose(ra['sum_f'], rb['sum_f'], rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(ra['sigf_out'], rb['sigf_out'], rtol=1e-9, atol=1e-300)
+
+
+# ----------------------------------------------------------------------------- BASELINE.json full sizes
+def _check_full_size(integ, f, exact, nitn_adapt, nitn, neval_lo=0.85):
+    """size-independent properties at a BASELINE configuration: every sample is counted exactly once
+    per axis by the training histogram; the allocation meets neval; sigf stays finite and
+    non-negative with sum(sigf) == sum_sigf; the integral agrees with the exact value"""
+    recs = []
+    integ._trace = lambda rec: recs.append(dict(last_neval=rec['last_neval'], n_f=rec['n_f'], sum_sigf=rec['sum_sigf'],
+                                                sum_f=rec['sum_f'], mean=rec['mean'], var=rec['var']))
+    integ(f, nitn=nitn_adapt)
+    r = integ(f, nitn=nitn)
+    for rec in recs:
+        assert np.array_equal(rec['n_f'].sum(axis=1), np.full(integ.dim, rec['last_neval']))
+        assert neval_lo * integ.neval < rec['last_neval'] <= 1.001 * integ.neval     # int() truncation per cube (pyx:1696)
+        assert np.isfinite(rec['sum_f']).all() and (rec['sum_f'] >= 0).all()
+    import torch
+    sg = integ._sigf_dev
+    assert bool(torch.isfinite(sg).all()) and float(sg.min()) >= 0.0
+    np.testing.assert_allclose(float(sg.sum()), recs[-1]['sum_sigf'], rtol=1e-10)
+    assert abs(r.mean - exact) < 5 * r.sdev, (r.mean, r.sdev, exact)
+    assert r.Q > 1e-4, r.Q
+    return r
+
+
+def test_full_size_config2_ridge():
+    """BASELINE config 2: 8-D ridge (N=1000), vegas+ beta=0.75, neval=1e8, one GPU"""
+    from scipy.special import erf
+    vegas = _vegas()
+    f = vegas.integrands.Ridge(8, N=1000)
+    integ = vegas.Integrator(8 * [[0., 1.]], neval=1e8, seed=20, nitn=1)
+    assert [int(v) for v in integ.nstrat] == [8, 8, 8, 8, 8, 7, 7, 7] and integ.nhcube == 11239424
+    one = 0.5 * (erf(10 * (1 - f.x0)) + erf(10 * f.x0))
+    r = _check_full_size(integ, f, float(np.mean(one ** 8)), 3, 3)
+    assert r.sdev < 1e-4
+
+
+def test_full_size_config3_genz():
+    """BASELINE config 3: 10-D Genz product peak, neval=1e9 (all on one GPU here; sharded in bench/test_gpu_multi)"""
+    vegas = _vegas()
+    rng = np.random.default_rng(0x5eed + 3)
+    f = vegas.integrands.Genz('product_peak', 2 + 3 * rng.random(10), rng.random(10))
+    integ = vegas.Integrator(10 * [[0., 1.]], neval=1e9, seed=21, nitn=1, max_mem=1e10)
+    assert [int(v) for v in integ.nstrat] == [7, 7, 7, 7, 6, 6, 6, 6, 6, 6] and integ.nhcube == 112021056
+    r = _check_full_size(integ, f, f.exact(), 3, 2)
+    assert integ._ctx.last_launch()['threads'] == 512            # cheap integrand: light geometry
+    assert r.sdev < 1e-4 * abs(f.exact())
+
+
+def test_large_config5_three_peaks():
+    """BASELINE config 5 (20-D three-peak Gaussian, nstrat = 5 x [n] + 15 x [1]) at 1/20 of its size"""
+    vegas = _vegas()
+    f = vegas.integrands.GaussMix([5 * [c] + 15 * [0.45] for c in (.23, .39, .74)], 100., 356047712484621.56)
+    integ = vegas.Integrator(20 * [[0., 1.]], nstrat=5 * [30] + 15 * [1], neval=5e8, seed=22, nitn=1, max_mem=1e10)
+    assert integ.nhcube == 30 ** 5
+    # sharp peaks: a few hypercubes hit the max_neval_hcube=50000 clamp (pyx:1704), so the total stays below neval
+    _check_full_size(integ, f, 1.0, 5, 3, neval_lo=0.1)
