@@ -317,6 +317,41 @@ def test_large_cubes_and_giant_cube_paths():
         compare_iterations(eng, ora, rtol=1e-11, var_rtol=1e-9)
 
 
+@pytest.mark.parametrize('name,fused', [('gauss4', True), ('peaks20', True), ('pathint10', True), ('gauss4', False),
+                                        ('pathint10', False), ('genz3_corner', False)])
+def test_split_chunks_vs_oracle(name, fused, monkeypatch):
+    """work items: chunks cut into several items (forced here with a 256-sample item size; in
+    production only chunks the vegas+ allocation piled > 4096 samples onto) give the same sums"""
+    monkeypatch.setenv('VB200_ITEM', '256')
+    limits, f, kw = _cases()[name]
+    eng = run_engine_iterations(limits, f, nitn=3, seed=321, fused=fused, **kw)
+    ora = run_oracle_iterations(limits, f, nitn=3, seed=321, engine=eng, **kw)
+    compare_iterations(eng, ora, rtol=1e-11 if name.startswith('pathint') else RTOL, var_rtol=1e-10)
+
+
+def test_split_chunks_big_cubes_and_batches(monkeypatch):
+    """item splitting with cubes larger than an item / than the staging buffer, and the sampler
+    (random_batch) under splitting: identical rows"""
+    vegas = _vegas()
+    f = vegas.integrands.GaussMix([[0.3, 0.6]], 400., 1.0)
+    monkeypatch.setenv('VB200_ITEM', '256')
+    for kw in (dict(neval=40000, nstrat=[4, 3]), dict(neval=200000, nstrat=[20, 30])):
+        eng = run_engine_iterations(2 * [[0., 1.]], f, nitn=3, seed=9, **kw)
+        ora = run_oracle_iterations(2 * [[0., 1.]], f, nitn=3, seed=9, engine=eng, **kw)
+        compare_iterations(eng, ora, rtol=1e-11, var_rtol=1e-9)
+    out = []
+    base = vegas.Integrator(2 * [[0., 1.]], neval=200000, nstrat=[20, 30], seed=11)
+    base(f, nitn=3)
+    for item in ('256', '1000000'):
+        monkeypatch.setenv('VB200_ITEM', item)
+        integ = vegas.Integrator(base, seed=11)          # same map and sigf
+        integ._itn_counter = 100
+        parts = list(integ.random_batch(yield_hcube=True, yield_y=True))
+        out.append([np.concatenate([p[i] for p in parts]) for i in range(4)])
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+
+
 # ----------------------------------------------------------------------------- light geometry
 @pytest.mark.parametrize('name', ['poly2', 'gauss4', 'ridge4_nomap', 'genz10_pp', 'genz10_osc', 'genz3_corner'])
 def test_light_geometry_vs_oracle(name, monkeypatch):

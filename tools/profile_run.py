@@ -23,7 +23,7 @@ elif what == 'gauss':
     integ(f, nitn=4)
 elif what == 'pathint_unfused':
     f = F.PathIntegral(T=4., ndT=10, x0list=np.linspace(0, 2., 6))
-    ft = None
+    NORM, NORM0, X0L = f.norm, f.norm_x0, [float(v) for v in f.x0list]
 
     @vegas.devicebatchintegrand
     def fdev(theta):
@@ -31,19 +31,19 @@ elif what == 'pathint_unfused':
         Vx = 0.5 * x * x
         a, m_2a = 0.4, 1.25
         jf = 1.0 + x * x
-        jac = f.norm * jf.prod(dim=1)
-        jac0 = f.norm_x0 * jf[:, 1:].prod(dim=1)
+        jac = NORM * jf.prod(dim=1)
+        jac0 = NORM0 * jf[:, 1:].prod(dim=1)
         Smid = a * Vx[:, -1] + (m_2a * (x[:, 2:] - x[:, 1:-1]) ** 2 + a * Vx[:, 1:-1]).sum(dim=1)
         out = torch.empty((x.shape[0], 7), dtype=torch.float64, device=x.device)
         for i in range(7):
-            e = x[:, 0] if i == 0 else torch.full_like(x[:, 0], float(f.x0list[i - 1]))
+            e = x[:, 0] if i == 0 else torch.full_like(x[:, 0], X0L[i - 1])
             Ve = 0.5 * e * e
             S = Smid + m_2a * ((x[:, 1] - e) ** 2 + (e - x[:, -1]) ** 2) + a * Ve
             out[:, i] = (jac if i == 0 else jac0) * torch.exp(-S)
         return out
     integ = vegas.Integrator(f.region, neval=neval, seed=3, alpha=0.1)
     integ(fdev, nitn=3)
-    f = fdev
+    fused_f, f = f, fdev
 torch.cuda.synchronize()
 r = integ(f, nitn=2)
 torch.cuda.synchronize()

@@ -41,6 +41,6 @@ D, nf = 10, 7
 print('rows %d  sample %.2f ms (%.0f GB/s of %d B/row)  callback %.2f ms  reduce %.2f ms (%.0f GB/s of %d B/row)' % (
     rows, ts, rows * (8 * D + 8) / ts / 1e6, 8 * D + 8, tc, tr, rows * (8 * nf + 8) / tr / 1e6, 8 * nf + 8))
 print('engine (sample+reduce) %.3e samples/s ; with torch callback %.3e samples/s' % (rows / ((ts + tr) * 1e-3), rows / ((ts + tc + tr) * 1e-3)))
-print('E0 =', -np.log(r['exp(-E0*T)'].mean) / 4., r['exp(-E0*T)'], 'Q=%.2f' % r.Q)
+print('E0 =', -np.log(r[0].mean) / 4., r[0], 'Q=%.2f' % r.Q)
 ff = integ(f, nitn=3)
 print('fused result', ff['exp(-E0*T)'])

@@ -101,7 +101,8 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
         p.chunk_end = (p.st.nlocal + CH - 1) / CH;
     }
     cfg.nchunks = p.chunk_end - p.chunk_begin;
-    const int max_grid = (int)(cfg.nchunks < 0x7fffffff ? cfg.nchunks : 0x7fffffff);
+    const int64_t nwork = CH == VB_CH ? p.item_end - p.item_begin : cfg.nchunks;   // claimable work items
+    const int max_grid = (int)(nwork < 0x7fffffff ? nwork : 0x7fffffff);
     // pass 1: residency without the windows (registers / staging buffer decide)
     vb_plan_windows(p, CH, 0, false);
     size_t smem0 = engine_smem_bytes(NF, cap, CH, dim, 0, Src::GRIDW, DIGB);

@@ -1,8 +1,10 @@
 // engine.cuh -- the vegas+ iteration engine: one persistent kernel per iteration (or per batch).
 //
 // Work decomposition ("hypercube tiling"):
-//   chunk  = VB_CH consecutive hypercubes of this rank's share; the persistent CTAs claim chunks
-//            from an atomic counter, so they all finish together whatever the sample counts.
+//   chunk  = VB_CH consecutive hypercubes of this rank's share.
+//   item   = the unit the persistent CTAs claim from an atomic counter (so they all finish together):
+//            a whole chunk, or -- when the vegas+ allocation piled more than VB_ITEM samples onto one
+//            chunk (k_plan) -- one of m runs of its cubes holding ~1/m of its samples each.
 //   tile   = maximal run of cubes inside a chunk whose samples fit the shared-memory staging
 //            buffer (cap samples).  Cubes larger than cap are staged through global scratch.
 //   phase 1 (thread per SAMPLE): Philox -> stratified y -> AdaptiveMap -> integrand -> w*f staged
@@ -41,7 +43,11 @@ struct EngineP {
     double* scratch;           // [gridDim.x][NF][scratch_stride]
     int64_t scratch_stride;
     int64_t chunk_begin, chunk_end;   // local chunk range of this launch
-    unsigned long long* work_counter; // zeroed before the launch: next chunk to claim
+    unsigned long long* work_counter; // zeroed before the launch: next work item to claim
+    // work items (heavy geometry): item j of the launch is global item item_begin + j; chunk lc owns
+    // items [item_off[lc], item_off[lc+1]) (item_off == nullptr: one item per chunk, item j == chunk j)
+    const int64_t* item_off;          // [nchunks+1]
+    int64_t item_begin, item_end;
     int64_t cstride[VB_MAXD];  // cstride[d] = prod_{e<d} nstrat[e]
     // shared-memory windows of the training histogram (0 bins on an axis: global atomics there)
     int wcap[VB_MAXD];         // bins of axis d's window
@@ -646,6 +652,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     __shared__ double bc_s[NF];
     __shared__ uint32_t base_s[VB_MAXD];
     __shared__ long long next_s;
+    __shared__ int sub_s[2];
     __shared__ int wnew_s[VB_MAXD], wneed_s[VB_MAXD];
     int* const wlo_s = vb_wlo_s;
 
@@ -663,13 +670,31 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     if (tid < VB_MAXD) wlo_s[tid] = -0x40000000;                   // no window yet: the first chunk installs them
     long long since_flush = 0;                                    // samples added since the last full flush
 
-    // chunks are claimed dynamically (one atomic per chunk) so that CTAs finish together
+    // work is claimed dynamically (one atomic per item) so that CTAs finish together
     for (;;) {
-        __syncthreads();                       // previous chunk fully consumed
-        if (tid == 0) next_s = p.chunk_begin + (long long)atomicAdd(p.work_counter, 1ull);
+        __syncthreads();                       // previous item fully consumed
+        if (tid == 0) {
+            long long j = (long long)atomicAdd(p.work_counter, 1ull);
+            if (CH != VB_CH || p.item_off == nullptr) {
+                next_s = p.chunk_begin + j;                        // one item per chunk
+                sub_s[0] = 0; sub_s[1] = 1;
+            } else if ((j += p.item_begin) >= p.item_end) {
+                next_s = p.chunk_end;
+            } else {
+                int64_t lo = p.chunk_begin, hi = p.chunk_end;      // item_off[lo] <= j < item_off[hi]
+                while (hi - lo > 1) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (p.item_off[mid] <= j) lo = mid; else hi = mid;
+                }
+                next_s = lo;
+                sub_s[0] = (int)(j - p.item_off[lo]);
+                sub_s[1] = (int)(p.item_off[lo + 1] - p.item_off[lo]);
+            }
+        }
         __syncthreads();
         const int64_t lc = next_s;
         if (lc >= p.chunk_end) break;
+        const int sub = sub_s[0], nsub = sub_s[1];                 // this CTA does part `sub` of `nsub` of the chunk
         const int64_t lh0 = lc * CH;
         const int64_t h0 = local_to_global(p.st, lh0);
         if (p.wtot > 0) {
@@ -739,19 +764,29 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
             }
         }
         if (tid == NT - 1) ex_s[CH] = total;
-        since_flush += total;
         __syncthreads();
         const int64_t chunk_row = p.chunk_off ? p.chunk_off[lc] - p.row0 : 0;
 
-        int c0 = 0;
-        while (c0 < CH) {
+        // cubes of this item: those whose first sample lies in part `sub` of the chunk's samples
+        // (a cube is never split; all threads search the same shared array: broadcast reads)
+        int c0 = 0, cend = CH;
+        if (nsub > 1) {
+            const long long b0 = total * sub / nsub, b1 = total * (sub + 1) / nsub;
+            int lo = -1, hi = CH;                                  // first c with ex_s[c] >= b0
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b0) hi = mid; else lo = mid; }
+            c0 = hi;
+            lo = c0 - 1; hi = CH;                                  // first c with ex_s[c] >= b1
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b1) hi = mid; else lo = mid; }
+            cend = hi;
+        }
+        since_flush += ex_s[cend] - ex_s[c0];
+        while (c0 < cend) {
             const long long base = ex_s[c0];
             if (base >= total) break;                              // only empty cubes remain
-            // c1 = one past the last cube whose samples still fit the staging buffer (all threads
-            // search the same shared array: broadcast reads, no barrier)
+            // c1 = one past the last cube whose samples still fit the staging buffer
             int c1;
             {
-                int lo = c0, hi = CH + 1;                       // ex_s[lo]-base <= cap < ex_s[hi]-base (virtual)
+                int lo = c0, hi = cend + 1;                     // ex_s[lo]-base <= cap < ex_s[hi]-base (virtual)
                 while (hi - lo > 1) {
                     int mid = (lo + hi) >> 1;
                     if (ex_s[mid] - base <= (long long)p.cap) lo = mid; else hi = mid;

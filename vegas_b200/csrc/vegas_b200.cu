@@ -72,14 +72,17 @@ struct vb200_ctx {
     bool have_plan = false;
     AllocP al;
     int64_t plan_total = 0, plan_min = 0, plan_max = 0;
-    DevBuf chunk_tot, chunk_off, stats;
+    int64_t plan_max_chunk = 0, plan_items = 0;
+    DevBuf chunk_tot, chunk_off, chunk_items, item_off, stats;
     std::vector<long long> chunk_off_host;   // fetched lazily by the unfused path
+    std::vector<long long> item_off_host;    // same (only when some chunk was split: plan_items != nchunks)
     // integrand
     int fid = -1, nf = 0, nx0 = 0;
     std::vector<char> functor;        // host copy of the functor struct
     DevBuf fparams;                   // device arrays the functor points to
     // scratch
     DevBuf partials, scratch, counter;
+    DevBuf sigf_shadow;               // engine output of sigf while chunks are split into items (see run_engine)
     int64_t launches = 0;
 };
 
@@ -115,8 +118,8 @@ extern "C" void vb200_destroy(vb200_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    c->grid.release(); c->chunk_tot.release(); c->chunk_off.release(); c->stats.release();
-    c->fparams.release(); c->partials.release(); c->scratch.release(); c->counter.release();
+    c->grid.release(); c->chunk_tot.release(); c->chunk_off.release(); c->chunk_items.release(); c->item_off.release(); c->stats.release();
+    c->fparams.release(); c->partials.release(); c->scratch.release(); c->counter.release(); c->sigf_shadow.release();
     delete c;
 }
 
@@ -284,14 +287,17 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
 // ---------------------------------------------------------------------------------------------
 // allocation pre-pass + chunk offsets
 // ---------------------------------------------------------------------------------------------
-// stats: [0] sum  [1] min  [2] max   (unsigned long long / long long)
+// stats: [0] sum  [1] min  [2] max  [3] largest chunk total   (unsigned long long / long long)
+// chunk_items[lc] = work items chunk lc is cut into: 1, or ceil(total / item_samples) <= VB_CH when
+// the vegas+ allocation piled more than item_samples samples onto its cubes (engine.cuh, "items")
 __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t nchunks, int32_t* neval_out,
-                                                long long* chunk_tot, long long* stats)
+                                                long long* chunk_tot, long long* chunk_items, long long item_samples,
+                                                long long* stats)
 {
     __shared__ long long red[VB_NT / 32];
     __shared__ int rmin[VB_NT / 32], rmax[VB_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    long long my_sum = 0;
+    long long my_sum = 0, my_maxc = 0;
     int my_min = 0x7fffffff, my_max = 0;
     for (int64_t lc = blockIdx.x; lc < nchunks; lc += gridDim.x) {
         int64_t lh = lc * VB_CH + tid;
@@ -312,7 +318,10 @@ __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t n
             long long t = 0;
             for (int i = 0; i < VB_NT / 32; ++i) t += red[i];
             chunk_tot[lc] = t;
+            long long m = (t + item_samples - 1) / item_samples;
+            chunk_items[lc] = m < 1 ? 1 : (m > VB_CH ? VB_CH : m);
             my_sum += t;
+            if (t > my_maxc) my_maxc = t;
         }
     }
 #pragma unroll
@@ -327,6 +336,7 @@ __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t n
         atomicAdd((unsigned long long*)&stats[0], (unsigned long long)my_sum);
         atomicMin(&stats[1], (long long)my_min);
         atomicMax(&stats[2], (long long)my_max);
+        atomicMax(&stats[3], my_maxc);
     }
 }
 
@@ -379,25 +389,35 @@ extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sig
     const int64_t nch = c->nchunks;
     CK(c->chunk_tot.ensure(sizeof(long long) * (size_t)(nch + 1)));
     CK(c->chunk_off.ensure(sizeof(long long) * (size_t)(nch + 1)));
+    CK(c->chunk_items.ensure(sizeof(long long) * (size_t)(nch + 1)));
+    CK(c->item_off.ensure(sizeof(long long) * (size_t)(nch + 1)));
     CK(c->stats.ensure(sizeof(long long) * 4));
+    long long item_samples = vb_env_int("VB200_ITEM", VB_ITEM);
+    if (item_samples < 256) item_samples = 256;
     long long init[4] = {0, 0x7fffffffffffffffLL, 0, 0};
     CK(cudaMemcpyAsync(c->stats.p, init, sizeof init, cudaMemcpyHostToDevice, st));
     if (nch > 0) {
         int grid = (int)(nch < (int64_t)c->sm_count * 8 ? nch : (int64_t)c->sm_count * 8);
-        k_plan<<<grid, VB_NT, 0, st>>>(c->st, c->al, nch, neval_hcube_dev, (long long*)c->chunk_tot.p, (long long*)c->stats.p);
+        k_plan<<<grid, VB_NT, 0, st>>>(c->st, c->al, nch, neval_hcube_dev, (long long*)c->chunk_tot.p,
+                                       (long long*)c->chunk_items.p, item_samples, (long long*)c->stats.p);
         k_scan<<<1, 1024, 0, st>>>((const long long*)c->chunk_tot.p, nch, (long long*)c->chunk_off.p);
-        c->launches += 2;
+        k_scan<<<1, 1024, 0, st>>>((const long long*)c->chunk_items.p, nch, (long long*)c->item_off.p);
+        c->launches += 3;
         CK(cudaGetLastError());
     } else {
         CK(cudaMemsetAsync(c->chunk_off.p, 0, sizeof(long long), st));
+        CK(cudaMemsetAsync(c->item_off.p, 0, sizeof(long long), st));
     }
-    long long out[4];
+    long long out[4], nitems = 0;
     CK(cudaMemcpyAsync(out, c->stats.p, sizeof out, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&nitems, (const long long*)c->item_off.p + nch, sizeof nitems, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (nch == 0) out[1] = 0;
-    c->plan_total = out[0]; c->plan_min = out[1]; c->plan_max = out[2];
+    c->plan_total = out[0]; c->plan_min = out[1]; c->plan_max = out[2]; c->plan_max_chunk = out[3];
+    c->plan_items = nitems;
     c->have_plan = true;
     c->chunk_off_host.clear();
+    c->item_off_host.clear();
     if (stats_host) { stats_host[0] = out[0]; stats_host[1] = out[1]; stats_host[2] = out[2]; stats_host[3] = nch; }
     return 0;
 }
@@ -408,6 +428,29 @@ static int fetch_chunk_off(vb200_ctx* c)
     CK(cudaSetDevice(c->device));
     c->chunk_off_host.resize((size_t)c->nchunks + 1);
     CK(cudaMemcpy(c->chunk_off_host.data(), c->chunk_off.p, sizeof(long long) * (size_t)(c->nchunks + 1), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// items of the local chunk range [chunk_begin, chunk_end): p.item_off / item_begin / item_end
+static int set_items(vb200_ctx* c, EngineP& p)
+{
+    if (c->plan_items == c->nchunks) {                 // nothing was split: item j == chunk j
+        p.item_off = nullptr;
+        p.item_begin = p.chunk_begin; p.item_end = p.chunk_end;
+        return 0;
+    }
+    p.item_off = (const int64_t*)c->item_off.p;
+    if (p.chunk_begin == 0 && p.chunk_end == c->nchunks) {
+        p.item_begin = 0; p.item_end = c->plan_items;
+        return 0;
+    }
+    if (c->item_off_host.empty()) {
+        CK(cudaSetDevice(c->device));
+        c->item_off_host.resize((size_t)c->nchunks + 1);
+        CK(cudaMemcpy(c->item_off_host.data(), c->item_off.p, sizeof(long long) * (size_t)(c->nchunks + 1), cudaMemcpyDeviceToHost));
+    }
+    p.item_begin = c->item_off_host[(size_t)p.chunk_begin];
+    p.item_end = c->item_off_host[(size_t)p.chunk_end];
     return 0;
 }
 
@@ -486,7 +529,12 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     const int force = vb_env_int("VB200_LIGHT", -1);
     if (force == 0) light = false;
     if (force != 1 && c->st.nlocal < (int64_t)VB_LCH * 4 * c->sm_count) light = false;
+    // the light geometry claims whole 1024-cube chunks: not for allocations so skewed that a single
+    // 256-cube chunk holds more than 1/(4 * SMs) of the samples (the heavy geometry splits those)
+    if (force != 1 && c->plan_max_chunk * 4 * c->sm_count > c->plan_total) light = false;
     cfg.light = light;
+    int rc_items = set_items(c, p);
+    if (rc_items) return rc_items;
     auto launch = [&](cudaStream_t s) { return fused ? do_launch_fused(c, p, cfg, s) : launch_buffer(p, nf, cfg, s); };
     int grid = launch(VB_DRYRUN);
     if (grid == -22) return fail(-4, "engine: no kernel compiled for dim=%d nf=%d integrand=%d", p.map.dim, nf, c->fid);
@@ -502,8 +550,23 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     CK(c->counter.ensure(sizeof(unsigned long long)));
     CK(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), st));
     p.work_counter = (unsigned long long*)c->counter.p;
+    // sigf is updated in place and also drives the allocation: while a chunk is shared by several
+    // CTAs (items), one of them must not see the new sigf of a cube another has already finished
+    // -> write to a shadow buffer and copy the launch's cube range back afterwards
+    double* const sigf_user = p.sigf_out;
+    const bool shadow = p.item_off != nullptr && (p.flags & VBF_UPDATE_SIGF) && sigf_user != nullptr;
+    if (shadow) {
+        CK(c->sigf_shadow.ensure(sizeof(double) * (size_t)c->st.nlocal));
+        p.sigf_out = (double*)c->sigf_shadow.p;
+    }
     int g2 = launch(st);
     if (g2 < 0) return fail(-2, "engine: launch failed (%d: %s)", g2, cudaGetErrorString((cudaError_t)(-(g2 + 1000))));
+    if (shadow) {
+        const int64_t lo = p.chunk_begin * VB_CH;
+        const int64_t hi = p.chunk_end * VB_CH < c->st.nlocal ? p.chunk_end * VB_CH : c->st.nlocal;
+        CK(cudaMemcpyAsync(sigf_user + lo, (const double*)c->sigf_shadow.p + lo, sizeof(double) * (size_t)(hi - lo),
+                           cudaMemcpyDeviceToDevice, st));
+    }
     c->last_grid = g2; c->last_bps = cfg.blocks_per_sm; c->last_smem = (int64_t)cfg.smem; c->last_wtot = cfg.wtot;
     c->last_nt = cfg.nt; c->last_ch = cfg.ch;
     k_finalize<<<1, 64, 0, st>>>(p.partials, g2, nacc, acc);
@@ -563,9 +626,27 @@ __global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ Engine
     __shared__ long long scan_s[VB_NT / 32];
     __shared__ uint32_t base_s[VB_MAXD];
     extern __shared__ uint32_t y0_s[];          // [VB_CH][dim]
+    __shared__ long long item_s[3];
     const int tid = threadIdx.x;
     const int dim = p.map.dim;
-    for (int64_t lc = p.chunk_begin + blockIdx.x; lc < p.chunk_end; lc += gridDim.x) {
+    // work items as in k_engine (a chunk, or one of the nsub parts of a chunk the allocation piled
+    // samples onto), dealt round-robin: items are bounded in size, so this balances
+    for (int64_t it = p.item_begin + blockIdx.x; it < p.item_end; it += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) {
+            if (p.item_off == nullptr) { item_s[0] = it; item_s[1] = 0; item_s[2] = 1; }
+            else {
+                int64_t lo = p.chunk_begin, hi = p.chunk_end;      // item_off[lo] <= it < item_off[hi]
+                while (hi - lo > 1) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (p.item_off[mid] <= it) lo = mid; else hi = mid;
+                }
+                item_s[0] = lo; item_s[1] = it - p.item_off[lo]; item_s[2] = p.item_off[lo + 1] - p.item_off[lo];
+            }
+        }
+        __syncthreads();
+        const int64_t lc = item_s[0];
+        const long long sub = item_s[1], nsub = item_s[2];
         const int64_t lh0 = lc * VB_CH;
         const int64_t h0 = local_to_global(p.st, lh0);
         const int n_mine = (lh0 + tid < p.st.nlocal) ? alloc_neval(p.al, lh0 + tid) : 0;
@@ -587,7 +668,17 @@ __global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ Engine
         }
         __syncthreads();
         const int64_t chunk_row = p.chunk_off[lc] - p.row0;
-        for (long long i = tid; i < total; i += VB_NT) {
+        long long i0 = 0, i1 = total;                  // rows of this item: whole cubes (see k_engine)
+        if (nsub > 1) {
+            const long long b0 = total * sub / nsub, b1 = total * (sub + 1) / nsub;
+            int lo = -1, hi = VB_CH;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b0) hi = mid; else lo = mid; }
+            i0 = ex_s[hi];
+            lo = hi - 1; hi = VB_CH;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b1) hi = mid; else lo = mid; }
+            i1 = ex_s[hi];
+        }
+        for (long long i = i0 + tid; i < i1; i += VB_NT) {
             int lo = 0, hi = VB_CH;
             while (hi - lo > 1) {
                 int mid = (lo + hi) >> 1;
@@ -657,7 +748,9 @@ static int sample_common(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_
     p.row0 = r[0];
     SampleOut o = o0;
     o.rows = r[1] - r[0];
-    const int64_t nch = chunk_end - chunk_begin;
+    rc = set_items(c, p);
+    if (rc) return rc;
+    const int64_t nch = p.item_end - p.item_begin;
     int64_t g = (int64_t)c->sm_count * 8;
     if (g > nch) g = nch;
     size_t smem = sizeof(uint32_t) * (size_t)VB_CH * c->map.dim;
