@@ -353,7 +353,19 @@ def test_split_chunks_big_cubes_and_batches(monkeypatch):
 
 
 # ----------------------------------------------------------------------------- light geometry
-@pytest.mark.parametrize('name', ['poly2', 'gauss4', 'ridge4_nomap', 'genz10_pp', 'genz10_osc', 'genz3_corner'])
+@pytest.mark.parametrize('name', ['gauss4', 'genz10_pp', 'peaks20'])
+def test_split_chunks_light_geometry(name, monkeypatch):
+    """work items in the light geometry (1024-cube chunks cut into items of 4 x 256 samples)"""
+    monkeypatch.setenv('VB200_ITEM', '256')
+    monkeypatch.setenv('VB200_LIGHT', '1')
+    limits, f, kw = _cases()[name]
+    eng = run_engine_iterations(limits, f, nitn=3, seed=99, **kw)
+    assert all(r['launch']['threads'] == 512 for r in eng), eng[0]['launch']
+    ora = run_oracle_iterations(limits, f, nitn=3, seed=99, engine=eng, **kw)
+    compare_iterations(eng, ora, rtol=RTOL, var_rtol=1e-10)
+
+
+@pytest.mark.parametrize('name', ['poly2', 'gauss4', 'ridge4_nomap', 'genz10_pp', 'genz10_osc', 'genz3_corner', 'peaks20'])
 def test_light_geometry_vs_oracle(name, monkeypatch):
     """the one-big-CTA-per-SM geometry (512 threads, 1024-cube chunks, grid + histogram windows in
     shared memory), forced on problems that would normally be too small for it, vs the oracle"""

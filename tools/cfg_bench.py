@@ -23,6 +23,8 @@ for name, (mk, limits, kw) in CFG.items():
     if len(sys.argv) > 2:
         kw['neval'] = float(sys.argv[2])
     f = mk()
+    if os.environ.get('CFG_ALPHA'):
+        kw['alpha'] = float(os.environ['CFG_ALPHA'])
     integ = vegas.Integrator(limits, seed=5, **kw)
     integ(f, nitn=5)
     integ._timing = []

@@ -15,6 +15,10 @@ struct LaunchCfg {
     int sm_count;
     size_t smem_per_sm, smem_optin;   // device limits
     bool light;                       // use the one-big-CTA-per-SM geometry (fused sources only)
+    // work items of the launch's chunk range, per geometry ([0]: VB_CH-cube chunks, [1]: VB_LCH-cube
+    // chunks, whole range only); item_off == nullptr: one item per chunk
+    const int64_t* item_off[2];
+    int64_t item_begin[2], item_end[2];
     // out
     int nt, ch;                       // CTA size and cubes per chunk of the chosen instantiation
     int cap;                          // staged samples per tile
@@ -89,7 +93,8 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     const int dim = p.map.dim;
     cfg.nt = NT; cfg.ch = CH;
     // staging capacity: ~16 samples per thread, at most 32 KB (heavy) / 64 KB (light)
-    int cap = vb_env_int(CH == VB_CH ? "VB200_CAP" : "VB200_LCAP", 16 * NT);
+    // (light geometry above 10 dimensions: 4 per thread -- the histogram windows need the room)
+    int cap = vb_env_int(CH == VB_CH ? "VB200_CAP" : "VB200_LCAP", (CH != VB_CH && !Src::GRIDW ? 4 : 16) * NT);
     const int lim = ((CH == VB_CH ? 32 : 64) * 1024) / (8 * NF);
     if (cap > lim) cap = lim;
     if (cap < 256) cap = 256;
@@ -101,7 +106,10 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
         p.chunk_end = (p.st.nlocal + CH - 1) / CH;
     }
     cfg.nchunks = p.chunk_end - p.chunk_begin;
-    const int64_t nwork = CH == VB_CH ? p.item_end - p.item_begin : cfg.nchunks;   // claimable work items
+    const int gi = CH == VB_CH ? 0 : 1;
+    p.item_off = cfg.item_off[gi]; p.item_begin = cfg.item_begin[gi]; p.item_end = cfg.item_end[gi];
+    if (p.item_off == nullptr) { p.item_begin = p.chunk_begin; p.item_end = p.chunk_end; }
+    const int64_t nwork = p.item_end - p.item_begin;                // claimable work items
     const int max_grid = (int)(nwork < 0x7fffffff ? nwork : 0x7fffffff);
     // pass 1: residency without the windows (registers / staging buffer decide)
     vb_plan_windows(p, CH, 0, false);
@@ -151,4 +159,4 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
 #define VB_CASE_D(F, fobj, DD)                                                                 \
     if (dim_ <= DD) { FusedSrc<F, DD> s_{fobj}; return launch_engine(p, s_, cfg, st); }
 #define VB_CASE_L(F, fobj, DD)                                                                 \
-    if (cfg.light && dim_ <= DD) { FusedSrc<F, DD, true> s_{fobj}; return launch_engine(p, s_, cfg, st); }
+    if (cfg.light && dim_ <= DD) { FusedSrc<F, DD, true, (DD <= 10)> s_{fobj}; return launch_engine(p, s_, cfg, st); }

@@ -44,8 +44,8 @@ struct EngineP {
     int64_t scratch_stride;
     int64_t chunk_begin, chunk_end;   // local chunk range of this launch
     unsigned long long* work_counter; // zeroed before the launch: next work item to claim
-    // work items (heavy geometry): item j of the launch is global item item_begin + j; chunk lc owns
-    // items [item_off[lc], item_off[lc+1]) (item_off == nullptr: one item per chunk, item j == chunk j)
+    // work items: item j of the launch is global item item_begin + j; chunk lc (CH cubes of the launched
+    // geometry) owns items [item_off[lc], item_off[lc+1]) (item_off == nullptr: item j == chunk j)
     const int64_t* item_off;          // [nchunks+1]
     int64_t item_begin, item_end;
     int64_t cstride[VB_MAXD];  // cstride[d] = prod_{e<d} nstrat[e]
@@ -409,14 +409,16 @@ static __device__ __noinline__ void train_cube(const EngineP& p, const HistW& H,
 #ifndef VB_LCH
 #define VB_LCH 1024
 #endif
-template <class F, int D, bool LIGHT = false>
+template <class F, int D, bool LIGHT = false, bool GW = LIGHT>
 struct FusedSrc {
     static constexpr int NF = F::NF;
     static constexpr int NT = LIGHT ? VB_LNT : VB_ENT;             // threads per CTA
     static constexpr int CH = LIGHT ? VB_LCH : VB_CH;              // hypercubes per chunk
-    static constexpr int MINB = LIGHT ? 1 : ((D <= 10 && F::NF == 1) ? 3 : 2);   // resident CTAs per SM the register budget is set for
-    static constexpr bool GRIDW = LIGHT;                           // grid windows in shared memory
-    typedef typename std::conditional<LIGHT, uint16_t, uint32_t>::type dig_t;   // stratum digits of a cube
+    static constexpr int MINB = LIGHT ? 1 : (F::NF == 1 ? 3 : 2);   // resident CTAs per SM the register budget is set for
+    static constexpr bool GRIDW = GW;                              // grid windows in shared memory (light, D <= 10)
+    // stratum digits of a cube (light: narrow, to leave the shared memory to the histogram windows;
+    // the host falls back to the heavy geometry when a digit does not fit)
+    typedef typename std::conditional<LIGHT, typename std::conditional<(D > 10), uint8_t, uint16_t>::type, uint32_t>::type dig_t;
     F f;
     __device__ __forceinline__ void sample(const EngineP& p, const HistW& H, int n, int64_t h, uint32_t k,
                                            int64_t /*row*/, const dig_t* y0, double (&wf)[NF]) const
@@ -425,7 +427,11 @@ struct FusedSrc {
         double x[D];
         unsigned code[D];     // training slot of axis d, see hist_slot_code
         double jac = 1.0;
-#pragma unroll
+        // Above 10 dimensions the axis loops stay rolled (x[], code[] then live in local memory, which
+        // is lane-interleaved and L1-resident): fully unrolled, the 20-D kernels were bound by
+        // instruction fetch (ncu: stall_no_instruction on top).
+        constexpr int UNR = D > 10 ? 1 : (D + 1) / 2;
+#pragma unroll UNR
         for (int pr = 0; pr < (D + 1) / 2; ++pr) {
             if (2 * pr < dim) {
                 double u[2];
@@ -469,7 +475,8 @@ struct FusedSrc {
             double a = wf[0] * (double)n;
             double fdv2 = __dmul_rn(a, a);
             // 4 axes at a time: their CAS loops run side by side
-#pragma unroll
+            constexpr int UNRH = D > 10 ? 1 : (D + 3) / 4;
+#pragma unroll UNRH
             for (int d0 = 0; d0 < D; d0 += 4) {
                 if (d0 < dim) {
                     uint32_t sa[4];
@@ -675,7 +682,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
         __syncthreads();                       // previous item fully consumed
         if (tid == 0) {
             long long j = (long long)atomicAdd(p.work_counter, 1ull);
-            if (CH != VB_CH || p.item_off == nullptr) {
+            if (p.item_off == nullptr) {
                 next_s = p.chunk_begin + j;                        // one item per chunk
                 sub_s[0] = 0; sub_s[1] = 1;
             } else if ((j += p.item_begin) >= p.item_end) {

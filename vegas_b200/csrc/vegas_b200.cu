@@ -73,6 +73,8 @@ struct vb200_ctx {
     AllocP al;
     int64_t plan_total = 0, plan_min = 0, plan_max = 0;
     int64_t plan_max_chunk = 0, plan_items = 0;
+    int64_t nsuper = 0, plan_super_items = -1;            // light geometry: VB_LCH-cube chunks and their items (-1: not planned)
+    DevBuf super_items, super_item_off;
     DevBuf chunk_tot, chunk_off, chunk_items, item_off, stats;
     std::vector<long long> chunk_off_host;   // fetched lazily by the unfused path
     std::vector<long long> item_off_host;    // same (only when some chunk was split: plan_items != nchunks)
@@ -118,7 +120,7 @@ extern "C" void vb200_destroy(vb200_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    c->grid.release(); c->chunk_tot.release(); c->chunk_off.release(); c->chunk_items.release(); c->item_off.release(); c->stats.release();
+    c->grid.release(); c->chunk_tot.release(); c->chunk_off.release(); c->chunk_items.release(); c->item_off.release(); c->super_items.release(); c->super_item_off.release(); c->stats.release();
     c->fparams.release(); c->partials.release(); c->scratch.release(); c->counter.release(); c->sigf_shadow.release();
     delete c;
 }
@@ -369,6 +371,18 @@ __global__ void __launch_bounds__(1024) k_scan(const long long* tot, int64_t n, 
     if (tid == 0) off[n] = carry_s;
 }
 
+// items of the light geometry's chunks (group consecutive VB_CH-cube chunks each)
+__global__ void k_super_items(const long long* chunk_tot, int64_t nchunks, int group, long long item_samples,
+                              int max_items, int64_t nsuper, long long* out)
+{
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nsuper; s += (int64_t)gridDim.x * blockDim.x) {
+        long long t = 0;
+        for (int g = 0; g < group; ++g) if (s * group + g < nchunks) t += chunk_tot[s * group + g];
+        long long m = (t + item_samples - 1) / item_samples;
+        out[s] = m < 1 ? 1 : (m > max_items ? max_items : m);
+    }
+}
+
 extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sigf, int64_t min_nh, int64_t max_nh,
                           int64_t uniform_neval, int32_t* neval_hcube_dev, int64_t stats_host[4], void* stream)
 {
@@ -403,15 +417,28 @@ extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sig
         k_scan<<<1, 1024, 0, st>>>((const long long*)c->chunk_tot.p, nch, (long long*)c->chunk_off.p);
         k_scan<<<1, 1024, 0, st>>>((const long long*)c->chunk_items.p, nch, (long long*)c->item_off.p);
         c->launches += 3;
+        if (c->light_hint) {
+            const int group = VB_LCH / VB_CH;
+            c->nsuper = (nch + group - 1) / group;
+            CK(c->super_items.ensure(sizeof(long long) * (size_t)(c->nsuper + 1)));
+            CK(c->super_item_off.ensure(sizeof(long long) * (size_t)(c->nsuper + 1)));
+            k_super_items<<<(int)((c->nsuper + 255) / 256 < 1024 ? (c->nsuper + 255) / 256 : 1024), 256, 0, st>>>(
+                (const long long*)c->chunk_tot.p, nch, group, item_samples * group, VB_LCH, c->nsuper, (long long*)c->super_items.p);
+            k_scan<<<1, 1024, 0, st>>>((const long long*)c->super_items.p, c->nsuper, (long long*)c->super_item_off.p);
+            c->launches += 2;
+        }
         CK(cudaGetLastError());
     } else {
         CK(cudaMemsetAsync(c->chunk_off.p, 0, sizeof(long long), st));
         CK(cudaMemsetAsync(c->item_off.p, 0, sizeof(long long), st));
     }
-    long long out[4], nitems = 0;
+    long long out[4], nitems = 0, nsitems = -1;
     CK(cudaMemcpyAsync(out, c->stats.p, sizeof out, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&nitems, (const long long*)c->item_off.p + nch, sizeof nitems, cudaMemcpyDeviceToHost, st));
+    if (c->light_hint && nch > 0)
+        CK(cudaMemcpyAsync(&nsitems, (const long long*)c->super_item_off.p + c->nsuper, sizeof nsitems, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    c->plan_super_items = nsitems;
     if (nch == 0) out[1] = 0;
     c->plan_total = out[0]; c->plan_min = out[1]; c->plan_max = out[2]; c->plan_max_chunk = out[3];
     c->plan_items = nitems;
@@ -431,26 +458,29 @@ static int fetch_chunk_off(vb200_ctx* c)
     return 0;
 }
 
-// items of the local chunk range [chunk_begin, chunk_end): p.item_off / item_begin / item_end
-static int set_items(vb200_ctx* c, EngineP& p)
+// work items of the local chunk range [chunk_begin, chunk_end) for the heavy geometry (and, for
+// whole-range launches, of the light geometry's chunks)
+struct ItemsSel { const int64_t* off[2]; int64_t begin[2], end[2]; };
+static int set_items(vb200_ctx* c, int64_t chunk_begin, int64_t chunk_end, ItemsSel& it)
 {
-    if (c->plan_items == c->nchunks) {                 // nothing was split: item j == chunk j
-        p.item_off = nullptr;
-        p.item_begin = p.chunk_begin; p.item_end = p.chunk_end;
-        return 0;
+    it.off[0] = it.off[1] = nullptr;
+    it.begin[0] = chunk_begin; it.end[0] = chunk_end;
+    it.begin[1] = 0; it.end[1] = -1;                   // light: unavailable unless set below
+    const bool whole = chunk_begin == 0 && chunk_end == c->nchunks;
+    if (whole && c->plan_super_items >= 0) {
+        it.end[1] = c->nsuper;
+        if (c->plan_super_items != c->nsuper) { it.off[1] = (const int64_t*)c->super_item_off.p; it.end[1] = c->plan_super_items; }
     }
-    p.item_off = (const int64_t*)c->item_off.p;
-    if (p.chunk_begin == 0 && p.chunk_end == c->nchunks) {
-        p.item_begin = 0; p.item_end = c->plan_items;
-        return 0;
-    }
+    if (c->plan_items == c->nchunks) return 0;         // nothing was split: item j == chunk j
+    it.off[0] = (const int64_t*)c->item_off.p;
+    if (whole) { it.begin[0] = 0; it.end[0] = c->plan_items; return 0; }
     if (c->item_off_host.empty()) {
         CK(cudaSetDevice(c->device));
         c->item_off_host.resize((size_t)c->nchunks + 1);
         CK(cudaMemcpy(c->item_off_host.data(), c->item_off.p, sizeof(long long) * (size_t)(c->nchunks + 1), cudaMemcpyDeviceToHost));
     }
-    p.item_begin = c->item_off_host[(size_t)p.chunk_begin];
-    p.item_end = c->item_off_host[(size_t)p.chunk_end];
+    it.begin[0] = c->item_off_host[(size_t)chunk_begin];
+    it.end[0] = c->item_off_host[(size_t)chunk_end];
     return 0;
 }
 
@@ -525,16 +555,16 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     // light geometry (one big CTA per SM): cheap integrand, digits fit 16 bits, and enough big chunks
     // to keep every SM busy; VB200_LIGHT=0/1 overrides the work-size test (developer switch)
     bool light = fused && c->light_hint;
-    for (int d = 0; d < c->map.dim; ++d) if (c->st.nstrat[d] > 65535) light = false;
+    for (int d = 0; d < c->map.dim; ++d) if (c->st.nstrat[d] > (c->map.dim > 10 ? 255 : 65535)) light = false;   // FusedSrc::dig_t
     const int force = vb_env_int("VB200_LIGHT", -1);
     if (force == 0) light = false;
     if (force != 1 && c->st.nlocal < (int64_t)VB_LCH * 4 * c->sm_count) light = false;
-    // the light geometry claims whole 1024-cube chunks: not for allocations so skewed that a single
-    // 256-cube chunk holds more than 1/(4 * SMs) of the samples (the heavy geometry splits those)
-    if (force != 1 && c->plan_max_chunk * 4 * c->sm_count > c->plan_total) light = false;
-    cfg.light = light;
-    int rc_items = set_items(c, p);
+    ItemsSel it;
+    int rc_items = set_items(c, p.chunk_begin, p.chunk_end, it);
     if (rc_items) return rc_items;
+    if (it.end[1] < 0) light = false;                  // light chunks were not planned (set_integrand after plan)
+    cfg.light = light;
+    for (int g = 0; g < 2; ++g) { cfg.item_off[g] = it.off[g]; cfg.item_begin[g] = it.begin[g]; cfg.item_end[g] = it.end[g]; }
     auto launch = [&](cudaStream_t s) { return fused ? do_launch_fused(c, p, cfg, s) : launch_buffer(p, nf, cfg, s); };
     int grid = launch(VB_DRYRUN);
     if (grid == -22) return fail(-4, "engine: no kernel compiled for dim=%d nf=%d integrand=%d", p.map.dim, nf, c->fid);
@@ -554,7 +584,7 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     // CTAs (items), one of them must not see the new sigf of a cube another has already finished
     // -> write to a shadow buffer and copy the launch's cube range back afterwards
     double* const sigf_user = p.sigf_out;
-    const bool shadow = p.item_off != nullptr && (p.flags & VBF_UPDATE_SIGF) && sigf_user != nullptr;
+    const bool shadow = (it.off[0] != nullptr || it.off[1] != nullptr) && (p.flags & VBF_UPDATE_SIGF) && sigf_user != nullptr;
     if (shadow) {
         CK(c->sigf_shadow.ensure(sizeof(double) * (size_t)c->st.nlocal));
         p.sigf_out = (double*)c->sigf_shadow.p;
@@ -748,8 +778,10 @@ static int sample_common(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_
     p.row0 = r[0];
     SampleOut o = o0;
     o.rows = r[1] - r[0];
-    rc = set_items(c, p);
+    ItemsSel it;
+    rc = set_items(c, chunk_begin, chunk_end, it);
     if (rc) return rc;
+    p.item_off = it.off[0]; p.item_begin = it.begin[0]; p.item_end = it.end[0];
     const int64_t nch = p.item_end - p.item_begin;
     int64_t g = (int64_t)c->sm_count * 8;
     if (g > nch) g = nch;
