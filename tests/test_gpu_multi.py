@@ -71,7 +71,10 @@ def test_two_gpus_match_one(light):
             np.testing.assert_allclose(a['var'], b['var'], rtol=1e-11)
             np.testing.assert_allclose(a['sum_sigf'], b['sum_sigf'], rtol=1e-12)
             assert np.array_equal(a['n_f'], b['n_f'])
-            np.testing.assert_allclose(a['sum_f'], b['sum_f'], rtol=1e-12, atol=1e-300)
+            # from the second iteration on the two runs start from grids that differ in the last bit
+            # (atomic summation order), and inc = g[i+1] - g[i] amplifies that ~1e3x in J^2: two
+            # single-GPU runs differ by the same ~1e-12 in the tail bins
+            np.testing.assert_allclose(a['sum_f'], b['sum_f'], rtol=1e-10, atol=1e-300)
         np.testing.assert_allclose(mean, one[1], rtol=1e-12)
         np.testing.assert_allclose(sigf, one[3], rtol=1e-8, atol=1e-300)
         np.testing.assert_allclose(grid, one[4], rtol=1e-10, atol=1e-14)

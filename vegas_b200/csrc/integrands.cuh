@@ -245,8 +245,8 @@ struct FPathInt {
         double x[D], Vx[D];
         double a = T / dim, m_2a = m / 2. / a;
         double jac = norm, jac_x0 = norm_x0;
-#pragma unroll
-        for (int j = 0; j < D; ++j)
+#pragma unroll 1
+        for (int j = 0; j < D; ++j)            // rolled: D inlined copies of tan() made the kernel instruction-fetch bound
             if (j < dim) {
                 x[j] = xscale * tan(th[j]);
                 Vx[j] = V(x[j]);
