@@ -167,6 +167,19 @@ def test_unfused_iterations_vs_oracle(name):
     compare_iterations(eng, ora, rtol=RTOL, var_rtol=1e-10)
 
 
+def test_unfused_philox_replay_equals_bins():
+    """reduce kernel: training bins re-derived from the Philox counter (train_bins=False) == bins
+    handed over by the sampler"""
+    limits, f, kw = _cases()['pathint10']
+    a = run_engine_iterations(limits, f, nitn=2, seed=5, fused=False, train_bins=True, **kw)
+    b = run_engine_iterations(limits, f, nitn=2, seed=5, fused=False, train_bins=False, **kw)
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra['neval_hcube'], rb['neval_hcube'])
+        assert np.array_equal(ra['n_f'], rb['n_f'])
+        np.testing.assert_allclose(ra['mean'], rb['mean'], rtol=1e-12)
+        np.testing.assert_allclose(ra['sum_f'], rb['sum_f'], rtol=1e-10, atol=1e-300)
+
+
 def test_fused_equals_unfused_streams():
     """the fused kernel and the unfused path consume the same samples"""
     limits, f, kw = _cases()['gauss4']

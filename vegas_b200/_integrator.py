@@ -35,7 +35,9 @@ class Integrator(object):
     (not in ``defaults``): ``device`` (CUDA device index, default the current device), ``seed``
     (Philox key; default drawn from ``gvar.RNG`` so ``gvar.ranseed`` makes runs reproducible),
     ``fused`` (use the compiled device functor when the integrand has one; default True),
-    ``max_batch`` (rows per batch handed to device callbacks).
+    ``max_batch`` (rows per batch handed to device callbacks), ``train_bins`` (callback path: pass the
+    samples' training bins from the sampler to the reduce kernel through HBM, 2 bytes per axis,
+    instead of replaying the Philox stream there; default True).
     """
 
     # Settings accessible via the constructor and Integrator.set (same keys as _vegas.pyx:1115-1140)
@@ -66,7 +68,7 @@ class Integrator(object):
         nproc=1,                # number of processors to use
     )
     # engine-specific settings (kept out of ``defaults`` so that dict mirrors the reference)
-    engine_defaults = dict(device=None, seed=None, fused=True, max_batch=1 << 22, slab=None)
+    engine_defaults = dict(device=None, seed=None, fused=True, max_batch=1 << 22, slab=None, train_bins=True)
 
     def __init__(self, map, **kargs):
         self.neval_hcube_range = None
@@ -736,10 +738,15 @@ class Integrator(object):
             x = torch.empty((rows, self.dim), dtype=torch.float64, device=ctx.device)
             wgt = torch.empty(rows, dtype=torch.float64, device=ctx.device)
             jac1d = torch.empty_like(x) if self.uses_jac else None
+            # training bins travel from the sampler to the reduce kernel (2 bytes per axis) instead of
+            # being re-derived there from the Philox counter
+            bins = (torch.empty((rows, self.dim), dtype=torch.int16, device=ctx.device)
+                    if (flags & _lib.TRAIN) and self.train_bins and not self.uses_jac
+                    and int(np.max(self.map.ninc)) <= 0xffff else None)
             if self._timing is not None:
                 tev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 tev[0].record()
-            ctx.sample(pitn, c0, c1, x, wgt, jac1d=jac1d)
+            ctx.sample(pitn, c0, c1, x, wgt, jac1d=jac1d, bins=bins)
             if self._timing is not None:
                 tev[1].record()
             if on_device:
@@ -754,7 +761,7 @@ class Integrator(object):
                                  % (tuple(fx.shape), rows, (rows, nf)))
             if self._timing is not None:
                 tev[2].record()
-            ctx.reduce(pitn, self.beta, flags, c0, c1, fx, nf, wgt, self._sigf_dev, acc, sum_f, n_f, hs, status)
+            ctx.reduce(pitn, self.beta, flags, c0, c1, fx, nf, wgt, self._sigf_dev, acc, sum_f, n_f, hs, status, bins=bins)
             if self._timing is not None:
                 tev[3].record()
                 self._unfused_events.append((tev, rows))

@@ -82,8 +82,8 @@ def load():
     L.vb200_plan.argtypes = [vp, vp, f64, i64, i64, i64, vp, pi64, vp]
     L.vb200_chunk_offsets.argtypes = [vp, vp, i64]
     L.vb200_iterate_fused.argtypes = [vp, u32, f64, i32, vp, vp, vp, vp, i64, vp, vp]
-    L.vb200_sample.argtypes = [vp, u32, i64, i64, vp, vp, vp, vp, vp, i32, vp]
-    L.vb200_reduce.argtypes = [vp, u32, f64, i32, i64, i64, vp, i32, vp, vp, vp, vp, vp, i64, vp, vp]
+    L.vb200_sample.argtypes = [vp, u32, i64, i64, vp, vp, vp, vp, vp, vp, i32, vp]
+    L.vb200_reduce.argtypes = [vp, u32, f64, i32, i64, i64, vp, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp]
     L.vb200_map.argtypes = [vp, vp, vp, vp, i64, vp]
     L.vb200_invmap.argtypes = [vp, vp, vp, vp, i64, vp]
     L.vb200_jac1d.argtypes = [vp, vp, vp, i64, vp]
@@ -97,7 +97,7 @@ def load():
     for name in SYMBOLS:
         if name not in ('vb200_last_error', 'vb200_destroy', 'vb200_launch_count'):
             getattr(L, name).restype = i32
-    if L.vb200_abi_version() != 1:
+    if L.vb200_abi_version() != 2:
         raise VegasB200Error('vegas_b200: ABI version mismatch')
     _lib = L
     return L
@@ -182,13 +182,13 @@ class Context(object):
         check(self.L.vb200_iterate_fused(self.h, itn, float(beta), flags, _ptr(sigf), _ptr(acc), _ptr(sum_f),
                                          _ptr(n_f), hstride, _ptr(status), _stream()))
 
-    def sample(self, itn, c0, c1, x, wgt, y=None, jac1d=None, hcube=None, transposed=False):
+    def sample(self, itn, c0, c1, x, wgt, y=None, jac1d=None, hcube=None, transposed=False, bins=None):
         check(self.L.vb200_sample(self.h, itn, c0, c1, _ptr(x), _ptr(wgt), _ptr(y), _ptr(jac1d), _ptr(hcube),
-                                  int(transposed), _stream()))
+                                  _ptr(bins), int(transposed), _stream()))
 
-    def reduce(self, itn, beta, flags, c0, c1, f, nf, wgt, sigf, acc, sum_f, n_f, hstride, status):
+    def reduce(self, itn, beta, flags, c0, c1, f, nf, wgt, sigf, acc, sum_f, n_f, hstride, status, bins=None):
         check(self.L.vb200_reduce(self.h, itn, float(beta), flags, c0, c1, _ptr(f), nf, _ptr(wgt), _ptr(sigf),
-                                  _ptr(acc), _ptr(sum_f), _ptr(n_f), hstride, _ptr(status), _stream()))
+                                  _ptr(acc), _ptr(sum_f), _ptr(n_f), hstride, _ptr(bins), _ptr(status), _stream()))
 
     def uniforms(self, itn, c0, c1, u):
         check(self.L.vb200_uniforms(self.h, itn, c0, c1, _ptr(u), _stream()))

@@ -13,6 +13,7 @@
 #define VB_ENT 128          // threads per CTA of the engine kernel (VB_CH / VB_ENT cubes per thread in set-up)
 #endif
 #define VB_ITEM 4096        // samples per work item: chunks holding more are cut into several items (k_plan)
+#define VB_MAXITEMS 4096    // most items one chunk is cut into
 #define VB_WARP_CUBE 64     // cubes with more samples than this are reduced by a whole warp
 #define VB_EPSILON (2.220446049250313e-16 * 1e4)   // reference EPSILON, _vegas.pyx:36
 

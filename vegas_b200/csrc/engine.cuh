@@ -57,6 +57,7 @@ struct EngineP {
     // unfused path
     const double* fbuf;        // [rows][nf]
     const double* wbuf;        // [rows]
+    const uint16_t* bins;      // [rows][dim] training bins written by the sampler (nullptr: replay Philox)
     const int64_t* chunk_off;  // [nchunks+1] exclusive scan of samples per chunk
     int64_t row0;              // chunk_off[chunk_begin]
 };
@@ -533,6 +534,22 @@ struct BufferSrc {
         if (p.flags & VBF_TRAIN) {
             double a = wf[0] * (double)n;
             double fdv2 = a * a;
+            if (p.bins != nullptr) {
+                // bins from the sampler; 4 axes at a time so their CAS loops run side by side
+                const int dim = p.map.dim;
+                const uint16_t* b = p.bins + row * dim;
+#pragma unroll 1
+                for (int d0 = 0; d0 < dim; d0 += 4) {
+                    uint32_t sa[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int d = d0 + j;
+                        const unsigned bv = d < dim ? b[d] : 0xffffu;
+                        sa[j] = hist_slot(p, H, d < dim ? d : 0, bv == 0xffffu ? -1 : (int)bv, fdv2);
+                    }
+                    hist_sum_slots4(sa[0], sa[1], sa[2], sa[3], fdv2);
+                }
+            } else
             for (int pr = 0; 2 * pr < p.map.dim; ++pr) {
                 double ua, ub;
                 philox_pair(p.key, p.itn, h, k, pr, ua, ub);

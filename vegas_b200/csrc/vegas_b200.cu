@@ -290,8 +290,9 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
 // allocation pre-pass + chunk offsets
 // ---------------------------------------------------------------------------------------------
 // stats: [0] sum  [1] min  [2] max  [3] largest chunk total   (unsigned long long / long long)
-// chunk_items[lc] = work items chunk lc is cut into: 1, or ceil(total / item_samples) <= VB_CH when
-// the vegas+ allocation piled more than item_samples samples onto its cubes (engine.cuh, "items")
+// chunk_items[lc] = work items chunk lc is cut into: 1, or ceil(total / item_samples) when the vegas+
+// allocation piled more than item_samples samples onto its cubes (engine.cuh, "items").  The engine
+// never splits a cube (items that no cube starts in are empty); the samplers split by rows.
 __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t nchunks, int32_t* neval_out,
                                                 long long* chunk_tot, long long* chunk_items, long long item_samples,
                                                 long long* stats)
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t n
             for (int i = 0; i < VB_NT / 32; ++i) t += red[i];
             chunk_tot[lc] = t;
             long long m = (t + item_samples - 1) / item_samples;
-            chunk_items[lc] = m < 1 ? 1 : (m > VB_CH ? VB_CH : m);
+            chunk_items[lc] = m < 1 ? 1 : (m > VB_MAXITEMS ? VB_MAXITEMS : m);
             my_sum += t;
             if (t > my_maxc) my_maxc = t;
         }
@@ -621,7 +622,8 @@ extern "C" int vb200_iterate_fused(vb200_ctx* c, uint32_t itn, double beta, int 
 
 extern "C" int vb200_reduce(vb200_ctx* c, uint32_t itn, double beta, int flags, int64_t chunk_begin, int64_t chunk_end,
                             const double* f_dev, int nf, const double* wgt_dev, double* sigf_dev, double* acc_dev,
-                            double* sum_f_dev, uint64_t* n_f_dev, int64_t hstride, int32_t* status_dev, void* stream)
+                            double* sum_f_dev, uint64_t* n_f_dev, int64_t hstride, const uint16_t* bins_dev,
+                            int32_t* status_dev, void* stream)
 {
     if (!c || !acc_dev || !f_dev || !wgt_dev) return fail(-1, "vb200_reduce: null argument");
     if (nf < 1 || nf > 8) return fail(-4, "vb200_reduce: nf=%d not compiled in (1..8)", nf);
@@ -635,7 +637,7 @@ extern "C" int vb200_reduce(vb200_ctx* c, uint32_t itn, double beta, int flags, 
     rc = fetch_chunk_off(c);
     if (rc) return rc;
     p.row0 = c->chunk_off_host[(size_t)chunk_begin];
-    p.fbuf = f_dev; p.wbuf = wgt_dev;
+    p.fbuf = f_dev; p.wbuf = wgt_dev; p.bins = bins_dev;
     return run_engine(c, p, nf, false, acc_dev, (cudaStream_t)stream);
 }
 
@@ -647,6 +649,7 @@ struct SampleOut {
     int x_transposed;
     int64_t rows;      // rows in this batch (for the transposed layout)
     double* u;         // raw uniforms (testing)
+    uint16_t* bins;    // [rows][dim] training bin of every sample (0xffff: none) for vb200_reduce
 };
 
 __global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ EngineP p, const __grid_constant__ SampleOut o)
@@ -698,16 +701,8 @@ __global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ Engine
         }
         __syncthreads();
         const int64_t chunk_row = p.chunk_off[lc] - p.row0;
-        long long i0 = 0, i1 = total;                  // rows of this item: whole cubes (see k_engine)
-        if (nsub > 1) {
-            const long long b0 = total * sub / nsub, b1 = total * (sub + 1) / nsub;
-            int lo = -1, hi = VB_CH;
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b0) hi = mid; else lo = mid; }
-            i0 = ex_s[hi];
-            lo = hi - 1; hi = VB_CH;
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b1) hi = mid; else lo = mid; }
-            i1 = ex_s[hi];
-        }
+        long long i0 = 0, i1 = total;                  // rows of this item
+        if (nsub > 1) { i0 = total * sub / nsub; i1 = total * (sub + 1) / nsub; }   // by rows: no per-cube state here
         for (long long i = i0 + tid; i < i1; i += VB_NT) {
             int lo = 0, hi = VB_CH;
             while (hi - lo > 1) {
@@ -757,6 +752,156 @@ __global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ Engine
     }
 }
 
+// The integration path's sampler: x[rows][dim] (or [dim][rows]), wgt[rows] and, optionally, the
+// samples' training bins.  Same items and arithmetic as k_sample; the differences are mechanical:
+// the axis loop is unrolled for D <= 10 (grid loads of all axes in flight together), and a warp's
+// 32 rows of x -- one contiguous block of the row-major array -- are staged in shared memory and
+// written out with full-line stores instead of 32 strided 8-byte stores per axis.
+template <int D, bool XT>
+__global__ void __launch_bounds__(VB_NT) k_sample_x(const __grid_constant__ EngineP p, const __grid_constant__ SampleOut o)
+{
+    __shared__ long long ex_s[VB_CH + 1];
+    __shared__ int n_s[VB_CH];
+    __shared__ long long scan_s[VB_NT / 32];
+    __shared__ uint32_t base_s[VB_MAXD];
+    __shared__ long long item_s[3];
+    extern __shared__ double sx_dyn[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int dim = p.map.dim;
+    const int S = dim | 1;                                       // odd row stride: conflict-free tile rows
+    double* tile = sx_dyn + (size_t)warp * 32 * S;               // [32][S] (row-major x only)
+    uint32_t* y0_s = (uint32_t*)(sx_dyn + (XT ? 0 : (size_t)(VB_NT / 32) * 32 * S));   // [VB_CH][dim]
+    uint16_t* btile = (uint16_t*)(y0_s + VB_CH * dim) + (size_t)warp * 32 * dim;       // [32][dim]
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) item_s[0] = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);   // items are claimed: CTAs finish together
+        __syncthreads();
+        const int64_t it = item_s[0];
+        if (it >= p.item_end) break;
+        __syncthreads();
+        if (tid == 0) {
+            if (p.item_off == nullptr) { item_s[0] = it; item_s[1] = 0; item_s[2] = 1; }
+            else {
+                int64_t lo = p.chunk_begin, hi = p.chunk_end;
+                while (hi - lo > 1) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (p.item_off[mid] <= it) lo = mid; else hi = mid;
+                }
+                item_s[0] = lo; item_s[1] = it - p.item_off[lo]; item_s[2] = p.item_off[lo + 1] - p.item_off[lo];
+            }
+        }
+        __syncthreads();
+        const int64_t lc = item_s[0];
+        const long long sub = item_s[1], nsub = item_s[2];
+        const int64_t lh0 = lc * VB_CH;
+        const int64_t h0 = local_to_global(p.st, lh0);
+        const int n_mine = (lh0 + tid < p.st.nlocal) ? alloc_neval(p.al, lh0 + tid) : 0;
+        if (tid < dim) base_s[tid] = (uint32_t)((h0 / p.cstride[tid]) % p.st.nstrat[tid]);
+        long long total;
+        long long ex = block_exscan<VB_NT>(n_mine, scan_s, &total);
+        ex_s[tid] = ex;
+        n_s[tid] = n_mine;
+        if (tid == VB_NT - 1) ex_s[VB_CH] = total;
+        {
+            uint32_t carry = (uint32_t)tid;
+            for (int d = 0; d < dim; ++d) {
+                uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
+                uint32_t qd = v / ns;
+                y0_s[tid * dim + d] = v - qd * ns;
+                carry = qd;
+            }
+        }
+        __syncthreads();
+        const int64_t chunk_row = p.chunk_off[lc] - p.row0;
+        long long i0 = 0, i1 = total;
+        if (nsub > 1) { i0 = total * sub / nsub; i1 = total * (sub + 1) / nsub; }   // by rows: no per-cube state here
+        for (long long ib = i0; ib < i1; ib += VB_NT) {           // warp-uniform trip count
+            const long long i = ib + tid;
+            const bool live = i < i1;
+            const int64_t row = chunk_row + i;
+            if (live) {
+                int lo = 0, hi = VB_CH;
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (ex_s[mid] <= i) lo = mid; else hi = mid;
+                }
+                const int c = lo;
+                const uint32_t k = (uint32_t)(i - ex_s[c]);
+                const int64_t h = h0 + c;
+                const uint32_t* y0 = y0_s + c * dim;
+                double jac = 1.0;
+                constexpr int UNR = D > 10 ? 1 : (D + 1) / 2;
+#pragma unroll UNR
+                for (int pr = 0; pr < (D + 1) / 2; ++pr) {
+                    if (2 * pr < dim) {
+                        double u[2];
+                        philox_pair(p.key, p.itn, h, k, pr, u[0], u[1]);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int d = 2 * pr + e;
+                            if (d < D && d < dim) {
+                                const int ni = p.map.ninc[d];
+                                const double y = div_exact((double)y0[d] + u[e], p.st.dns[d], p.st.rns[d]);
+                                const double t = __dmul_rn(y, p.dni[d]);
+                                const int iy = __double2int_rd(t);
+                                const int ic = min(iy, ni - 1);
+                                const double* gp = p.map.grid + (size_t)d * p.map.gstride + ic;
+                                const double g0 = __ldg(gp), g1 = __ldg(gp + 1);
+                                const double inc = g1 - g0;
+                                const double xin = __dadd_rn(g0, __dmul_rn(inc, __dsub_rn(t, (double)iy)));   // no FMA: pyx:354
+                                const double xv = iy < ni ? xin : g1;                                         // pyx:357-359
+                                jac *= inc * p.dni[d];
+                                if (XT) o.x[(int64_t)d * o.rows + row] = xv;
+                                else tile[lane * S + d] = xv;
+                                if (o.bins) btile[lane * dim + d] = (y > 0.0 && y < 1.0) ? (uint16_t)ic : (uint16_t)0xffff;   // pyx:460
+                            }
+                        }
+                    }
+                }
+                o.wgt[row] = jac * (p.dv_y / (double)n_s[c]);
+            }
+            __syncwarp();
+            // the warp's rows are consecutive: one contiguous block of x (and of bins)
+            const long long wfirst = ib + (tid - lane);
+            const int nlive = (int)(i1 - wfirst < 32 ? (i1 - wfirst > 0 ? i1 - wfirst : 0) : 32);
+            const int64_t wrow = chunk_row + wfirst;
+            const int nel = nlive * dim;
+            if (!XT) {
+                double* dst = o.x + wrow * dim;
+                for (int e = lane; e < nel; e += 32) {
+                    const int r = e / dim;
+                    dst[e] = tile[r * S + (e - r * dim)];
+                }
+            }
+            if (o.bins) {
+                uint16_t* dst = o.bins + wrow * dim;
+                for (int e = lane; e < nel; e += 32) dst[e] = btile[e];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int D>
+static int launch_sample_x(const EngineP& p, const SampleOut& o, int grid, cudaStream_t st)
+{
+    const int dim = p.map.dim;
+    const size_t tile = o.x_transposed ? 0 : sizeof(double) * (size_t)(VB_NT / 32) * 32 * (dim | 1);
+    size_t smem = tile + sizeof(uint32_t) * (size_t)VB_CH * dim + (o.bins ? sizeof(uint16_t) * (size_t)VB_NT * dim : 0);
+    smem = (smem + 15) & ~(size_t)15;
+    cudaError_t e;
+    if (o.x_transposed) {
+        e = cudaFuncSetAttribute(k_sample_x<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -(int)e - 1000;
+        k_sample_x<D, true><<<grid, VB_NT, smem, st>>>(p, o);
+    } else {
+        e = cudaFuncSetAttribute(k_sample_x<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -(int)e - 1000;
+        k_sample_x<D, false><<<grid, VB_NT, smem, st>>>(p, o);
+    }
+    return 0;
+}
+
 static int sample_common(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, const SampleOut& o0, void* stream)
 {
     if (!c->have_map || !c->have_strata) return fail(-1, "sample: map/strata not set");
@@ -785,20 +930,39 @@ static int sample_common(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_
     const int64_t nch = p.item_end - p.item_begin;
     int64_t g = (int64_t)c->sm_count * 8;
     if (g > nch) g = nch;
-    size_t smem = sizeof(uint32_t) * (size_t)VB_CH * c->map.dim;
-    k_sample<<<(int)g, VB_NT, smem, (cudaStream_t)stream>>>(p, o);
+    for (int d = 0; d < VB_MAXD; ++d) p.dni[d] = (double)c->map.ninc[d];
+    CK(c->counter.ensure(sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    p.work_counter = (unsigned long long*)c->counter.p;
+    if (o.x && o.wgt && !o.y && !o.jac1d && !o.hcube && !o.u) {
+        // the integration path: x, wgt (+ training bins)
+        const int dim = c->map.dim;
+        int e = dim <= 4 ? launch_sample_x<4>(p, o, (int)g, (cudaStream_t)stream)
+              : dim <= 8 ? launch_sample_x<8>(p, o, (int)g, (cudaStream_t)stream)
+              : dim <= 10 ? launch_sample_x<10>(p, o, (int)g, (cudaStream_t)stream)
+                          : launch_sample_x<VB_MAXD>(p, o, (int)g, (cudaStream_t)stream);
+        if (e) return fail(-2, "sample: launch set-up failed (%s)", cudaGetErrorString((cudaError_t)(-(e + 1000))));
+    } else {
+        if (o.bins) return fail(-1, "sample: training bins are only written together with x and wgt alone");
+        size_t smem = sizeof(uint32_t) * (size_t)VB_CH * c->map.dim;
+        k_sample<<<(int)g, VB_NT, smem, (cudaStream_t)stream>>>(p, o);
+    }
     c->launches += 1;
     CK(cudaGetLastError());
     return 0;
 }
 
 extern "C" int vb200_sample(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* x_dev, double* wgt_dev,
-                            double* y_dev, double* jac1d_dev, int64_t* hcube_dev, int x_transposed, void* stream)
+                            double* y_dev, double* jac1d_dev, int64_t* hcube_dev, uint16_t* bins_dev, int x_transposed, void* stream)
 {
     if (!c || !x_dev || !wgt_dev) return fail(-1, "vb200_sample: null argument");
+    if (bins_dev)
+        for (int d = 0; d < c->map.dim; ++d)
+            if (c->map.ninc[d] > 0xffff) return fail(-1, "vb200_sample: training bins need ninc <= 65535");
     SampleOut o;
     memset(&o, 0, sizeof o);
     o.x = x_dev; o.wgt = wgt_dev; o.y = y_dev; o.jac1d = jac1d_dev; o.hcube = hcube_dev; o.x_transposed = x_transposed;
+    o.bins = bins_dev;
     return sample_common(c, itn, chunk_begin, chunk_end, o, stream);
 }
 
