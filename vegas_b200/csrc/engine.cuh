@@ -516,7 +516,13 @@ template <int NF_>
 struct BufferSrc {
     static constexpr int NF = NF_;
     static constexpr int NT = VB_ENT, CH = VB_CH;
-    static constexpr int MINB = NF_ <= 4 ? 4 : 3;
+#ifndef VB_BUF_MINB_HI
+#define VB_BUF_MINB_HI 3
+#endif
+#ifndef VB_BUF_MINB_LO
+#define VB_BUF_MINB_LO 4
+#endif
+    static constexpr int MINB = NF_ <= 4 ? VB_BUF_MINB_LO : VB_BUF_MINB_HI;
     static constexpr bool GRIDW = false;
     typedef uint32_t dig_t;
     __device__ __forceinline__ void sample(const EngineP& p, const HistW& H, int n, int64_t h, uint32_t k,
