@@ -103,6 +103,21 @@ int  vb200_reduce(vb200_ctx* ctx, uint32_t itn, double beta, int flags, int64_t 
                   double* sigf_dev, double* acc_dev, double* sum_f_dev, uint64_t* n_f_dev,
                   int64_t hstride, const uint16_t* bins_dev, int32_t* status_dev, void* stream);
 
+/* The built-in functor on buffers: f_dev[rows][nf] = F(x_dev[rows][dim]) (same device code the fused
+ * kernel inlines; stands where the reference calls fcn.eval(x), pyx:2103-2131). */
+int  vb200_eval_integrand(vb200_ctx* ctx, const double* x_dev, int64_t rows, double* f_dev, void* stream);
+
+/* Stratification profile for vegas.restratify (src/vegas/__init__.py:1314-1419): per axis mu and
+ * y-bin i (yst_host = numpy.linspace(0, 1, ndy+1), ndy <= 32), mean and variance of the component
+ * dI[mu][i] = f * [yst[i] <= y_mu <= yst[i+1]] of the reference's auxiliary integrand
+ * (__init__.py:1390-1419), accumulated per hypercube with the two-pass of pyx:2142-2186
+ * (correlate_integrals=False) from the callback path's buffers of the same chunk range:
+ * f_dev[row*fstride] (component 0 of the integrand) and wgt_dev[row].  y is re-derived from the
+ * Philox counter.  acc_dev[(mu*ndy + i)*2 + {0: mean, 1: var}] += ... */
+int  vb200_dy_profile(vb200_ctx* ctx, uint32_t itn, int64_t chunk_begin, int64_t chunk_end,
+                      const double* f_dev, int fstride, const double* wgt_dev, int ndy,
+                      const double* yst_host, double* acc_dev, void* stream);
+
 /* AdaptiveMap array methods on device buffers (pyx:310-360, 362-416, 265-295, 421-464) */
 int  vb200_map(vb200_ctx* ctx, const double* y_dev, double* x_dev, double* jac_dev, int64_t n, void* stream);
 int  vb200_invmap(vb200_ctx* ctx, const double* x_dev, double* y_dev, double* jac_dev, int64_t n, void* stream);

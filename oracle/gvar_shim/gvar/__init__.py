@@ -71,6 +71,19 @@ class GVar(object):
     def internaldata(self):
         return (self.mean, self._terms)
 
+    # comparisons act on the means (as in gvar; the reference's restratify sorts weights with them)
+    def __lt__(self, other):
+        return self.mean < getattr(other, 'mean', other)
+
+    def __gt__(self, other):
+        return self.mean > getattr(other, 'mean', other)
+
+    def __le__(self, other):
+        return self.mean <= getattr(other, 'mean', other)
+
+    def __ge__(self, other):
+        return self.mean >= getattr(other, 'mean', other)
+
     @property
     def var(self):
         return float(_cov_between(self, self))
@@ -427,6 +440,14 @@ class BufferDict(dict):
 
     def __reduce__(self):
         return (BufferDict, ([(k, self[k]) for k in self],))
+
+    def _r2lbatch(self):
+        """rbatch values (batch index last) -> (lbatch BufferDict, None); used by the reference's
+        restratify auxiliary integrand (src/vegas/__init__.py:1419)"""
+        out = BufferDict()
+        for k in self:
+            out[k] = _np.moveaxis(_np.asarray(self[k]), -1, 0)
+        return out, None
 
 
 def asbufferdict(g):

@@ -407,3 +407,56 @@ def uavg(means, variances):
     dof = n - 1
     Q = float(gammaincc(dof / 2., chi2 / 2.)) if dof > 0 and chi2 >= 0 else float('nan')
     return mean, math.sqrt(var), chi2, dof, Q
+
+
+# --------------------------------------------------------------------------- restratify
+def profile_integrand(vmap, f, ndy):
+    """The auxiliary integrand of ``vegas.restratify`` (src/vegas/__init__.py:1390-1419):
+    component 0 is ``I = f(x)[:, 0]``; component ``1 + mu*ndy + i`` is ``I`` where
+    ``yst[i] <= y[mu] <= yst[i+1]`` (closed on both sides) with ``y = map.invmap(x)``, else 0."""
+    yst = np.linspace(0, 1, ndy + 1)                                       # __init__.py:1321
+
+    def fcn(x):
+        x = np.asarray(x, dtype=float)
+        n, dim = x.shape
+        y, _ = vmap.invmap(x)                                              # __init__.py:1402
+        I = np.asarray(f(x), dtype=float).reshape(n, -1)[:, 0]             # __init__.py:1406
+        out = np.zeros((n, 1 + dim * ndy))
+        out[:, 0] = I
+        for mu in range(dim):
+            for i in range(ndy):
+                idx = (yst[i] <= y[:, mu]) & (y[:, mu] <= yst[i + 1])      # __init__.py:1411
+                out[idx, 1 + mu * ndy + i] = I[idx]
+        return out
+    return fcn
+
+
+def restratify_weights(I, dI, ndy):
+    """weight[mu] = sum_i (dI[mu][i] - I/ndy)^2 * ndy   (__init__.py:1340-1344), on mean values"""
+    dI = np.asarray(dI, dtype=float)
+    return np.sum((dI - I / ndy) ** 2, axis=1) * ndy
+
+
+def restratify_nstrat(old_nstrat, weight, gamma=1.0, below_avg_nstrat=None):
+    """new strata per axis (__init__.py:1349-1365): proportional to the weights at constant
+    geometric-mean strata, assigned smallest first; what rounding (or ``below_avg_nstrat``) takes
+    from an axis is handed to the axes not yet assigned."""
+    old = np.asarray(old_nstrat)
+    dim = len(old)
+    weight = np.asarray(weight, dtype=float)
+    w_avg = np.average(weight)
+    w_gm = np.prod(weight) ** (1 / dim)
+    nstrat_gm = np.prod(old) ** (1 / dim)
+    nstrat = old * ((weight / w_gm) * nstrat_gm / old) ** gamma
+    nleft = dim
+    musort = np.array(np.argsort(nstrat))
+    new = np.array(old)
+    for mu in musort:
+        new[mu] = nstrat[mu] if nstrat[mu] > 1 else 1
+        if below_avg_nstrat and weight[mu] < w_avg:
+            new[mu] = below_avg_nstrat
+        nleft -= 1
+        if nleft > 0:
+            nstrat[musort[-nleft:]] *= (nstrat[mu] / new[mu]) ** (1 / nleft)
+            nstrat[mu] = new[mu]
+    return new

@@ -15,6 +15,8 @@ def integrand(name):
             g = np.exp(-30. * np.sum((x - 0.4) ** 2, axis=1))
             return np.stack([g, g * x[:, 0], x[:, 1] ** 2], axis=1)
         return f
+    if name == 'two_axes':
+        return lambda x: np.exp(-100. * ((x[:, 0] - 0.5) ** 2 + (x[:, 1] - 0.3) ** 2)) * (1. + 0.01 * x[:, 2] + 0.01 * x[:, 3])
     if name == 'const':
         return lambda x: 7. * np.ones(x.shape[0])
     raise KeyError(name)
@@ -32,4 +34,12 @@ CASES = {
     'gauss2_bigcubes': dict(limits=2 * [[0., 1.]], f='gauss', kw=dict(neval=3000, nstrat=[3, 2]), nitn=3, seed=17),
     'const1': dict(limits=[[0., 1.]], f='const', kw=dict(neval=100, alpha=0.0), nitn=3, seed=18),
     'gauss3_noadapt': dict(limits=3 * [[0., 1.]], f='gauss', kw=dict(neval=2000, adapt=False), nitn=2, seed=19),
+}
+
+
+# vegas.restratify (src/vegas/__init__.py:1313-1592): adapt for nitn_adapt iterations, then restratify
+RESTRATIFY = {
+    'plain': dict(limits=4 * [[0., 1.]], f='two_axes', kw=dict(neval=20000), nitn_adapt=3, nitn=2, ndy=5, opt={}, seed=31),
+    'damped': dict(limits=4 * [[0., 1.]], f='two_axes', kw=dict(neval=20000), nitn_adapt=3, nitn=1, ndy=4,
+                   opt=dict(gamma=0.5, below_avg_nstrat=2), seed=32),
 }

@@ -365,6 +365,71 @@ def test_split_chunks_big_cubes_and_batches(monkeypatch):
         assert np.array_equal(a, b)
 
 
+# ----------------------------------------------------------------------------- restratify
+@pytest.mark.parametrize('case', ['functor', 'host', 'bigcubes', 'split'])
+def test_stratification_profile_vs_oracle(case, monkeypatch):
+    """I and the profile dI[mu][i] of vegas.restratify (vb200_reduce + vb200_dy_profile on the callback
+    path's buffers) vs the oracle's restatement of the reference's auxiliary integrand
+    (src/vegas/__init__.py:1390-1419; pinned to the reference by tests/test_oracle_golden.py)"""
+    vegas = _vegas()
+    O = _oracle()
+    from vegas_b200._restratify import stratification_profile
+    from tests.golden.cases import integrand
+    limits, ndy, seed, kw = 4 * [[0., 1.]], 5, 515, dict(neval=20000)
+    if case == 'host':
+        twin = integrand('two_axes')
+        f = vegas.lbatchintegrand(lambda x: twin(x))
+    else:
+        f = vegas.integrands.GaussMix([[0.5, 0.3, 0.5, 0.5], [0.2, 0.7, 0.5, 0.5]], 60., 3.0)
+        twin = f
+    if case == 'bigcubes':
+        kw = dict(neval=10000, nstrat=[4, 3, 2, 1])          # ~100 samples per cube and more: the warp-per-cube path
+        ndy = 7
+    if case == 'split':
+        monkeypatch.setenv('VB200_ITEM', '256')
+    integ = vegas.Integrator(limits, seed=seed, **kw)
+    integ(f, nitn=3)
+    for it in range(2):
+        sigf_in, sum_sigf_in, grid_in = integ.sigf.copy(), float(integ.sum_sigf), integ.map.grid.copy()
+        res = stratification_profile(integ, f, nitn=1, ndy=ndy)
+        v = O.Vegas(limits, alpha=0.0, correlate_integrals=False, **kw)
+        v.map.grid = grid_in[:, :v.map.grid.shape[1]].copy()
+        v.sigf, v.sum_sigf = sigf_in, sum_sigf_in
+        pitn = integ._itn_counter
+        mean, var = v.iterate(O.profile_integrand(v.map, twin, ndy), lambda h0, nh: O.philox_uniforms(seed, pitn, 4, h0, nh))
+        var = np.asarray(var).reshape(-1)
+        r = res.itn_results[0]
+        assert integ.last_neval == v.last_neval
+        np.testing.assert_allclose(r['I'].mean, mean[0], rtol=1e-12)
+        np.testing.assert_allclose(r['I'].sdev ** 2, var[0], rtol=1e-10)
+        dI = np.asarray(r['dI'])
+        np.testing.assert_allclose([[g.mean for g in row] for row in dI], mean[1:].reshape(4, ndy), rtol=1e-11, atol=1e-300)
+        np.testing.assert_allclose([[g.sdev ** 2 for g in row] for row in dI], var[1:].reshape(4, ndy), rtol=1e-9, atol=1e-300)
+        np.testing.assert_allclose(integ.sigf, v.sigf, rtol=1e-8, atol=1e-300)
+        np.testing.assert_allclose(integ.sum_sigf, v.sum_sigf, rtol=1e-12)
+        np.testing.assert_allclose(sum(g.mean for g in dI[0]), r['I'].mean, rtol=1e-12)      # every sample is in one bin per axis
+
+
+def test_restratify_end_to_end():
+    """vegas.restratify on an integrand whose structure lives on two of six axes: the strata move
+    there, the hypercube count stays close, and the new integrator integrates correctly"""
+    vegas = _vegas()
+    f = vegas.integrands.Genz('gaussian', [12., 12., .2, .2, .2, .2], [.5, .3, .5, .5, .5, .5])
+    exact = f.exact()
+    integ = vegas.Integrator(6 * [[0., 1.]], neval=200000, seed=77)
+    integ(f, nitn=5)
+    new = vegas.restratify(integ, f, nitn=2, ndy=5)
+    assert isinstance(new, vegas.Integrator) and len(new.weight) == 6 and np.shape(new.dI) == (6, 5)
+    assert 0.5 * integ.nhcube < new.nhcube <= 1.05 * integ.nhcube
+    assert min(new.nstrat[:2]) > max(new.nstrat[2:]), new.nstrat
+    assert abs(new.I.mean - exact) < 5 * new.I.sdev
+    r = new(f, nitn=5)
+    assert abs(r.mean - exact) < 5 * r.sdev and r.Q > 1e-3, (r, exact)
+    # the device functor and its numpy twin on the host path give the same profile
+    host = vegas.restratify(integ, vegas.lbatchintegrand(lambda x: f(x)), nitn=2, ndy=5)
+    assert list(host.nstrat) == list(new.nstrat)
+
+
 # ----------------------------------------------------------------------------- light geometry
 @pytest.mark.parametrize('name', ['gauss4', 'genz10_pp', 'peaks20'])
 def test_split_chunks_light_geometry(name, monkeypatch):

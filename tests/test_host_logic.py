@@ -403,3 +403,17 @@ def test_block_cyclic_partition_covers_every_cube_once(nh, slab, world):
         out = ctypes.c_int64()
         h = ctypes.c_void_p()
     assert np.all(seen == 1)
+
+
+def test_new_stratification_matches_reference_golden():
+    """restratify's strata assignment (src/vegas/__init__.py:1349-1365) on the weights the unmodified
+    reference computed (tests/golden/ref_restratify.npz): identical integer nstrat"""
+    from vegas_b200._restratify import new_stratification
+    from tests.golden.cases import RESTRATIFY
+    G = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_restratify.npz'))
+    for name, spec in RESTRATIFY.items():
+        new = new_stratification(G[name + '_old_nstrat'], G[name + '_weight'], **spec['opt'])
+        assert list(new) == list(G[name + '_new_nstrat']), (name, new)
+    # axes rounded down to one stratum hand their share to the others: the product stays close
+    new = new_stratification([4, 4, 4, 4], [1.0, 1e-6, 1e-6, 0.5])
+    assert list(new[1:3]) == [1, 1] and 0.7 * 256 < np.prod(new) <= 256

@@ -199,3 +199,36 @@ print('ok')
 ''' % (os.path.join(os.path.dirname(HERE), 'oracle', 'gvar_shim'), ref_dir, os.path.dirname(HERE))
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
     assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
+
+
+def test_restratify_matches_reference():
+    """vegas.restratify (src/vegas/__init__.py:1313-1419): the oracle's restatement of the auxiliary
+    I/dI integrand, the weights and the new stratification vs the unmodified reference run recorded
+    by tests/golden/make_golden_restratify.py (same injected uniforms)"""
+    from tests.golden.cases import RESTRATIFY
+    G = np.load(os.path.join(HERE, 'golden', 'ref_restratify.npz'))
+    for name, spec in RESTRATIFY.items():
+        v = O.Vegas(spec['limits'], alpha=0.0, correlate_integrals=False, **spec['kw'])
+        assert list(v.nstrat) == list(G[name + '_old_nstrat'])
+        v.map.grid = G[name + '_grid'][:, :v.map.grid.shape[1]].copy()
+        v.sigf = G[name + '_sigf'].copy()
+        v.sum_sigf = float(G[name + '_sum_sigf'])
+        rng = np.random.default_rng(spec['seed'] + 1000)
+        ndy = spec['ndy']
+        fcn = O.profile_integrand(v.map, integrand(spec['f']), ndy)
+        means, variances = [], []
+        for i in range(spec['nitn']):
+            mean, var = v.iterate(fcn, lambda h0, nh: rng.random((int(nh.sum()), v.dim)))
+            means.append(mean)
+            variances.append(np.asarray(var).reshape(-1))
+        m, s2 = np.array(means), np.array(variances)
+        w = 1. / s2
+        avg = (m * w).sum(axis=0) / w.sum(axis=0)                 # independent components: plain weighted averages
+        avar = 1. / w.sum(axis=0)
+        np.testing.assert_allclose([avg[0], avar[0]], G[name + '_I'], rtol=1e-11)
+        np.testing.assert_allclose(avg[1:].reshape(v.dim, ndy), G[name + '_dI_mean'], rtol=1e-10, atol=1e-300)
+        np.testing.assert_allclose(avar[1:].reshape(v.dim, ndy), G[name + '_dI_var'], rtol=1e-9, atol=1e-300)
+        weight = O.restratify_weights(avg[0], avg[1:].reshape(v.dim, ndy), ndy)
+        np.testing.assert_allclose(weight, G[name + '_weight'], rtol=1e-8)
+        new = O.restratify_nstrat(v.nstrat, G[name + '_weight'], **spec['opt'])
+        assert list(new) == list(G[name + '_new_nstrat'])

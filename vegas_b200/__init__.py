@@ -14,6 +14,7 @@ from ._integrand import (VegasIntegrand, LBatchIntegrand, RBatchIntegrand, Batch
                          devicebatchintegrand, vecintegrand, MPIintegrand)
 from ._results import RAvg, RAvgArray, RAvgDict, VegasResult, reporter
 from ._integrator import Integrator
+from ._restratify import restratify, restratifyIntegrator, stratification_profile
 from . import integrands
 
 __version__ = '0.1.0'
@@ -22,4 +23,5 @@ ranseed = _gv.ranseed
 __all__ = ['Integrator', 'AdaptiveMap', 'RAvg', 'RAvgArray', 'RAvgDict', 'VegasResult', 'reporter',
            'VegasIntegrand', 'LBatchIntegrand', 'RBatchIntegrand', 'BatchIntegrand', 'DeviceIntegrand',
            'lbatchintegrand', 'rbatchintegrand', 'batchintegrand', 'devicebatchintegrand', 'integrands',
+           'restratify', 'restratifyIntegrator',
            'ranseed']

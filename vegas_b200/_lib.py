@@ -22,7 +22,7 @@ SYMBOLS = (
     'vb200_set_map', 'vb200_set_strata', 'vb200_set_integrand', 'vb200_plan', 'vb200_chunk_offsets',
     'vb200_iterate_fused', 'vb200_sample', 'vb200_reduce', 'vb200_map', 'vb200_invmap', 'vb200_jac1d',
     'vb200_add_training_data', 'vb200_map_adapt', 'vb200_uniforms', 'vb200_fp64_peak', 'vb200_launch_count',
-    'vb200_last_launch',
+    'vb200_last_launch', 'vb200_eval_integrand', 'vb200_dy_profile',
 )
 
 
@@ -90,6 +90,8 @@ def load():
     L.vb200_add_training_data.argtypes = [vp, vp, vp, i64, vp, vp, i64, vp]
     L.vb200_map_adapt.argtypes = [vp, vp, i32, i64, vp, vp, i64, f64, vp, vp, i64]
     L.vb200_uniforms.argtypes = [vp, u32, i64, i64, vp, vp]
+    L.vb200_eval_integrand.argtypes = [vp, vp, i64, vp, vp]
+    L.vb200_dy_profile.argtypes = [vp, u32, i64, i64, vp, i32, vp, i32, vp, vp, vp]
     L.vb200_fp64_peak.argtypes = [i32, i32, ctypes.POINTER(f64), ctypes.POINTER(f64)]
     L.vb200_launch_count.argtypes = [vp]
     L.vb200_launch_count.restype = i64
@@ -189,6 +191,15 @@ class Context(object):
     def reduce(self, itn, beta, flags, c0, c1, f, nf, wgt, sigf, acc, sum_f, n_f, hstride, status, bins=None):
         check(self.L.vb200_reduce(self.h, itn, float(beta), flags, c0, c1, _ptr(f), nf, _ptr(wgt), _ptr(sigf),
                                   _ptr(acc), _ptr(sum_f), _ptr(n_f), hstride, _ptr(bins), _ptr(status), _stream()))
+
+    def eval_integrand(self, x, f):
+        """f[rows, nf] = the context's built-in functor at x[rows, dim] (device tensors)"""
+        check(self.L.vb200_eval_integrand(self.h, _ptr(x), x.shape[0], _ptr(f), _stream()))
+
+    def dy_profile(self, itn, c0, c1, f, fstride, wgt, yst, acc):
+        yst = np.ascontiguousarray(yst, dtype=np.float64)
+        check(self.L.vb200_dy_profile(self.h, itn, c0, c1, _ptr(f), int(fstride), _ptr(wgt), len(yst) - 1,
+                                      yst.ctypes.data, _ptr(acc), _stream()))
 
     def uniforms(self, itn, c0, c1, u):
         check(self.L.vb200_uniforms(self.h, itn, c0, c1, _ptr(u), _stream()))

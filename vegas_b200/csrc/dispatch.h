@@ -160,3 +160,43 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     if (dim_ <= DD) { FusedSrc<F, DD> s_{fobj}; return launch_engine(p, s_, cfg, st); }
 #define VB_CASE_L(F, fobj, DD)                                                                 \
     if (cfg.light && dim_ <= DD) { FusedSrc<F, DD, true, (DD <= 10)> s_{fobj}; return launch_engine(p, s_, cfg, st); }
+
+
+// ---------------------------------------------------------------------------------------------
+// The built-in functors on HBM buffers: f[rows][NF] = F(x[rows][dim]) -- the same device code the
+// fused kernel inlines, for callers that need the values themselves (vb200_eval_integrand: the
+// stratification profile of restratify, DeviceIntegrand as a device batch callback).
+// ---------------------------------------------------------------------------------------------
+template <class F, int D>
+__global__ void __launch_bounds__(256) k_eval(const __grid_constant__ F f, int dim, const double* __restrict__ x, int64_t rows,
+                                              double* __restrict__ out)
+{
+    vb_exp_init();
+    __syncthreads();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
+        double xv[D], fx[F::NF];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xv[d] = d < dim ? x[i * dim + d] : 0.0;
+        f(xv, dim, fx);
+#pragma unroll
+        for (int s = 0; s < F::NF; ++s) out[i * F::NF + s] = fx[s];
+    }
+}
+
+template <class F, int D>
+static int launch_eval(const F& f, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st)
+{
+    int64_t g = (rows + 255) / 256, cap = (int64_t)sm_count * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    k_eval<F, D><<<(int)g, 256, 0, st>>>(f, dim, x, rows, out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+#define VB_EVAL_D(F, fobj, DD) if (dim <= DD) return launch_eval<F, DD>(fobj, dim, x, rows, out, sm_count, st);
+
+int eval_poly(const void* functor, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st);
+int eval_gaussmix(const void* functor, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st);
+int eval_ridge(const void* functor, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st);
+int eval_genz(const void* functor, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st);
+int eval_pathint(const void* functor, int nx0, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st);

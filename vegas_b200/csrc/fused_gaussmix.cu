@@ -9,3 +9,10 @@ int launch_fused_gaussmix_heavy(const EngineP& p, const void* functor, LaunchCfg
     const FGaussMix& f = *(const FGaussMix*)functor;
     VB_DISPATCH_D(FGaussMix, f, LIST_);
 }
+
+int eval_gaussmix(const void* functor, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st)
+{
+    const FGaussMix& f = *(const FGaussMix*)functor;
+    VB_EVAL_D(FGaussMix, f, 4) VB_EVAL_D(FGaussMix, f, 8) VB_EVAL_D(FGaussMix, f, 12) VB_EVAL_D(FGaussMix, f, 20)
+    return -22;
+}

@@ -9,3 +9,10 @@ int launch_fused_genz_heavy(const EngineP& p, const void* functor, LaunchCfg& cf
     const FGenz& f = *(const FGenz*)functor;
     VB_DISPATCH_D(FGenz, f, LIST_);
 }
+
+int eval_genz(const void* functor, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st)
+{
+    const FGenz& f = *(const FGenz*)functor;
+    VB_EVAL_D(FGenz, f, 4) VB_EVAL_D(FGenz, f, 8) VB_EVAL_D(FGenz, f, 12) VB_EVAL_D(FGenz, f, 20)
+    return -22;
+}

@@ -18,3 +18,20 @@ int launch_fused_pathint(const EngineP& p, const void* functor, int nx0, LaunchC
     default: return -22;
     }
 }
+
+template <int NX0>
+static int eval_nx0(const void* functor, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st)
+{
+    const FPathInt<NX0>& f = *(const FPathInt<NX0>*)functor;
+    VB_EVAL_D(FPathInt<NX0>, f, 8) VB_EVAL_D(FPathInt<NX0>, f, 10) VB_EVAL_D(FPathInt<NX0>, f, 16)
+    return -22;
+}
+
+int eval_pathint(const void* functor, int nx0, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st)
+{
+    switch (nx0) {
+    case 0: return eval_nx0<0>(functor, dim, x, rows, out, sm_count, st);
+    case 6: return eval_nx0<6>(functor, dim, x, rows, out, sm_count, st);
+    default: return -22;
+    }
+}

@@ -9,3 +9,10 @@ int launch_fused_poly_heavy(const EngineP& p, const void* functor, LaunchCfg& cf
     const FPoly& f = *(const FPoly*)functor;
     VB_DISPATCH_D(FPoly, f, LIST_);
 }
+
+int eval_poly(const void* functor, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st)
+{
+    const FPoly& f = *(const FPoly*)functor;
+    VB_EVAL_D(FPoly, f, 4) VB_EVAL_D(FPoly, f, 8) VB_EVAL_D(FPoly, f, 12) VB_EVAL_D(FPoly, f, 20)
+    return -22;
+}

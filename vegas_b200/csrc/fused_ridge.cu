@@ -9,3 +9,10 @@ int launch_fused_ridge_heavy(const EngineP& p, const void* functor, LaunchCfg& c
     const FRidge& f = *(const FRidge*)functor;
     VB_DISPATCH_D(FRidge, f, LIST_);
 }
+
+int eval_ridge(const void* functor, int dim, const double* x, int64_t rows, double* out, int sm_count, cudaStream_t st)
+{
+    const FRidge& f = *(const FRidge*)functor;
+    VB_EVAL_D(FRidge, f, 4) VB_EVAL_D(FRidge, f, 8) VB_EVAL_D(FRidge, f, 12) VB_EVAL_D(FRidge, f, 20)
+    return -22;
+}
