@@ -240,6 +240,7 @@ def ours(args):
                 out['cpu_baseline'] = dict(error=(cp.stderr or cp.stdout)[-300:])
         if world == 1 and args.variants:
             out['variants'] = variants(vegas, _lib, fp64_peak)
+            out['other_configs'] = other_configs(vegas, _lib, fp64_peak)
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -263,6 +264,91 @@ def variants(vegas, _lib, fp64_peak):
         out['ridge_N%d%s' % (n, '_shifted' if shifted else '')] = dict(value=float(r.sum_neval) / (ms * 1e-3), unit='samples/s',
                                     roofline_frac=float(r.sum_neval) * fl / (kms * 1e-3) / 1e12 / fp64_peak,
                                     flops_per_sample=fl, result=str(r), launch=integ._ctx.last_launch())
+    return out
+
+
+def hbm_peak_gbs():
+    """HBM copy bandwidth the driver measured on this pool (MEASURED_PEAKS.json), else the figure it
+    recorded when the survey was written"""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'MEASURED_PEAKS.json'
+    except Exception:
+        return 6549.8, 'BASELINE.md section 4 (MEASURED_PEAKS.json absent)'
+
+
+def other_configs(vegas, _lib, fp64_peak):
+    """one-GPU numbers of the other BASELINE.json configurations (fused kernels) and of the HBM-bound
+    callback path (config 4: 10-D path integral, 7 outputs): kernel-level rows/s of the sampler and
+    the reduce kernel on one 8M-row batch, against the HBM copy bandwidth"""
+    import torch
+    F = vegas.integrands
+    rng = np.random.default_rng(0x5eed + 3)
+    out = {}
+    cfgs = {
+        'cfg3_genz10_product_peak': (F.Genz('product_peak', 2 + 3 * rng.random(10), rng.random(10)), 10 * [[0., 1.]],
+                                     dict(neval=1e9, max_mem=1e10)),
+        'cfg5_peaks20_nstrat30x5': (F.GaussMix([5 * [c] + 15 * [0.45] for c in (.23, .39, .74)], 100., 356047712484621.56),
+                                    20 * [[0., 1.]], dict(neval=5e8, nstrat=5 * [30] + 15 * [1], max_mem=1e10)),
+        'cfg4_pathint10_fused': (F.PathIntegral(T=4., ndT=10, x0list=np.linspace(0, 2., 6)), 10 * [[-np.pi / 2, np.pi / 2]],
+                                 dict(neval=1e8, alpha=0.1)),
+    }
+    for name, (f, limits, kw) in cfgs.items():
+        integ = vegas.Integrator(limits, seed=5, **kw)
+        integ(f, nitn=5)
+        integ._timing = []
+        r = integ(f, nitn=3)
+        torch.cuda.synchronize()
+        kms = float(np.sum([ev[1].elapsed_time(ev[2]) for ev, _ in integ._timing]))
+        r0 = r if not hasattr(r, 'keys') else r['exp(-E0*T)']
+        out[name] = dict(value=float(r.sum_neval) / (kms * 1e-3), unit='samples/s', neval=kw['neval'], kernel_ms=kms / 3,
+                         nhcube=int(integ.nhcube), neval_hcube_range=[int(v) for v in integ.neval_hcube_range],
+                         result='%s Q=%.2f' % (r0, r.Q), launch=integ._ctx.last_launch())
+    # ---- callback path kernels on the adapted path-integral state (integ, f from the last loop turn)
+    peak, src = hbm_peak_gbs()
+    ctx, _ = integ._engine()
+    integ._plan(ctx)
+    batches = integ._batches(ctx, 1 << 23)
+    c0, c1, rows = batches[len(batches) // 2]
+    dim, nf, dev = integ.dim, 7, ctx.device
+    x = torch.empty((rows, dim), dtype=torch.float64, device=dev)
+    wgt = torch.empty(rows, dtype=torch.float64, device=dev)
+    bins = torch.empty((rows, dim), dtype=torch.int16, device=dev)
+    fx = torch.empty((rows, nf), dtype=torch.float64, device=dev)
+    hs = int(integ.map.inc.shape[1])
+    acc = torch.zeros(nf + nf * (nf + 1) // 2 + 1, dtype=torch.float64, device=dev)
+    sum_f = torch.zeros((dim, hs), dtype=torch.float64, device=dev)
+    n_f = torch.zeros((dim, hs), dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    sig = integ._sigf_dev.clone()
+    flags = integ._flags(nf)
+
+    def timeit(fn, n=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e-3
+
+    ts = timeit(lambda: ctx.sample(7, c0, c1, x, wgt, bins=bins))
+    te = timeit(lambda: ctx.eval_integrand(x, fx))
+    tr = timeit(lambda: ctx.reduce(7, integ.beta, flags, c0, c1, fx, nf, wgt, sig, acc, sum_f, n_f, hs, status, bins=bins))
+    b_s, b_e, b_r = 8 * dim + 8 + 2 * dim, 8 * dim + 8 * nf, 8 * nf + 8 + 2 * dim
+    out['cfg4_pathint10_callback_path'] = dict(
+        rows=int(rows), note='kernel-level, one batch of the adapted state (vegas+ allocation 2..50000 samples per hypercube); '
+                             'inputs > L2 (x alone is %.0f MB); bytes per row: sampler writes x, wgt, training bins; the '
+                             'integrand kernel (library functor on buffers) reads x, writes f; reduce reads f, wgt, bins' % (rows * 8 * dim / 1e6),
+        sampler=dict(rows_per_s=rows / ts, bytes_per_row=b_s, gbs=rows * b_s / ts / 1e9, frac=rows * b_s / ts / 1e9 / peak),
+        integrand=dict(rows_per_s=rows / te, bytes_per_row=b_e, gbs=rows * b_e / te / 1e9, frac=rows * b_e / te / 1e9 / peak),
+        reduce=dict(rows_per_s=rows / tr, bytes_per_row=b_r, gbs=rows * b_r / tr / 1e9, frac=rows * b_r / tr / 1e9 / peak),
+        path=dict(value=rows / (ts + te + tr), unit='samples/s', bytes_per_sample=b_s + b_e + b_r,
+                  gbs=rows * (b_s + b_e + b_r) / (ts + te + tr) / 1e9, frac=rows * (b_s + b_e + b_r) / (ts + te + tr) / 1e9 / peak),
+        hbm_peak_gbs=peak, hbm_peak_source=src)
     return out
 
 
