@@ -95,7 +95,7 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     // staging capacity: ~16 samples per thread, at most 32 KB (heavy) / 64 KB (light)
     // (light geometry above 10 dimensions: 4 per thread -- the histogram windows need the room)
     int cap = vb_env_int(CH == VB_CH ? "VB200_CAP" : "VB200_LCAP", (CH != VB_CH && !Src::GRIDW ? 4 : 16) * NT);
-    const int lim = ((CH == VB_CH ? 32 : 64) * 1024) / (8 * NF);
+    const int lim = ((CH == VB_CH ? (NF > 4 ? 48 : 32) : 64) * 1024) / (8 * NF);   // many components: fewer, larger tiles
     if (cap > lim) cap = lim;
     if (cap < 256) cap = 256;
     cfg.cap = p.cap = cap;

@@ -19,6 +19,8 @@
 #include <type_traits>
 #include "common.cuh"
 
+#define VB_LARGE_MAX 128      // large cubes (> VB_WARP_CUBE samples) one tile can hold: 8192 / 65
+#define VB_LARGE_G 8          // large cubes reduced per round of phase 2b
 #define VBF_UPDATE_SIGF   1   // adaptive stratification: write sigf, accumulate sum_sigf
 #define VBF_TRAIN         2   // add (J f dv_y)^2 to the map's training histogram
 #define VBF_TRAIN_ERRORS  4   // adapt_to_errors: one training point per cube carrying its variance
@@ -679,10 +681,11 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     dig_t* y0_s = (dig_t*)(H.cnt + p.wtot);                       // [CH][dim]
     __shared__ long long scan_s[NW];
     __shared__ double red_s[NW];
-    __shared__ double bc_s[NF];
     __shared__ uint32_t base_s[VB_MAXD];
     __shared__ long long next_s;
     __shared__ int sub_s[2];
+    __shared__ int nlarge_s, large_s[VB_LARGE_MAX];
+    __shared__ double p1_s[VB_LARGE_G * NW * NF], p2_s[VB_LARGE_G * NW * (NF + NV)];
     __shared__ int wnew_s[VB_MAXD], wneed_s[VB_MAXD];
     int* const wlo_s = vb_wlo_s;
 
@@ -841,15 +844,23 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
                     }
                     __syncwarp();
                 }
+                // both passes end in ONE block-wide reduction of all their sums (warp sums -> shared
+                // memory -> fixed-order sum over the warps): 3 barriers per giant cube
                 double m[NF];
 #pragma unroll
                 for (int s = 0; s < NF; ++s) {
-                    double t = block_sum<NT>(S[s], red_s);
-                    if (tid == 0) bc_s[s] = t;
+                    const double t = warp_sum(S[s]);
+                    if (lane == 0) p1_s[warp * NF + s] = t;
                 }
                 __syncthreads();
 #pragma unroll
-                for (int s = 0; s < NF; ++s) { S[s] = bc_s[s]; m[s] = S[s] / (double)n; }
+                for (int s = 0; s < NF; ++s) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) t += p1_s[w * NF + s];
+                    S[s] = t;
+                    m[s] = t / (double)n;
+                }
                 double sd[NF], q[NV];
 #pragma unroll
                 for (int s = 0; s < NF; ++s) sd[s] = 0.0;
@@ -862,10 +873,27 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
                     pass2_sample<NF>(w, m, correlate, sd, q);
                 }
 #pragma unroll
-                for (int s = 0; s < NF; ++s) sd[s] = block_sum<NT>(sd[s], red_s);
+                for (int s = 0; s < NF; ++s) {
+                    const double t = warp_sum(sd[s]);
+                    if (lane == 0) p2_s[warp * (NF + NV) + s] = t;
+                }
 #pragma unroll
-                for (int v = 0; v < NV; ++v) q[v] = block_sum<NT>(q[v], red_s);
+                for (int v = 0; v < NV; ++v) {
+                    const double t = warp_sum(q[v]);
+                    if (lane == 0) p2_s[warp * (NF + NV) + NF + v] = t;
+                }
+                __syncthreads();
                 if (tid == 0) {
+#pragma unroll
+                    for (int s = 0; s < NF; ++s) sd[s] = 0.0;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) q[v] = 0.0;
+                    for (int w = 0; w < NW; ++w) {
+#pragma unroll
+                        for (int s = 0; s < NF; ++s) sd[s] += p2_s[w * (NF + NV) + s];
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) q[v] += p2_s[w * (NF + NV) + NF + v];
+                    }
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
                     cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c0, h, n, y0_s + c0 * dim);
                 }
@@ -893,6 +921,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
                 }
                 __syncwarp();                                      // lanes leave the histogram CAS loops at different times
             }
+            if (tid == 0) nlarge_s = 0;
             __syncthreads();
 
             // ---- phase 2a: one thread per small cube, serial in the reference's order
@@ -918,37 +947,83 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
                     }
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
                     cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
+                } else if (n > VB_WARP_CUBE) {
+                    large_s[atomicAdd(&nlarge_s, 1)] = c;          // at most cap / (VB_WARP_CUBE + 1) per tile
                 }
             }
-            // ---- phase 2b: one warp per large cube
-            for (int c = c0 + warp; c < c1; c += NW) {
-                const int n = n_s[c];
-                if (n <= VB_WARP_CUBE) continue;
-                const int o = (int)(ex_s[c] - base);
-                double S[NF], m[NF], sd[NF], q[NV];
+            __syncthreads();
+            // ---- phase 2b: large cubes, each shared by ALL warps (warp w reduces the w-th slice of its
+            // samples; partial sums meet in shared memory).  One warp per cube left the other warps
+            // idle at the barrier whenever a tile held fewer large cubes than warps -- the common
+            // case once the vegas+ allocation concentrates samples.
+            const int nlarge = nlarge_s;
+            for (int g0 = 0; g0 < nlarge; g0 += VB_LARGE_G) {
+                const int ng = min(VB_LARGE_G, nlarge - g0);
+                for (int j = 0; j < ng; ++j) {
+                    const int c = large_s[g0 + j], n = n_s[c], o = (int)(ex_s[c] - base);
+                    const int lo = (int)((long long)n * warp / NW), hi = (int)((long long)n * (warp + 1) / NW);
+                    double S[NF];
 #pragma unroll
-                for (int s = 0; s < NF; ++s) { S[s] = 0.0; sd[s] = 0.0; }
+                    for (int s = 0; s < NF; ++s) S[s] = 0.0;
+                    for (int k = lo + lane; k < hi; k += 32)
 #pragma unroll
-                for (int v = 0; v < NV; ++v) q[v] = 0.0;
-                for (int k = lane; k < n; k += 32)
+                        for (int s = 0; s < NF; ++s) S[s] += wf_s[(size_t)s * p.cap + o + k];
 #pragma unroll
-                    for (int s = 0; s < NF; ++s) S[s] += wf_s[(size_t)s * p.cap + o + k];
-#pragma unroll
-                for (int s = 0; s < NF; ++s) { S[s] = warp_sum(S[s]); m[s] = S[s] / (double)n; }
-                for (int k = lane; k < n; k += 32) {
-                    double w[NF];
-#pragma unroll
-                    for (int s = 0; s < NF; ++s) w[s] = wf_s[(size_t)s * p.cap + o + k];
-                    pass2_sample<NF>(w, m, correlate, sd, q);
+                    for (int s = 0; s < NF; ++s) {
+                        const double t = warp_sum(S[s]);
+                        if (lane == 0) p1_s[(j * NW + warp) * NF + s] = t;
+                    }
                 }
+                __syncthreads();
+                for (int j = 0; j < ng; ++j) {
+                    const int c = large_s[g0 + j], n = n_s[c], o = (int)(ex_s[c] - base);
+                    const int lo = (int)((long long)n * warp / NW), hi = (int)((long long)n * (warp + 1) / NW);
+                    double m[NF], sd[NF], q[NV];
 #pragma unroll
-                for (int s = 0; s < NF; ++s) sd[s] = warp_sum(sd[s]);
+                    for (int s = 0; s < NF; ++s) {
+                        double t = 0.0;
 #pragma unroll
-                for (int v = 0; v < NV; ++v) q[v] = warp_sum(q[v]);
-                if (lane == 0) {
+                        for (int w = 0; w < NW; ++w) t += p1_s[(j * NW + w) * NF + s];
+                        m[s] = t / (double)n;
+                        sd[s] = 0.0;
+                    }
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) q[v] = 0.0;
+                    for (int k = lo + lane; k < hi; k += 32) {
+                        double w[NF];
+#pragma unroll
+                        for (int s = 0; s < NF; ++s) w[s] = wf_s[(size_t)s * p.cap + o + k];
+                        pass2_sample<NF>(w, m, correlate, sd, q);
+                    }
+#pragma unroll
+                    for (int s = 0; s < NF; ++s) {
+                        const double t = warp_sum(sd[s]);
+                        if (lane == 0) p2_s[(j * NW + warp) * (NF + NV) + s] = t;
+                    }
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const double t = warp_sum(q[v]);
+                        if (lane == 0) p2_s[(j * NW + warp) * (NF + NV) + NF + v] = t;
+                    }
+                }
+                __syncthreads();
+                if (tid < ng) {
+                    const int c = large_s[g0 + tid], n = n_s[c];
+                    double S[NF], sd[NF], q[NV];
+#pragma unroll
+                    for (int s = 0; s < NF; ++s) { S[s] = 0.0; sd[s] = 0.0; }
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) q[v] = 0.0;
+                    for (int w = 0; w < NW; ++w) {
+#pragma unroll
+                        for (int s = 0; s < NF; ++s) { S[s] += p1_s[(tid * NW + w) * NF + s]; sd[s] += p2_s[(tid * NW + w) * (NF + NV) + s]; }
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) q[v] += p2_s[(tid * NW + w) * (NF + NV) + NF + v];
+                    }
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
                     cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
                 }
+                __syncthreads();
             }
             __syncthreads();
             c0 = c1;
