@@ -81,3 +81,47 @@ def test_two_gpus_match_one(light):
         if light:
             assert geom['threads'] > 128, geom                 # the light geometry really ran on the shards
     assert np.array_equal(outs[0][5], outs[1][5])              # identical grids on both ranks
+
+
+def _restrat_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    q.put((rank,) + _restrat(True))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _restrat(mpi):
+    import vegas_b200 as vegas
+    f = vegas.integrands.Genz('gaussian', [12., 12., .2, .2], [.5, .3, .5, .5])
+    integ = vegas.Integrator(LIMITS, mpi=mpi, neval=200000, seed=99)
+    integ(f, nitn=3)
+    new = vegas.restratify(integ, f, nitn=1, ndy=5)
+    return ([int(v) for v in new.nstrat], float(new.I.mean), [[float(g.mean) for g in row] for row in new.dI])
+
+
+def test_restratify_two_gpus_match_one():
+    """the stratification profile is all-reduced like the iteration sums: same dI, same new nstrat"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_restrat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    one = _restrat(False)
+    for o in outs:
+        assert o[1] == one[0]
+        np.testing.assert_allclose(o[2], one[1], rtol=1e-9)
+        np.testing.assert_allclose(o[3], one[2], rtol=1e-8, atol=1e-300)
