@@ -530,6 +530,16 @@ struct BufferSrc {
     __device__ __forceinline__ void sample(const EngineP& p, const HistW& H, int n, int64_t h, uint32_t k,
                                            int64_t row, const dig_t* y0, double (&wf)[NF]) const
     {
+        // every global load of the row is issued up front (the kernel is latency-bound on them): the
+        // training bins as packed pairs when the row is 4-byte aligned (even dim) and fits 8 words
+        const int dim_ = p.map.dim;
+        const bool packed = (p.flags & VBF_TRAIN) && p.bins != nullptr && !(dim_ & 1) && dim_ <= 16;
+        uint32_t bw[8];
+        if (packed) {
+            const uint32_t* b32 = (const uint32_t*)(p.bins + row * dim_);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bw[j] = 2 * j < dim_ ? __ldg(b32 + j) : 0xffffffffu;
+        }
         double wgt = p.wbuf[row];
         bool bad = false;
 #pragma unroll
@@ -542,7 +552,21 @@ struct BufferSrc {
         if (p.flags & VBF_TRAIN) {
             double a = wf[0] * (double)n;
             double fdv2 = a * a;
-            if (p.bins != nullptr) {
+            if (packed) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (4 * g < dim_) {
+                        uint32_t sa[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int d = 4 * g + j;
+                            const unsigned bv = (j & 1) ? (bw[2 * g + (j >> 1)] >> 16) : (bw[2 * g + (j >> 1)] & 0xffffu);
+                            sa[j] = hist_slot(p, H, d < dim_ ? d : 0, (d >= dim_ || bv == 0xffffu) ? -1 : (int)bv, fdv2);
+                        }
+                        hist_sum_slots4(sa[0], sa[1], sa[2], sa[3], fdv2);
+                    }
+                }
+            } else if (p.bins != nullptr) {
                 // bins from the sampler; 4 axes at a time so their CAS loops run side by side
                 const int dim = p.map.dim;
                 const uint16_t* b = p.bins + row * dim;
@@ -816,15 +840,22 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
         while (c0 < cend) {
             const long long base = ex_s[c0];
             if (base >= total) break;                              // only empty cubes remain
-            // c1 = one past the last cube whose samples still fit the staging buffer
+            // c1 = one past the last cube of this tile.  The item's remaining samples are cut into the
+            // fewest tiles that fit the staging buffer, of about equal size (not one full tile and a
+            // sliver: every tile costs the same barriers), so the limit is remaining / ntiles <= cap.
             int c1;
             {
-                int lo = c0, hi = cend + 1;                     // ex_s[lo]-base <= cap < ex_s[hi]-base (virtual)
+                const long long rem = ex_s[cend] - base;
+                const long long ntile = (rem + p.cap - 1) / p.cap;
+                long long lim = ntile > 1 ? (rem + ntile - 1) / ntile : (long long)p.cap;
+                if (lim > (long long)p.cap) lim = p.cap;
+                int lo = c0, hi = cend + 1;                     // ex_s[lo]-base <= lim < ex_s[hi]-base (virtual)
                 while (hi - lo > 1) {
                     int mid = (lo + hi) >> 1;
-                    if (ex_s[mid] - base <= (long long)p.cap) lo = mid; else hi = mid;
+                    if (ex_s[mid] - base <= lim) lo = mid; else hi = mid;
                 }
                 c1 = lo;
+                if (c1 == c0 && ex_s[c0 + 1] - base <= (long long)p.cap) c1 = c0 + 1;   // one cube above the even share but within the buffer
             }
             if (c1 == c0) {
                 // ---- giant cube c0: staged through global scratch, reduced by the whole CTA
@@ -907,13 +938,16 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
             for (int ib = 0; ib < Tt; ib += NT) {                  // warp-uniform trip count
                 const int i = ib + tid;
                 if (i < Tt) {
+                    // offsets inside a tile fit 32 bits: search on the low words of the prefix array
+                    const unsigned* exl = (const unsigned*)ex_s;
+                    const unsigned bl = (unsigned)base;
                     int lo = c0, hi = c1;
                     while (hi - lo > 1) {
                         int mid = (lo + hi) >> 1;
-                        if ((int)(ex_s[mid] - base) <= i) lo = mid; else hi = mid;
+                        if ((int)(exl[2 * mid] - bl) <= i) lo = mid; else hi = mid;
                     }
                     const int c = lo;
-                    const int k = i - (int)(ex_s[c] - base);
+                    const int k = i - (int)(exl[2 * c] - bl);
                     double w[NF];
                     src.sample(p, H, n_s[c], h0 + c, (uint32_t)k, chunk_row + base + i, y0_s + c * dim, w);
 #pragma unroll
