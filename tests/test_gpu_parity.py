@@ -433,24 +433,23 @@ def test_restratify_end_to_end():
 # ----------------------------------------------------------------------------- light geometry
 @pytest.mark.parametrize('name', ['gauss4', 'genz10_pp', 'peaks20'])
 def test_split_chunks_light_geometry(name, monkeypatch):
-    """work items in the light geometry (1024-cube chunks cut into items of 4 x 256 samples)"""
+    """work items in the light geometry (512-cube chunks cut into items of 2 x 256 samples)"""
     monkeypatch.setenv('VB200_ITEM', '256')
     monkeypatch.setenv('VB200_LIGHT', '1')
     limits, f, kw = _cases()[name]
     eng = run_engine_iterations(limits, f, nitn=3, seed=99, **kw)
-    assert all(r['launch']['threads'] == 512 for r in eng), eng[0]['launch']
+    assert all(r['launch']['threads'] == 256 for r in eng), eng[0]['launch']
     ora = run_oracle_iterations(limits, f, nitn=3, seed=99, engine=eng, **kw)
     compare_iterations(eng, ora, rtol=RTOL, var_rtol=1e-10)
 
 
-@pytest.mark.parametrize('name', ['poly2', 'gauss4', 'ridge4_nomap', 'genz10_pp', 'genz10_osc', 'genz3_corner', 'peaks20'])
+@pytest.mark.parametrize('name', ['poly2', 'gauss4', 'ridge4_nomap', 'ridge8', 'genz10_pp', 'genz10_osc', 'genz3_corner', 'peaks20'])
 def test_light_geometry_vs_oracle(name, monkeypatch):
-    """the one-big-CTA-per-SM geometry (512 threads, 1024-cube chunks, grid + histogram windows in
-    shared memory), forced on problems that would normally be too small for it, vs the oracle"""
+    """the light geometry (256-thread CTAs, 512-cube chunks, grid + histogram windows in shared memory), forced on problems that would normally be too small for it, vs the oracle"""
     monkeypatch.setenv('VB200_LIGHT', '1')
     limits, f, kw = _cases()[name]
     eng = run_engine_iterations(limits, f, nitn=3, seed=4000 + len(name), **kw)
-    assert all(r['launch']['threads'] == 512 and r['launch']['chunk_cubes'] == 1024 for r in eng), eng[0]['launch']
+    assert all(r['launch']['threads'] == 256 and r['launch']['chunk_cubes'] == 512 for r in eng), eng[0]['launch']
     ora = run_oracle_iterations(limits, f, nitn=3, seed=4000 + len(name), engine=eng, **kw)
     compare_iterations(eng, ora, rtol=RTOL, var_rtol=1e-10)
 
@@ -462,7 +461,7 @@ def test_light_equals_heavy(monkeypatch):
     a = run_engine_iterations(limits, f, nitn=2, seed=6, **kw)
     monkeypatch.setenv('VB200_LIGHT', '1')
     b = run_engine_iterations(limits, f, nitn=2, seed=6, **kw)
-    assert a[0]['launch']['threads'] == 128 and b[0]['launch']['threads'] == 512
+    assert a[0]['launch']['threads'] == 128 and b[0]['launch']['threads'] == 256
     for ra, rb in zip(a, b):
         assert np.array_equal(ra['neval_hcube'], rb['neval_hcube'])
         assert np.array_equal(ra['n_f'], rb['n_f'])
@@ -515,7 +514,7 @@ def test_full_size_config3_genz():
     integ = vegas.Integrator(10 * [[0., 1.]], neval=1e9, seed=21, nitn=1, max_mem=1e10)
     assert [int(v) for v in integ.nstrat] == [7, 7, 7, 7, 6, 6, 6, 6, 6, 6] and integ.nhcube == 112021056
     r = _check_full_size(integ, f, f.exact(), 3, 2)
-    assert integ._ctx.last_launch()['threads'] == 512            # cheap integrand: light geometry
+    assert integ._ctx.last_launch()['threads'] == 256            # cheap integrand: light geometry
     assert r.sdev < 1e-4 * abs(f.exact())
 
 

@@ -461,7 +461,7 @@ class Integrator(object):
         if world == 1:
             return _lib.CHUNK
         per = -(-int(self.nhcube) // (world * 8))
-        unit = 4 * _lib.CHUNK if per >= 4 * _lib.CHUNK else _lib.CHUNK    # whole 1024-cube chunks of the light geometry
+        unit = 4 * _lib.CHUNK if per >= 4 * _lib.CHUNK else _lib.CHUNK    # whole chunks of the light geometry (512 cubes)
         per = -(-per // unit) * unit
         return int(max(_lib.CHUNK, min(64 * _lib.CHUNK, per)))
 

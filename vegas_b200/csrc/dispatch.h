@@ -14,7 +14,7 @@ struct LaunchCfg {
     // in
     int sm_count;
     size_t smem_per_sm, smem_optin;   // device limits
-    bool light;                       // use the one-big-CTA-per-SM geometry (fused sources only)
+    bool light;                       // use the light geometry (fused sources only)
     // work items of the launch's chunk range, per geometry ([0]: VB_CH-cube chunks, [1]: VB_LCH-cube
     // chunks, whole range only); item_off == nullptr: one item per chunk
     const int64_t* item_off[2];
@@ -92,9 +92,9 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     EngineP p = p_in;
     const int dim = p.map.dim;
     cfg.nt = NT; cfg.ch = CH;
-    // staging capacity: ~16 samples per thread, at most 32 KB (heavy) / 64 KB (light)
-    // (light geometry above 10 dimensions: 4 per thread -- the histogram windows need the room)
-    int cap = vb_env_int(CH == VB_CH ? "VB200_CAP" : "VB200_LCAP", (CH != VB_CH && !Src::GRIDW ? 4 : 16) * NT);
+    // staging capacity: 16 samples per thread (heavy) / 20 (light: a 512-cube chunk then usually
+    // is one tile; measured better than leaving the room to the histogram windows)
+    int cap = vb_env_int(CH == VB_CH ? "VB200_CAP" : "VB200_LCAP", (CH != VB_CH ? 20 : 16) * NT);
     const int lim = ((CH == VB_CH ? (NF > 4 ? 48 : 32) : 64) * 1024) / (8 * NF);   // many components: fewer, larger tiles
     if (cap > lim) cap = lim;
     if (cap < 256) cap = 256;
@@ -149,6 +149,9 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     return grid;
 }
 
+#ifndef VB_LGW_MAXD
+#define VB_LGW_MAXD 10     // light geometry: map-grid windows in shared memory up to this many dimensions
+#endif
 // padded-dimension dispatch; light geometry first when asked for and compiled in
 #define VB_DISPATCH_D(F, fobj, LIST_MACRO)                                                     \
     do {                                                                                       \
@@ -159,7 +162,7 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
 #define VB_CASE_D(F, fobj, DD)                                                                 \
     if (dim_ <= DD) { FusedSrc<F, DD> s_{fobj}; return launch_engine(p, s_, cfg, st); }
 #define VB_CASE_L(F, fobj, DD)                                                                 \
-    if (cfg.light && dim_ <= DD) { FusedSrc<F, DD, true, (DD <= 10)> s_{fobj}; return launch_engine(p, s_, cfg, st); }
+    if (cfg.light && dim_ <= DD) { FusedSrc<F, DD, true, (DD <= VB_LGW_MAXD)> s_{fobj}; return launch_engine(p, s_, cfg, st); }
 
 
 // ---------------------------------------------------------------------------------------------

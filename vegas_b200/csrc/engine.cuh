@@ -402,22 +402,26 @@ static __device__ __noinline__ void train_cube(const EngineP& p, const HistW& H,
 // Two geometries:
 //   heavy (LIGHT = false): 128-thread CTAs, several per SM, 256-cube chunks, wide register budget --
 //                          for integrands whose own loop dominates (the N = 1000 ridge);
-//   light (LIGHT = true):  ONE big CTA per SM (VB_LNT threads, VB_LCH-cube chunks) so that all warps
-//                          of the SM share one set of histogram windows AND a shared-memory copy of
-//                          the map's grid nodes for those windows -- for cheap integrands, where the
-//                          sampler itself is the work and occupancy / smem locality decide.
+//   light (LIGHT = true):  TWO 256-thread CTAs per SM (VB_LNT threads, VB_LCH = 512-cube chunks, 128
+//                          registers), each with ~100 KB of shared memory for its histogram windows AND
+//                          a copy of the map's grid nodes for those windows -- for cheap integrands, where
+//                          the sampler itself is the work.  (One 512-thread CTA per SM shares bigger
+//                          windows but idles the whole SM at every barrier: 7.7 -> 7.4 ms on the N = 1 ridge.)
 #ifndef VB_LNT
-#define VB_LNT 512
+#define VB_LNT 256
 #endif
 #ifndef VB_LCH
-#define VB_LCH 1024
+#define VB_LCH 512
 #endif
 template <class F, int D, bool LIGHT = false, bool GW = LIGHT>
 struct FusedSrc {
     static constexpr int NF = F::NF;
     static constexpr int NT = LIGHT ? VB_LNT : VB_ENT;             // threads per CTA
     static constexpr int CH = LIGHT ? VB_LCH : VB_CH;              // hypercubes per chunk
-    static constexpr int MINB = LIGHT ? 1 : (F::NF == 1 ? 3 : 2);   // resident CTAs per SM the register budget is set for
+#ifndef VB_LMINB
+#define VB_LMINB 2
+#endif
+    static constexpr int MINB = LIGHT ? VB_LMINB : (F::NF == 1 ? 3 : 2);   // resident CTAs per SM the register budget is set for
     static constexpr bool GRIDW = GW;                              // grid windows in shared memory (light, D <= 10)
     // stratum digits of a cube (light: narrow, to leave the shared memory to the histogram windows;
     // the host falls back to the heavy geometry when a digit does not fit)

@@ -1,4 +1,4 @@
-// fused_light.cu -- engine instantiations of the light geometry (one big CTA per SM, grid and
+// fused_light.cu -- engine instantiations of the light geometry (two 256-thread CTAs per SM, grid and
 // histogram windows shared by all its warps) for the cheap built-in integrands, and the
 // light-or-heavy choice of every family.
 #include "dispatch.h"

@@ -163,22 +163,42 @@ struct FRidge {
     }
 };
 
-// The same ridge for n < 8 terms without the 8-wide lock-step machinery (and its registers): the
-// light engine geometry uses it.  Arithmetic identical to FRidge's tail loop (mode 0).
+// The same ridge (mode 0) for the light engine geometry, whose one big CTA per SM leaves 128
+// registers per thread: terms 4 at a time in lock-step (FRidge's 8-wide loop needs ~160), then the
+// scalar tail.  Used for short ridges (n <= 128), where the sampler around the integrand is a large
+// part of the work.
 struct FRidgeLight : FRidge {
     template <int D>
     __device__ __forceinline__ void operator()(const double (&x)[D], int dim, double (&f)[1]) const
     {
-        double s = 0.0;
-        for (int k = 0; k < n; ++k) {
+        constexpr int W = 4;
+        double s0 = 0.0, s1 = 0.0;
+        int k = 0;
+        for (; k + W <= n; k += W) {
+            double c[W], q[W], e[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) { c[j] = __ldg(x0 + k + j); q[j] = 0.0; }
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                if (d < dim) {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) { double t = x[d] - c[j]; q[j] = fma(t, t, q[j]); }
+                }
+#pragma unroll
+            for (int j = 0; j < W; ++j) q[j] *= -a;
+            vb_exp_n<W>(q, e);
+            s0 += e[0] + e[2];
+            s1 += e[1] + e[3];
+        }
+        for (; k < n; ++k) {
             const double c = __ldg(x0 + k);
             double q = 0.0;
 #pragma unroll
             for (int d = 0; d < D; ++d)
                 if (d < dim) { double t = x[d] - c; q = fma(t, t, q); }
-            s += vb_exp(-a * q);
+            s0 += vb_exp(-a * q);
         }
-        f[0] = s / (double)n * norm;
+        f[0] = (s0 + s1) / (double)n * norm;
     }
 };
 

@@ -240,7 +240,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         f.x0 = (const double*)c->fparams.p; f.xs = f.x0 + q->n; f.n = q->n; f.mode = q->mode; f.a = q->a; f.norm = q->norm;
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
-        c->light_hint = q->n < 8 && q->mode == 0;          // FRidgeLight == FRidge's tail loop
+        c->light_hint = q->n <= vb_env_int("VB200_RIDGE_LIGHT_N", 48) && q->mode == 0;   // FRidgeLight: 4-wide lock-step
         break;
     }
     case VB200_F_GENZ_OSC: case VB200_F_GENZ_PRODPEAK: case VB200_F_GENZ_CORNER:
@@ -553,7 +553,7 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     cfg.sm_count = c->sm_count;
     cfg.smem_per_sm = c->smem_per_sm;
     cfg.smem_optin = c->smem_per_block_optin;
-    // light geometry (one big CTA per SM): cheap integrand, digits fit 16 bits, and enough big chunks
+    // light geometry (two 256-thread CTAs per SM): cheap integrand, digits fit 16 bits, and enough big chunks
     // to keep every SM busy; VB200_LIGHT=0/1 overrides the work-size test (developer switch)
     bool light = fused && c->light_hint;
     for (int d = 0; d < c->map.dim; ++d) if (c->st.nstrat[d] > (c->map.dim > 10 ? 255 : 65535)) light = false;   // FusedSrc::dig_t
