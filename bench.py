@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 DIM = 8
 RIDGE_N = 1000
 NEVAL_PER_GPU = int(1e8)
-NCU_DRAM_BYTES_PER_LAUNCH = 129.46e6   # 91.42 MB read + 38.04 MB written: ncu capture of one launch at the bench configuration (profiles/prof_ridge1000_r01.summary.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 145.98e6   # 95.15 MB read + 50.83 MB written: ncu capture of one launch at the bench configuration (profiles/prof_ridge1000_r01.summary.txt)
 C_EXP = 18            # fp64 flops charged per exp(): the table-driven vb_exp_n executes 8 DFMA + 1 DADD + 1 DMUL
 METRIC = 'fp64 integrand samples/sec, 8-D ridge (N=%d), vegas+ beta=0.75' % RIDGE_N
 
