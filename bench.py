@@ -216,7 +216,7 @@ def ours(args):
                                'occupancy corresponds to frac=%.3f' % (C_EXP, 3 * DIM + 2 + C_EXP, (3 * DIM + 2 + C_EXP) / 56.),
                     peak_source='measured live: vb200_fp64_peak DFMA probe (MEASURED_PEAKS.json has no FP64 entry); '
                                 'nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2')
-    out = dict(metric=METRIC, value=value, unit='samples/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+    out = dict(metric=METRIC.replace('N=%d' % RIDGE_N, 'N=%d' % args.ridge_n), value=value, unit='samples/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
                data='synthetic',
                config=dict(workload='8-D Gaussian ridge N=%d (examples/ridge.py), vegas+ beta=0.75 alpha=0.5, '

@@ -621,9 +621,9 @@ class Integrator(object):
         self._itn_counter += 1
         return self._itn_counter & 0xFFFFFF
 
-    def _set_neval_stats(self, total, nmax, adaptive):
+    def _set_neval_stats(self, total, nmax, adaptive, reduced=False):
         rank, world = self._rank_world()
-        if world > 1:
+        if world > 1 and not reduced:
             total, nmax = allreduce_neval_stats(total, nmax, self._ctx.device)
         self.last_neval = int(total)
         # pyx:1682,1699-1702: both ends start at min_neval_hcube
@@ -666,10 +666,17 @@ class Integrator(object):
                 self.analyzer.begin(itn, self)
             ctx, torch = self._engine()          # map / sigf may have changed
             hs = int(self.map.inc.shape[1])
-            acc = torch.zeros(nf + nv + 1, dtype=torch.float64, device=dev)
-            sum_f = torch.zeros((self.dim, hs), dtype=torch.float64, device=dev)
-            n_f = torch.zeros((self.dim, hs), dtype=torch.int64, device=dev)
-            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            # device buffers of the iteration, packed by reduction type so that sharded runs need
+            # three collectives and every run three device-to-host copies:
+            #   buf_f (fp64, SUM):  [mean, cov, sum_sigf | sum_f]     buf_i (int64, SUM): [n_f | samples]
+            #   buf_m (int64, MAX): [NaN flag, max samples per hypercube]
+            nacc = nf + nv + 1
+            buf_f = torch.zeros(nacc + self.dim * hs, dtype=torch.float64, device=dev)
+            buf_i = torch.zeros(self.dim * hs + 1, dtype=torch.int64, device=dev)
+            buf_m = torch.zeros(2, dtype=torch.int64, device=dev)
+            acc, sum_f = buf_f[:nacc], buf_f[nacc:].view(self.dim, hs)
+            n_f = buf_i[:self.dim * hs].view(self.dim, hs)
+            status = buf_m[:1].view(torch.int32)              # the kernels set its low word
             if self._timing is not None:
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 ev[0].record()
@@ -686,14 +693,20 @@ class Integrator(object):
             if self._timing is not None:
                 ev[2].record()
             if world > 1:
-                allreduce_iteration(acc, sum_f, n_f, status)
+                buf_i[-1:].fill_(int(total))
+                buf_m[1:].fill_(int(nmax))
+                exchange_iteration(buf_f, buf_i, buf_m)
             if self._timing is not None:
                 ev[3].record()
                 self._timing.append((ev, total))
-            self._set_neval_stats(total, nmax, adaptive)
-            if int(status.item()) != 0:
+            hf, hi, hm = buf_f.cpu().numpy(), buf_i.cpu().numpy(), buf_m.cpu().numpy()
+            if world > 1:
+                total, nmax = int(hi[-1]), int(hm[1])
+            self._set_neval_stats(total, nmax, adaptive, reduced=True)
+            if int(hm[0]) != 0:
                 raise ValueError('integrand evaluates to nan')
-            acc_h = acc.cpu().numpy()
+            acc_h = hf[:nacc]
+            sum_f_h, n_f_h = hf[nacc:].reshape(self.dim, hs), hi[:self.dim * hs].reshape(self.dim, hs)
             mean = acc_h[:nf].copy()
             if self.correlate_integrals:
                 var = np.zeros((nf, nf), float)
@@ -704,7 +717,7 @@ class Integrator(object):
             sum_sigf = float(acc_h[nf + nv])
             if self._trace is not None:
                 self._trace(dict(itn=pitn, mean=mean, var=var, sum_sigf=sum_sigf, last_neval=self.last_neval,
-                                 sum_f=sum_f.cpu().numpy(), n_f=n_f.cpu().numpy(), flags=flags))
+                                 sum_f=sum_f_h.copy(), n_f=n_f_h.copy(), flags=flags))
             result.update(mean, var, self.last_neval)
 
             if self.beta > 0 and not self.adapt_to_errors and self.adapt:
@@ -716,7 +729,7 @@ class Integrator(object):
                         self._sigf_dev.fill_(1.)
                     self.sum_sigf = self._sigf_len
             if flags & (_lib.TRAIN | _lib.TRAIN_ERRORS):
-                self.map._accumulate_training(sum_f.cpu().numpy(), n_f.cpu().numpy())
+                self.map._accumulate_training(sum_f_h, n_f_h)
             if self.alpha > 0 and self.adapt:
                 self.map.adapt(alpha=self.alpha)
             if self.analyzer is not None:
@@ -783,6 +796,15 @@ def allreduce_iteration(acc, sum_f, n_f, status):
     dist.all_reduce(sum_f)
     dist.all_reduce(n_f)
     dist.all_reduce(status, op=dist.ReduceOp.MAX)
+
+
+def exchange_iteration(buf_f, buf_i, buf_m):
+    """The same exchange on the packed buffers of ``Integrator.__call__``: fp64 sums, integer sums
+    (training counts, samples), and maxima (NaN flag, largest hypercube) -- three collectives."""
+    dist = _dist()
+    dist.all_reduce(buf_f)
+    dist.all_reduce(buf_i)
+    dist.all_reduce(buf_m, op=dist.ReduceOp.MAX)
 
 
 def allreduce_neval_stats(total, nmax, device):
