@@ -76,6 +76,8 @@ struct vb200_ctx {
     int64_t nsuper = 0, plan_super_items = -1;            // light geometry: VB_LCH-cube chunks and their items (-1: not planned)
     DevBuf super_items, super_item_off;
     DevBuf chunk_tot, chunk_off, chunk_items, item_off, stats;
+    // the exclusive scans are made when first used: the fused path needs none of them unless a chunk was split
+    bool chunk_off_valid = false, item_off_valid = false, super_off_valid = false;
     std::vector<long long> chunk_off_host;   // fetched lazily by the unfused path
     std::vector<long long> item_off_host;    // same (only when some chunk was split: plan_items != nchunks)
     // integrand
@@ -289,7 +291,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
 // ---------------------------------------------------------------------------------------------
 // allocation pre-pass + chunk offsets
 // ---------------------------------------------------------------------------------------------
-// stats: [0] sum  [1] min  [2] max  [3] largest chunk total   (unsigned long long / long long)
+// stats: [0] sum  [1] min  [2] max  [3] largest chunk total  [4] items  [5] items of the light geometry
 // chunk_items[lc] = work items chunk lc is cut into: 1, or ceil(total / item_samples) when the vegas+
 // allocation piled more than item_samples samples onto its cubes (engine.cuh, "items").  The engine
 // never splits a cube (items that no cube starts in are empty); the samplers split by rows.
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t n
     __shared__ long long red[VB_NT / 32];
     __shared__ int rmin[VB_NT / 32], rmax[VB_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    long long my_sum = 0, my_maxc = 0;
+    long long my_sum = 0, my_maxc = 0, my_items = 0;
     int my_min = 0x7fffffff, my_max = 0;
     for (int64_t lc = blockIdx.x; lc < nchunks; lc += gridDim.x) {
         int64_t lh = lc * VB_CH + tid;
@@ -322,7 +324,9 @@ __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t n
             for (int i = 0; i < VB_NT / 32; ++i) t += red[i];
             chunk_tot[lc] = t;
             long long m = (t + item_samples - 1) / item_samples;
-            chunk_items[lc] = m < 1 ? 1 : (m > VB_MAXITEMS ? VB_MAXITEMS : m);
+            m = m < 1 ? 1 : (m > VB_MAXITEMS ? VB_MAXITEMS : m);
+            chunk_items[lc] = m;
+            my_items += m;
             my_sum += t;
             if (t > my_maxc) my_maxc = t;
         }
@@ -340,6 +344,7 @@ __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t n
         atomicMin(&stats[1], (long long)my_min);
         atomicMax(&stats[2], (long long)my_max);
         atomicMax(&stats[3], my_maxc);
+        atomicAdd((unsigned long long*)&stats[4], (unsigned long long)my_items);
     }
 }
 
@@ -374,14 +379,20 @@ __global__ void __launch_bounds__(1024) k_scan(const long long* tot, int64_t n, 
 
 // items of the light geometry's chunks (group consecutive VB_CH-cube chunks each)
 __global__ void k_super_items(const long long* chunk_tot, int64_t nchunks, int group, long long item_samples,
-                              int max_items, int64_t nsuper, long long* out)
+                              int max_items, int64_t nsuper, long long* out, long long* stats)
 {
+    long long mine = 0;
     for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nsuper; s += (int64_t)gridDim.x * blockDim.x) {
         long long t = 0;
         for (int g = 0; g < group; ++g) if (s * group + g < nchunks) t += chunk_tot[s * group + g];
         long long m = (t + item_samples - 1) / item_samples;
-        out[s] = m < 1 ? 1 : (m > max_items ? max_items : m);
+        m = m < 1 ? 1 : (m > max_items ? max_items : m);
+        out[s] = m;
+        mine += m;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd((unsigned long long*)&stats[5], (unsigned long long)mine);
 }
 
 extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sigf, int64_t min_nh, int64_t max_nh,
@@ -406,53 +417,65 @@ extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sig
     CK(c->chunk_off.ensure(sizeof(long long) * (size_t)(nch + 1)));
     CK(c->chunk_items.ensure(sizeof(long long) * (size_t)(nch + 1)));
     CK(c->item_off.ensure(sizeof(long long) * (size_t)(nch + 1)));
-    CK(c->stats.ensure(sizeof(long long) * 4));
+    CK(c->stats.ensure(sizeof(long long) * 6));
     long long item_samples = vb_env_int("VB200_ITEM", VB_ITEM);
     if (item_samples < 256) item_samples = 256;
-    long long init[4] = {0, 0x7fffffffffffffffLL, 0, 0};
+    long long init[6] = {0, 0x7fffffffffffffffLL, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(c->stats.p, init, sizeof init, cudaMemcpyHostToDevice, st));
     if (nch > 0) {
         int grid = (int)(nch < (int64_t)c->sm_count * 8 ? nch : (int64_t)c->sm_count * 8);
         k_plan<<<grid, VB_NT, 0, st>>>(c->st, c->al, nch, neval_hcube_dev, (long long*)c->chunk_tot.p,
                                        (long long*)c->chunk_items.p, item_samples, (long long*)c->stats.p);
-        k_scan<<<1, 1024, 0, st>>>((const long long*)c->chunk_tot.p, nch, (long long*)c->chunk_off.p);
-        k_scan<<<1, 1024, 0, st>>>((const long long*)c->chunk_items.p, nch, (long long*)c->item_off.p);
-        c->launches += 3;
+        c->launches += 1;
         if (c->light_hint) {
             const int group = VB_LCH / VB_CH;
             c->nsuper = (nch + group - 1) / group;
             CK(c->super_items.ensure(sizeof(long long) * (size_t)(c->nsuper + 1)));
             CK(c->super_item_off.ensure(sizeof(long long) * (size_t)(c->nsuper + 1)));
             k_super_items<<<(int)((c->nsuper + 255) / 256 < 1024 ? (c->nsuper + 255) / 256 : 1024), 256, 0, st>>>(
-                (const long long*)c->chunk_tot.p, nch, group, item_samples * group, VB_LCH, c->nsuper, (long long*)c->super_items.p);
-            k_scan<<<1, 1024, 0, st>>>((const long long*)c->super_items.p, c->nsuper, (long long*)c->super_item_off.p);
-            c->launches += 2;
+                (const long long*)c->chunk_tot.p, nch, group, item_samples * group, VB_LCH, c->nsuper, (long long*)c->super_items.p,
+                (long long*)c->stats.p);
+            c->launches += 1;
         }
         CK(cudaGetLastError());
-    } else {
-        CK(cudaMemsetAsync(c->chunk_off.p, 0, sizeof(long long), st));
-        CK(cudaMemsetAsync(c->item_off.p, 0, sizeof(long long), st));
     }
-    long long out[4], nitems = 0, nsitems = -1;
+    long long out[6];
     CK(cudaMemcpyAsync(out, c->stats.p, sizeof out, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&nitems, (const long long*)c->item_off.p + nch, sizeof nitems, cudaMemcpyDeviceToHost, st));
-    if (c->light_hint && nch > 0)
-        CK(cudaMemcpyAsync(&nsitems, (const long long*)c->super_item_off.p + c->nsuper, sizeof nsitems, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    c->plan_super_items = nsitems;
+    c->plan_super_items = (c->light_hint && nch > 0) ? out[5] : -1;
     if (nch == 0) out[1] = 0;
     c->plan_total = out[0]; c->plan_min = out[1]; c->plan_max = out[2]; c->plan_max_chunk = out[3];
-    c->plan_items = nitems;
+    c->plan_items = out[4];
     c->have_plan = true;
+    c->chunk_off_valid = c->item_off_valid = c->super_off_valid = false;
     c->chunk_off_host.clear();
     c->item_off_host.clear();
     if (stats_host) { stats_host[0] = out[0]; stats_host[1] = out[1]; stats_host[2] = out[2]; stats_host[3] = nch; }
     return 0;
 }
 
-static int fetch_chunk_off(vb200_ctx* c)
+// row offsets of the chunks (exclusive scan of the chunk totals), made on first use after a plan
+static int ensure_chunk_off(vb200_ctx* c, cudaStream_t st)
+{
+    if (c->chunk_off_valid) return 0;
+    CK(cudaSetDevice(c->device));
+    if (c->nchunks > 0) {
+        k_scan<<<1, 1024, 0, st>>>((const long long*)c->chunk_tot.p, c->nchunks, (long long*)c->chunk_off.p);
+        c->launches += 1;
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemsetAsync(c->chunk_off.p, 0, sizeof(long long), st));
+    }
+    c->chunk_off_valid = true;
+    return 0;
+}
+
+static int fetch_chunk_off(vb200_ctx* c, cudaStream_t st = 0)
 {
     if (!c->chunk_off_host.empty()) return 0;
+    int rc0 = ensure_chunk_off(c, st);
+    if (rc0) return rc0;
+    CK(cudaStreamSynchronize(st));
     CK(cudaSetDevice(c->device));
     c->chunk_off_host.resize((size_t)c->nchunks + 1);
     CK(cudaMemcpy(c->chunk_off_host.data(), c->chunk_off.p, sizeof(long long) * (size_t)(c->nchunks + 1), cudaMemcpyDeviceToHost));
@@ -462,7 +485,7 @@ static int fetch_chunk_off(vb200_ctx* c)
 // work items of the local chunk range [chunk_begin, chunk_end) for the heavy geometry (and, for
 // whole-range launches, of the light geometry's chunks)
 struct ItemsSel { const int64_t* off[2]; int64_t begin[2], end[2]; };
-static int set_items(vb200_ctx* c, int64_t chunk_begin, int64_t chunk_end, ItemsSel& it)
+static int set_items(vb200_ctx* c, int64_t chunk_begin, int64_t chunk_end, ItemsSel& it, cudaStream_t st)
 {
     it.off[0] = it.off[1] = nullptr;
     it.begin[0] = chunk_begin; it.end[0] = chunk_end;
@@ -470,13 +493,28 @@ static int set_items(vb200_ctx* c, int64_t chunk_begin, int64_t chunk_end, Items
     const bool whole = chunk_begin == 0 && chunk_end == c->nchunks;
     if (whole && c->plan_super_items >= 0) {
         it.end[1] = c->nsuper;
-        if (c->plan_super_items != c->nsuper) { it.off[1] = (const int64_t*)c->super_item_off.p; it.end[1] = c->plan_super_items; }
+        if (c->plan_super_items != c->nsuper) {
+            if (!c->super_off_valid) {
+                k_scan<<<1, 1024, 0, st>>>((const long long*)c->super_items.p, c->nsuper, (long long*)c->super_item_off.p);
+                c->launches += 1;
+                CK(cudaGetLastError());
+                c->super_off_valid = true;
+            }
+            it.off[1] = (const int64_t*)c->super_item_off.p; it.end[1] = c->plan_super_items;
+        }
     }
     if (c->plan_items == c->nchunks) return 0;         // nothing was split: item j == chunk j
+    if (!c->item_off_valid) {
+        k_scan<<<1, 1024, 0, st>>>((const long long*)c->chunk_items.p, c->nchunks, (long long*)c->item_off.p);
+        c->launches += 1;
+        CK(cudaGetLastError());
+        c->item_off_valid = true;
+    }
     it.off[0] = (const int64_t*)c->item_off.p;
     if (whole) { it.begin[0] = 0; it.end[0] = c->plan_items; return 0; }
     if (c->item_off_host.empty()) {
         CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(st));
         c->item_off_host.resize((size_t)c->nchunks + 1);
         CK(cudaMemcpy(c->item_off_host.data(), c->item_off.p, sizeof(long long) * (size_t)(c->nchunks + 1), cudaMemcpyDeviceToHost));
     }
@@ -561,7 +599,7 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     if (force == 0) light = false;
     if (force != 1 && c->st.nlocal < (int64_t)VB_LCH * 4 * c->sm_count) light = false;
     ItemsSel it;
-    int rc_items = set_items(c, p.chunk_begin, p.chunk_end, it);
+    int rc_items = set_items(c, p.chunk_begin, p.chunk_end, it, st);
     if (rc_items) return rc_items;
     if (it.end[1] < 0) light = false;                  // light chunks were not planned (set_integrand after plan)
     cfg.light = light;
@@ -634,7 +672,7 @@ extern "C" int vb200_reduce(vb200_ctx* c, uint32_t itn, double beta, int flags, 
     if (chunk_begin < 0 || chunk_end > c->nchunks || chunk_begin > chunk_end) return fail(-1, "vb200_reduce: bad chunk range");
     p.chunk_begin = chunk_begin; p.chunk_end = chunk_end;
     p.chunk_off = (const int64_t*)c->chunk_off.p;
-    rc = fetch_chunk_off(c);
+    rc = fetch_chunk_off(c, (cudaStream_t)stream);
     if (rc) return rc;
     p.row0 = c->chunk_off_host[(size_t)chunk_begin];
     p.fbuf = f_dev; p.wbuf = wgt_dev; p.bins = bins_dev;
@@ -917,14 +955,14 @@ static int sample_common(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_
     for (int d = 0; d < VB_MAXD; ++d) p.cstride[d] = c->cstride[d];
     p.chunk_begin = chunk_begin; p.chunk_end = chunk_end;
     p.chunk_off = (const int64_t*)c->chunk_off.p;
-    int rc = fetch_chunk_off(c);
+    int rc = fetch_chunk_off(c, (cudaStream_t)stream);
     if (rc) return rc;
     long long r[2] = {c->chunk_off_host[(size_t)chunk_begin], c->chunk_off_host[(size_t)chunk_end]};
     p.row0 = r[0];
     SampleOut o = o0;
     o.rows = r[1] - r[0];
     ItemsSel it;
-    rc = set_items(c, chunk_begin, chunk_end, it);
+    rc = set_items(c, chunk_begin, chunk_end, it, (cudaStream_t)stream);
     if (rc) return rc;
     p.item_off = it.off[0]; p.item_begin = it.begin[0]; p.item_end = it.end[0];
     const int64_t nch = p.item_end - p.item_begin;
@@ -1361,11 +1399,11 @@ extern "C" int vb200_dy_profile(vb200_ctx* c, uint32_t itn, int64_t chunk_begin,
     for (int d = 0; d < VB_MAXD; ++d) p.cstride[d] = c->cstride[d];
     p.chunk_begin = chunk_begin; p.chunk_end = chunk_end;
     p.chunk_off = (const int64_t*)c->chunk_off.p;
-    int rc = fetch_chunk_off(c);
+    int rc = fetch_chunk_off(c, st);
     if (rc) return rc;
     p.row0 = c->chunk_off_host[(size_t)chunk_begin];
     ItemsSel it;
-    rc = set_items(c, chunk_begin, chunk_end, it);
+    rc = set_items(c, chunk_begin, chunk_end, it, st);
     if (rc) return rc;
     p.item_off = it.off[0]; p.item_begin = it.begin[0]; p.item_end = it.end[0];
     CK(c->counter.ensure(sizeof(unsigned long long)));
