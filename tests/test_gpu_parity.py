@@ -524,5 +524,11 @@ def test_large_config5_three_peaks():
     f = vegas.integrands.GaussMix([5 * [c] + 15 * [0.45] for c in (.23, .39, .74)], 100., 356047712484621.56)
     integ = vegas.Integrator(20 * [[0., 1.]], nstrat=5 * [30] + 15 * [1], neval=5e8, seed=22, nitn=1, max_mem=1e10)
     assert integ.nhcube == 30 ** 5
-    # sharp peaks: a few hypercubes hit the max_neval_hcube=50000 clamp (pyx:1704), so the total stays below neval
-    _check_full_size(integ, f, 1.0, 5, 3, neval_lo=0.1)
+    # sharp peaks: a few hypercubes hit the max_neval_hcube=50000 clamp (pyx:1704), so the total stays below neval.
+    # Exact value on the unit cube (the tails of the peaks at 0.23 and 0.74 are cut, and the reference's
+    # normalisation constant is 1.000295 x (100/pi)^10 / 3): 0.99914660
+    from scipy.special import erf
+    one = lambda c: 0.5 * (erf(10 * (1 - c)) + erf(10 * c))
+    exact = np.mean([one(c) ** 5 * one(0.45) ** 15 for c in (.23, .39, .74)]) * 356047712484621.56 * 3 / (100 / np.pi) ** 10
+    assert abs(exact - 0.9991466) < 1e-7
+    _check_full_size(integ, f, exact, 5, 3, neval_lo=0.1)

@@ -14,11 +14,13 @@ CFG = {
     'genz_osc': (lambda: F.Genz('oscillatory', rng.random(10), rng.random(10)), 10 * [[0., 1.]], dict(neval=1e9, max_mem=1e10)),
     'peaks20': (lambda: F.GaussMix([5 * [c] + 15 * [0.45] for c in (.23, .39, .74)], 100., 356047712484621.56), 20 * [[0., 1.]],
                 dict(neval=5e8, nstrat=5 * [30] + 15 * [1], max_mem=1e10)),
+    'peaks20_full': (lambda: F.GaussMix([5 * [c] + 15 * [0.45] for c in (.23, .39, .74)], 100., 356047712484621.56), 20 * [[0., 1.]],
+                     dict(neval=1e10, nstrat=5 * [60] + 15 * [1], max_mem=1e11)),
     'pathint': (lambda: F.PathIntegral(T=4., ndT=10, x0list=np.linspace(0, 2., 6)), 10 * [[-np.pi / 2, np.pi / 2]],
                 dict(neval=1e8, alpha=0.1)),
 }
 for name, (mk, limits, kw) in CFG.items():
-    if what not in ('all', name):
+    if what != name and not (what == 'all' and name != 'peaks20_full'):
         continue
     if len(sys.argv) > 2:
         kw['neval'] = float(sys.argv[2])
@@ -26,7 +28,7 @@ for name, (mk, limits, kw) in CFG.items():
     if os.environ.get('CFG_ALPHA'):
         kw['alpha'] = float(os.environ['CFG_ALPHA'])
     integ = vegas.Integrator(limits, seed=5, **kw)
-    integ(f, nitn=5)
+    integ(f, nitn=int(os.environ.get('CFG_ADAPT', 5)))
     integ._timing = []
     r = integ(f, nitn=3)
     torch.cuda.synchronize()
