@@ -50,6 +50,8 @@ xt = torch.empty((dim, rows), dtype=torch.float64, device=dev)
 t = timeit(lambda: ctx.sample(7, c0, c1, xt, wgt, transposed=True)); print('sample x^T,wgt      %.3f ms  %.3e rows/s' % (t, rows / t * 1e3))
 y = torch.empty_like(x)
 t = timeit(lambda: ctx.sample(7, c0, c1, x, wgt, y=y));            print('sample x,wgt,y (generic kernel) %.3f ms  %.3e rows/s' % (t, rows / t * 1e3))
-for name, b, fl in (('replay', None, flags), ('bins', bins, flags), ('no training', None, flags & ~_lib.TRAIN)):
+for name, b, fl in (('replay', None, flags), ('bins', bins, flags), ('no training', None, flags & ~_lib.TRAIN),
+                    ('no train/corr', None, flags & ~_lib.TRAIN & ~_lib.CORRELATE), ('bins, no corr', bins, flags & ~_lib.CORRELATE),
+                    ('bins, no sigf', bins, flags & ~_lib.UPDATE_SIGF)):
     t = timeit(lambda: ctx.reduce(7, integ.beta, fl, c0, c1, fx, nf, wgt, sig, acc, sum_f, n_f, hs, status, bins=b))
     print('reduce %-12s %.3f ms  %.3e rows/s  %.0f GB/s   launch %s' % (name, t, rows / t * 1e3, rows * (8 * nf + 8 + (2 * dim if b is not None else 0)) / t / 1e6, ctx.last_launch()))

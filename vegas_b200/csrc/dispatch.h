@@ -95,7 +95,7 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     // staging capacity: 16 samples per thread (heavy) / 20 (light: a 512-cube chunk then usually
     // is one tile; measured better than leaving the room to the histogram windows)
     int cap = vb_env_int(CH == VB_CH ? "VB200_CAP" : "VB200_LCAP", (CH != VB_CH ? 20 : 16) * NT);
-    const int lim = ((CH == VB_CH ? (NF > 4 ? 48 : 32) : 64) * 1024) / (8 * NF);   // many components: fewer, larger tiles
+    const int lim = ((CH == VB_CH ? (NF > 4 ? 48 : 32) : 64) * 1024) / (8 * NF);   // many components: fewer, larger tiles (measured)
     if (cap > lim) cap = lim;
     if (cap < 256) cap = 256;
     cfg.cap = p.cap = cap;

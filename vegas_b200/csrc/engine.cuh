@@ -544,17 +544,11 @@ struct BufferSrc {
 #pragma unroll
             for (int j = 0; j < 8; ++j) bw[j] = 2 * j < dim_ ? __ldg(b32 + j) : 0xffffffffu;
         }
-        double wgt = p.wbuf[row];
-        bool bad = false;
-#pragma unroll
-        for (int s = 0; s < NF; ++s) {
-            double fx = p.fbuf[row * NF + s];
-            bad |= isnan(fx);
-            wf[s] = wgt * fx;
-        }
-        if (bad) p.status[0] = 1;
+        const double wgt = p.wbuf[row];
+        // the training adds only need component 0: they come first, while little else is live
+        // (with 7 components in registers the CAS loops below were compiled around ~1.6 KB of spills)
         if (p.flags & VBF_TRAIN) {
-            double a = wf[0] * (double)n;
+            double a = (wgt * p.fbuf[row * NF]) * (double)n;
             double fdv2 = a * a;
             if (packed) {
 #pragma unroll
@@ -567,7 +561,8 @@ struct BufferSrc {
                             const unsigned bv = (j & 1) ? (bw[2 * g + (j >> 1)] >> 16) : (bw[2 * g + (j >> 1)] & 0xffffu);
                             sa[j] = hist_slot(p, H, d < dim_ ? d : 0, (d >= dim_ || bv == 0xffffu) ? -1 : (int)bv, fdv2);
                         }
-                        hist_sum_slots4(sa[0], sa[1], sa[2], sa[3], fdv2);
+                        if ((sa[0] & sa[1] & sa[2] & sa[3]) != VB_NO_SLOT)         // some bin of the group is in a window
+                            hist_sum_slots4(sa[0], sa[1], sa[2], sa[3], fdv2);
                     }
                 }
             } else if (p.bins != nullptr) {
@@ -594,6 +589,14 @@ struct BufferSrc {
                     hist_add(p, H, 2 * pr + 1, bin_of(p, 2 * pr + 1, y0[2 * pr + 1], ub, nullptr), fdv2);
             }
         }
+        bool bad = false;
+#pragma unroll
+        for (int s = 0; s < NF; ++s) {
+            double fx = p.fbuf[row * NF + s];
+            bad |= isnan(fx);
+            wf[s] = wgt * fx;
+        }
+        if (bad) p.status[0] = 1;
     }
 };
 
