@@ -225,111 +225,6 @@ __device__ __forceinline__ void hist_sum_slots4(uint32_t a0, uint32_t a1, uint32
         :: "r"(a0), "r"(a1), "r"(a2), "r"(a3), "d"(v), "r"(dummy) : "memory");
 }
 
-__device__ __forceinline__ void hist_sum_slots2(uint32_t a0, uint32_t a1, double v)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p0, p1, q;\n\t"
-        ".reg .b64 o0, o1, s0, s1;\n\t"
-        ".reg .f64 n0, n1, f0, f1;\n\t"
-        "setp.ne.u32 p0, %0, 0xffffffff;\n\t"
-        "setp.ne.u32 p1, %1, 0xffffffff;\n\t"
-        "@p0 ld.shared.b64 o0, [%0];\n\t"
-        "@p1 ld.shared.b64 o1, [%1];\n"
-        "VB_CAS_LOOP2:\n\t"
-        "@p0 mov.b64 f0, o0;\n\t"
-        "@p1 mov.b64 f1, o1;\n\t"
-        "@p0 add.rn.f64 n0, f0, %2;\n\t"
-        "@p1 add.rn.f64 n1, f1, %2;\n\t"
-        "@p0 mov.b64 s0, n0;\n\t"
-        "@p1 mov.b64 s1, n1;\n\t"
-        "@p0 atom.shared.cas.b64 s0, [%0], o0, s0;\n\t"
-        "@p1 atom.shared.cas.b64 s1, [%1], o1, s1;\n\t"
-        "@p0 setp.ne.b64 p0, s0, o0;\n\t"
-        "@p1 setp.ne.b64 p1, s1, o1;\n\t"
-        "@p0 mov.b64 o0, s0;\n\t"
-        "@p1 mov.b64 o1, s1;\n\t"
-        "or.pred q, p0, p1;\n\t"
-        "@q bra VB_CAS_LOOP2;\n\t"
-        "}\n"
-        :: "r"(a0), "r"(a1), "d"(v) : "memory");
-}
-
-__device__ __forceinline__ void hist_sum_slot1_ptx(uint32_t a0, double v)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p0;\n\t"
-        ".reg .b64 o0, s0;\n\t"
-        ".reg .f64 n0, f0;\n\t"
-        "setp.ne.u32 p0, %0, 0xffffffff;\n\t"
-        "@p0 ld.shared.b64 o0, [%0];\n"
-        "VB_CAS_LOOP1:\n\t"
-        "@p0 mov.b64 f0, o0;\n\t"
-        "@p0 add.rn.f64 n0, f0, %1;\n\t"
-        "@p0 mov.b64 s0, n0;\n\t"
-        "@p0 atom.shared.cas.b64 s0, [%0], o0, s0;\n\t"
-        "@p0 setp.ne.b64 p0, s0, o0;\n\t"
-        "@p0 mov.b64 o0, s0;\n\t"
-        "@p0 bra VB_CAS_LOOP1;\n\t"
-        "}\n"
-        :: "r"(a0), "d"(v) : "memory");
-}
-
-// one slot, branches instead of predicated instructions
-__device__ __forceinline__ void hist_sum_slot1_bra(uint32_t a0, double v)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p0;\n\t"
-        ".reg .b64 o0, s0;\n\t"
-        ".reg .f64 n0, f0;\n\t"
-        "setp.eq.u32 p0, %0, 0xffffffff;\n\t"
-        "@p0 bra VB_CAS_DONE;\n\t"
-        "ld.shared.b64 o0, [%0];\n"
-        "VB_CAS_LOOPB:\n\t"
-        "mov.b64 f0, o0;\n\t"
-        "add.rn.f64 n0, f0, %1;\n\t"
-        "mov.b64 s0, n0;\n\t"
-        "atom.shared.cas.b64 s0, [%0], o0, s0;\n\t"
-        "setp.ne.b64 p0, s0, o0;\n\t"
-        "mov.b64 o0, s0;\n\t"
-        "@p0 bra VB_CAS_LOOPB;\n"
-        "VB_CAS_DONE:\n\t"
-        "}\n"
-        :: "r"(a0), "d"(v) : "memory");
-}
-
-#ifndef VB_HIST_W
-#define VB_HIST_W 4
-#endif
-
-// fp64 adds of v to W shared slots in lock-step: there is no native shared-memory fp64 add, so
-// each is a compare-and-swap loop; running the W loops side by side overlaps their round trips.
-template <int W>
-__device__ __forceinline__ void hist_sum_slots(uint32_t (&sa)[W], double v)
-{
-    unsigned long long old[W];
-#pragma unroll
-    for (int j = 0; j < W; ++j) old[j] = sa[j] != VB_NO_SLOT ? lds_u64(sa[j]) : 0ull;
-    bool pending;
-    do {
-        unsigned long long seen[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j)
-            if (sa[j] != VB_NO_SLOT)
-                seen[j] = cas_shared_u64(sa[j], old[j], (unsigned long long)__double_as_longlong(__longlong_as_double((long long)old[j]) + v));
-        pending = false;
-#pragma unroll
-        for (int j = 0; j < W; ++j)
-            if (sa[j] != VB_NO_SLOT) {
-                if (seen[j] == old[j]) sa[j] = VB_NO_SLOT;
-                else { old[j] = seen[j]; pending = true; }
-            }
-    } while (pending);
-}
-
-
 // one slot: plain loop
 __device__ __forceinline__ void hist_sum_slot1(uint32_t sa, double v)
 {
@@ -490,26 +385,7 @@ struct FusedSrc {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         sa[j] = (d0 + j < D && d0 + j < dim) ? hist_slot_code(p, H, d0 + j, code[d0 + j < D ? d0 + j : 0], fdv2) : VB_NO_SLOT;
-#if VB_HIST_W == 0
-                    hist_sum_slots<4>(sa, fdv2);
-#elif VB_HIST_W == 4
                     hist_sum_slots4(sa[0], sa[1], sa[2], sa[3], fdv2);
-#elif VB_HIST_W == 2
-                    hist_sum_slots2(sa[0], sa[1], fdv2);
-                    hist_sum_slots2(sa[2], sa[3], fdv2);
-#elif VB_HIST_W == 5
-                    hist_sum_slot1_bra(sa[0], fdv2);
-                    hist_sum_slot1_bra(sa[1], fdv2);
-                    hist_sum_slot1_bra(sa[2], fdv2);
-                    hist_sum_slot1_bra(sa[3], fdv2);
-#elif VB_HIST_W == 6
-                    (void)sa;
-#else
-                    hist_sum_slot1_ptx(sa[0], fdv2);
-                    hist_sum_slot1_ptx(sa[1], fdv2);
-                    hist_sum_slot1_ptx(sa[2], fdv2);
-                    hist_sum_slot1_ptx(sa[3], fdv2);
-#endif
                 }
             }
         }
