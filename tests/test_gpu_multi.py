@@ -21,10 +21,12 @@ NITN = 3
 
 def _run(mpi, light):
     import vegas_b200 as vegas
-    if light:
+    if light == 'callback':
+        os.environ['VB200_ITEM'] = '512'                 # callback path (sample -> host integrand -> reduce), split chunks
+    elif light:
         os.environ['VB200_LIGHT'] = '1'
     f = vegas.integrands.Ridge(dim=4, N=3)
-    integ = vegas.Integrator(LIMITS, mpi=mpi, **KW)
+    integ = vegas.Integrator(LIMITS, mpi=mpi, fused=(light != 'callback'), **KW)
     recs = []
     integ._trace = lambda rec: recs.append(dict(rec))
     r = integ(f, nitn=NITN)
@@ -44,7 +46,7 @@ def _worker(rank, world, port, light, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('light', [False, True])
+@pytest.mark.parametrize('light', [False, True, 'callback'])
 def test_two_gpus_match_one(light):
     import torch
     if torch.cuda.device_count() < 2:
@@ -52,7 +54,7 @@ def test_two_gpus_match_one(light):
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 2000) + int(light)
+    port = 29600 + (os.getpid() % 2000) + [False, True, 'callback'].index(light)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, light, q)) for r in range(2)]
     for p in procs:
         p.start()
@@ -62,6 +64,7 @@ def test_two_gpus_match_one(light):
         assert p.exitcode == 0
     one = _run(False, light)
     os.environ.pop('VB200_LIGHT', None)
+    os.environ.pop('VB200_ITEM', None)
     for o in outs:
         recs, mean, sdev, sigf, grid, geom = o[1:]
         assert len(recs) == NITN
@@ -78,7 +81,7 @@ def test_two_gpus_match_one(light):
         np.testing.assert_allclose(mean, one[1], rtol=1e-12)
         np.testing.assert_allclose(sigf, one[3], rtol=1e-8, atol=1e-300)
         np.testing.assert_allclose(grid, one[4], rtol=1e-10, atol=1e-14)
-        if light:
+        if light is True:
             assert geom['threads'] > 128, geom                 # the light geometry really ran on the shards
     assert np.array_equal(outs[0][5], outs[1][5])              # identical grids on both ranks
 
