@@ -239,8 +239,12 @@ def ours(args):
             except Exception:
                 out['cpu_baseline'] = dict(error=(cp.stderr or cp.stdout)[-300:])
         if world == 1 and args.variants:
-            out['variants'] = variants(vegas, _lib, fp64_peak)
-            out['other_configs'] = other_configs(vegas, _lib, fp64_peak)
+            # companion numbers: never allowed to take the headline line down with them
+            for key, fn in (('variants', variants), ('other_configs', other_configs)):
+                try:
+                    out[key] = fn(vegas, _lib, fp64_peak)
+                except Exception as e:        # noqa: BLE001
+                    out[key] = dict(error='%s: %s' % (type(e).__name__, str(e)[:300]))
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

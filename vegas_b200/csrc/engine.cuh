@@ -332,7 +332,10 @@ struct FusedSrc {
         // Above 10 dimensions the axis loops stay rolled (x[], code[] then live in local memory, which
         // is lane-interleaved and L1-resident): fully unrolled, the 20-D kernels were bound by
         // instruction fetch (ncu: stall_no_instruction on top).
-        constexpr int UNR = D > 10 ? 1 : (D + 1) / 2;
+#ifndef VB_ROLL_UNR
+#define VB_ROLL_UNR 1
+#endif
+        constexpr int UNR = D > 10 ? VB_ROLL_UNR : (D + 1) / 2;
 #pragma unroll UNR
         for (int pr = 0; pr < (D + 1) / 2; ++pr) {
             if (2 * pr < dim) {
