@@ -417,3 +417,21 @@ def test_new_stratification_matches_reference_golden():
     # axes rounded down to one stratum hand their share to the others: the product stays close
     new = new_stratification([4, 4, 4, 4], [1.0, 1e-6, 1e-6, 0.5])
     assert list(new[1:3]) == [1, 1] and 0.7 * 256 < np.prod(new) <= 256
+
+
+def test_ravg_function():
+    """vegas.ravg (src/vegas/__init__.py:1220-1311): running averages rebuilt from iteration results"""
+    import vegas_b200 as vegas
+    from vegas_b200._gv import gv
+    rs = [gv.gvar(1.0, 0.1), gv.gvar(1.2, 0.2), gv.gvar(0.9, 0.1)]
+    w, u = vegas.ravg(rs), vegas.ravg(rs, weighted=False)
+    wts = np.array([100., 25., 100.])
+    assert abs(w.mean - (wts * [1.0, 1.2, 0.9]).sum() / wts.sum()) < 1e-12 and abs(w.sdev - wts.sum() ** -0.5) < 1e-12
+    assert abs(u.mean - np.mean([1.0, 1.2, 0.9])) < 1e-12 and w.nitn == u.nitn == 3
+    assert abs(vegas.ravg(w, weighted=False).mean - u.mean) < 1e-12          # from a result object: its itn_results
+    a = vegas.ravg([gv.gvar([1.0, 2.0], [0.1, 0.2]), gv.gvar([1.1, 2.1], [0.1, 0.2])])
+    assert a.shape == (2,) and abs(a[0].mean - 1.05) < 1e-12
+    d = vegas.ravg([dict(a=gv.gvar(1, 0.1)), dict(a=gv.gvar(1.1, 0.1))])
+    assert abs(d['a'].mean - 1.05) < 1e-12
+    with pytest.raises(ValueError):
+        vegas.ravg([])

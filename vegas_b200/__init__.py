@@ -12,7 +12,7 @@ from ._map import AdaptiveMap
 from ._integrand import (VegasIntegrand, LBatchIntegrand, RBatchIntegrand, BatchIntegrand, VecIntegrand,
                          DeviceIntegrand, lbatchintegrand, rbatchintegrand, batchintegrand,
                          devicebatchintegrand, vecintegrand, MPIintegrand)
-from ._results import RAvg, RAvgArray, RAvgDict, VegasResult, reporter
+from ._results import RAvg, RAvgArray, RAvgDict, VegasResult, reporter, ravg
 from ._integrator import Integrator
 from ._restratify import restratify, restratifyIntegrator, stratification_profile
 from . import integrands
@@ -23,5 +23,5 @@ ranseed = _gv.ranseed
 __all__ = ['Integrator', 'AdaptiveMap', 'RAvg', 'RAvgArray', 'RAvgDict', 'VegasResult', 'reporter',
            'VegasIntegrand', 'LBatchIntegrand', 'RBatchIntegrand', 'BatchIntegrand', 'DeviceIntegrand',
            'lbatchintegrand', 'rbatchintegrand', 'batchintegrand', 'devicebatchintegrand', 'integrands',
-           'restratify', 'restratifyIntegrator',
+           'restratify', 'restratifyIntegrator', 'ravg',
            'ranseed']

@@ -490,3 +490,32 @@ class reporter(object):
         print(self.integrator.map.settings(ngrid=self.ngrid))
         print('')
         sys.stdout.flush()
+
+
+def ravg(reslist, weighted=None, rescale=None):
+    r""" Running average built from a list of |vegas| results (``src/vegas/__init__.py:1220-1311``):
+    ``reslist`` is a list of |GVar|\s, arrays of them, or dictionaries -- or a result object, whose
+    ``itn_results`` are then used.  ``weighted=False`` gives the unweighted (unbiased) average, e.g.
+    ``vegas.ravg(r.itn_results[5:], weighted=False)`` to drop the iterations where the map was still
+    adapting.  ``rescale`` as in :class:`RAvgArray`. """
+    src = reslist
+    if isinstance(reslist, (RAvg, RAvgArray, RAvgDict)):
+        reslist = reslist.itn_results
+    try:
+        if len(reslist) < 1:
+            raise ValueError('reslist empty')
+    except TypeError:
+        raise ValueError('improper type for reslist')
+    if weighted is None:
+        weighted = getattr(src, 'weighted', True)
+    if rescale is None:
+        rescale = getattr(src, 'rescale', reslist[-1])
+    if hasattr(reslist[0], 'keys'):
+        return RAvgDict(itn_results=reslist, weighted=weighted, rescale=rescale)
+    try:
+        shape = np.shape(reslist[0])
+    except Exception:
+        raise ValueError('reslist[i] not GVar, array, or dictionary')
+    if shape == ():
+        return RAvg(itn_results=reslist, weighted=weighted)
+    return RAvgArray(itn_results=reslist, weighted=weighted, rescale=rescale)
