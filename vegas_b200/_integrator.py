@@ -667,13 +667,15 @@ class Integrator(object):
             ctx, torch = self._engine()          # map / sigf may have changed
             hs = int(self.map.inc.shape[1])
             # device buffers of the iteration, packed by reduction type so that sharded runs need
-            # three collectives and every run three device-to-host copies:
+            # three collectives and every run one device-to-host copy:
             #   buf_f (fp64, SUM):  [mean, cov, sum_sigf | sum_f]     buf_i (int64, SUM): [n_f | samples]
             #   buf_m (int64, MAX): [NaN flag, max samples per hypercube]
             nacc = nf + nv + 1
-            buf_f = torch.zeros(nacc + self.dim * hs, dtype=torch.float64, device=dev)
-            buf_i = torch.zeros(self.dim * hs + 1, dtype=torch.int64, device=dev)
-            buf_m = torch.zeros(2, dtype=torch.int64, device=dev)
+            n_bf, n_bi = nacc + self.dim * hs, self.dim * hs + 1
+            raw = torch.zeros(8 * (n_bf + n_bi + 2), dtype=torch.uint8, device=dev)     # one allocation, one D2H copy
+            buf_f = raw[:8 * n_bf].view(torch.float64)
+            buf_i = raw[8 * n_bf:8 * (n_bf + n_bi)].view(torch.int64)
+            buf_m = raw[8 * (n_bf + n_bi):].view(torch.int64)
             acc, sum_f = buf_f[:nacc], buf_f[nacc:].view(self.dim, hs)
             n_f = buf_i[:self.dim * hs].view(self.dim, hs)
             status = buf_m[:1].view(torch.int32)              # the kernels set its low word
@@ -699,7 +701,9 @@ class Integrator(object):
             if self._timing is not None:
                 ev[3].record()
                 self._timing.append((ev, total))
-            hf, hi, hm = buf_f.cpu().numpy(), buf_i.cpu().numpy(), buf_m.cpu().numpy()
+            hraw = raw.cpu().numpy()
+            hf, hi, hm = (hraw[:8 * n_bf].view(np.float64), hraw[8 * n_bf:8 * (n_bf + n_bi)].view(np.int64),
+                          hraw[8 * (n_bf + n_bi):].view(np.int64))
             if world > 1:
                 total, nmax = int(hi[-1]), int(hm[1])
             self._set_neval_stats(total, nmax, adaptive, reduced=True)

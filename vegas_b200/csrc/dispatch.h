@@ -3,6 +3,8 @@
 #pragma once
 #include <stdlib.h>
 
+#include <map>
+
 #include "engine.cuh"
 #include "integrands.cuh"
 
@@ -114,14 +116,34 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     // pass 1: residency without the windows (registers / staging buffer decide)
     vb_plan_windows(p, CH, 0, false);
     size_t smem0 = engine_smem_bytes(NF, cap, CH, dim, 0, Src::GRIDW, DIGB);
-    cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    // The kernel's attributes and its residency per shared-memory size are asked of the driver once
+    // per (device, instantiation): these queries run twice per iteration otherwise, a visible share
+    // of the ~0.5 ms an iteration costs at the reference's everyday sizes (neval = 1e4).
+    struct KernelInfo { bool ready = false; cudaFuncAttributes fa; std::map<size_t, int> bps; };
+    static thread_local std::map<int, KernelInfo> info_by_device;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return -(int)e - 1000;
+    KernelInfo& ki = info_by_device[device];
+    if (!ki.ready) {
+        e = cudaFuncGetAttributes(&ki.fa, kern);
+        if (e != cudaSuccess) return -(int)e - 1000;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((long long)cfg.smem_optin - (long long)ki.fa.sharedSizeBytes));
+        if (e != cudaSuccess) return -(int)e - 1000;
+        ki.ready = true;
+    }
+    const cudaFuncAttributes& fa = ki.fa;
     const long long dyn_max = (long long)cfg.smem_optin - (long long)fa.sharedSizeBytes;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max);
-    if (e != cudaSuccess) return -(int)e - 1000;
+    auto residency = [&](size_t smem, int& out) -> cudaError_t {
+        auto it = ki.bps.find(smem);
+        if (it != ki.bps.end()) { out = it->second; return cudaSuccess; }
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&out, kern, NT, smem);
+        if (err == cudaSuccess) ki.bps[smem] = out;
+        return err;
+    };
     int bps = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, NT, smem0);
+    e = residency(smem0, bps);
     if (e != cudaSuccess) return -(int)e - 1000;
     if (bps < 1) return -24;                                        // does not fit at all
     // pass 2: give the windows the shared memory that this residency leaves unused
@@ -135,7 +157,7 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     vb_plan_windows(p, CH, budget, Src::GRIDW);
     cfg.wtot = p.wtot;
     cfg.smem = engine_smem_bytes(NF, cap, CH, dim, p.wtot, Src::GRIDW, DIGB);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, NT, cfg.smem);
+    e = residency(cfg.smem, bps);
     if (e != cudaSuccess) return -(int)e - 1000;
     if (bps < 1) return -24;
     cfg.blocks_per_sm = bps;
