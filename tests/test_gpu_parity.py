@@ -302,6 +302,20 @@ def test_python_integrands_through_gpu_sampler():
         integ(boom, nitn=1)
 
 
+@pytest.mark.parametrize('dim', [1, 3, 25, 32])
+def test_odd_and_maximum_dimensions_callback_path(dim):
+    """dimensions outside the fused instantiations (odd, above 20, the ABI maximum of 32) through
+    the callback path: engine == oracle on the same uniforms"""
+    vegas = _vegas()
+    c = np.linspace(0.3, 0.7, dim)
+    twin = lambda x: np.exp(-3. * np.sum((x - c) ** 2, axis=1)) * (1. + 0.1 * x[:, 0])
+    f = vegas.lbatchintegrand(lambda x: twin(x))
+    kw = dict(neval=6000)
+    eng = run_engine_iterations(dim * [[0., 1.]], f, nitn=2, seed=300 + dim, **kw)
+    ora = run_oracle_iterations(dim * [[0., 1.]], twin, nitn=2, seed=300 + dim, engine=eng, **kw)
+    compare_iterations(eng, ora, rtol=RTOL, var_rtol=1e-10)
+
+
 def test_device_batch_callback():
     """@devicebatchintegrand: torch CUDA tensors in HBM, no host round trip"""
     import torch

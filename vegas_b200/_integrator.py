@@ -648,7 +648,10 @@ class Integrator(object):
         ``RAvgArray`` / ``RAvgDict``. """
         if kargs:
             self.set(kargs)
-        device_fcn = fcn if (isinstance(fcn, DeviceIntegrand) and self.fused and not self.uses_jac) else None
+        # built-in functors are compiled for up to 20 dimensions; above that their numpy twins run
+        # through the callback path like any other lbatch integrand
+        device_fcn = fcn if (isinstance(fcn, DeviceIntegrand) and self.fused and not self.uses_jac
+                             and self.dim <= _lib.MAX_FUSED_DIM) else None
         std = self._make_std_integrand(fcn)
         nf = std.size
         ctx, torch = self._engine()

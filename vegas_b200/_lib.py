@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get('VB200_LIB') or os.path.join(_HERE, 'libvegas_b200.so'
 
 MAXDIM = 32
 CHUNK = 256
+MAX_FUSED_DIM = 20      # largest padded dimension the fused kernels are instantiated for (csrc/fused_*.cu)
 UPDATE_SIGF, TRAIN, TRAIN_ERRORS, CORRELATE = 1, 2, 4, 8
 F_POLY, F_GAUSS_MIX, F_RIDGE, F_GENZ_OSC, F_GENZ_PRODPEAK, F_GENZ_CORNER, F_GENZ_GAUSS, F_GENZ_C0, \
     F_GENZ_DISC, F_PATHINT = range(10)

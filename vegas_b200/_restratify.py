@@ -43,7 +43,7 @@ def stratification_profile(integ, f, nitn=1, ndy=5):
         raise ValueError('ndy = %s but require 1 <= ndy <= 32' % str(ndy))
     ndy = int(ndy)
     std = integ._make_std_integrand(f)
-    device_fcn = f if (isinstance(f, DeviceIntegrand) and not integ.uses_jac) else None
+    device_fcn = f if (isinstance(f, DeviceIntegrand) and not integ.uses_jac and integ.dim <= _lib.MAX_FUSED_DIM) else None
     ctx, torch = integ._engine()
     dev = ctx.device
     rank, world = integ._rank_world()
