@@ -316,6 +316,17 @@ def test_odd_and_maximum_dimensions_callback_path(dim):
     compare_iterations(eng, ora, rtol=RTOL, var_rtol=1e-10)
 
 
+def test_fused_falls_back_when_no_instantiation():
+    """a built-in functor in a dimension its family is not compiled for (path integral, 20 time
+    slices: instantiated up to 16) runs through the callback path instead of failing"""
+    vegas = _vegas()
+    f = vegas.integrands.PathIntegral(T=4., ndT=20, x0list=np.linspace(0, 2., 6))
+    kw = dict(neval=30000, alpha=0.1)
+    eng = run_engine_iterations(20 * [[-np.pi / 2, np.pi / 2]], f, nitn=2, seed=808, **kw)
+    ora = run_oracle_iterations(20 * [[-np.pi / 2, np.pi / 2]], f, nitn=2, seed=808, engine=eng, **kw)
+    compare_iterations(eng, ora, rtol=1e-11, var_rtol=1e-9)
+
+
 def test_device_batch_callback():
     """@devicebatchintegrand: torch CUDA tensors in HBM, no host round trip"""
     import torch

@@ -691,9 +691,14 @@ class Integrator(object):
             if self._timing is not None:
                 ev[1].record()
             if device_fcn is not None:
-                ctx.iterate_fused(pitn, self.beta, flags, self._sigf_dev, acc, sum_f, n_f, hs, status)
-                self._launches += 2
-            else:
+                try:
+                    ctx.iterate_fused(pitn, self.beta, flags, self._sigf_dev, acc, sum_f, n_f, hs, status)
+                    self._launches += 2
+                except _lib.VegasB200Error as err:
+                    if getattr(err, 'code', 0) != -4:
+                        raise
+                    device_fcn = None          # no fused instantiation for this dimension: callback path from here on
+            if device_fcn is None:
                 self._iterate_unfused(ctx, torch, std, pitn, flags, acc, sum_f, n_f, hs, status)
             if self._timing is not None:
                 ev[2].record()

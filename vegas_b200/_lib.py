@@ -108,7 +108,9 @@ def load():
 
 def check(rc):
     if rc != 0:
-        raise VegasB200Error(load().vb200_last_error().decode())
+        err = VegasB200Error(load().vb200_last_error().decode())
+        err.code = rc            # -4: no kernel compiled for this dimension / number of components
+        raise err
 
 
 def _ptr(t):
