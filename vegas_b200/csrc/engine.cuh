@@ -555,6 +555,79 @@ __device__ __forceinline__ void cube_epilogue(const EngineP& p, const HistW& H, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// work items and chunk set-up, shared by the engine, the samplers and the restratify profile
+// ---------------------------------------------------------------------------------------------
+// which chunk does work item g (numbered over the whole plan) belong to, and which of its parts?
+// (one thread; item_off == nullptr: item g is chunk g)
+__device__ __forceinline__ void locate_item(const EngineP& p, long long g, long long& lc, int& sub, int& nsub)
+{
+    if (p.item_off == nullptr) { lc = g; sub = 0; nsub = 1; return; }
+    int64_t lo = p.chunk_begin, hi = p.chunk_end;                  // item_off[lo] <= g < item_off[hi]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (p.item_off[mid] <= g) lo = mid; else hi = mid;
+    }
+    lc = lo;
+    sub = (int)(g - p.item_off[lo]);
+    nsub = (int)(p.item_off[lo + 1] - p.item_off[lo]);
+}
+
+// whole CTA (NT threads): samples per cube (n_s), their exclusive scan (ex_s[0..CH], ex_s[CH] = total)
+// and the stratum digits (y0_s[c*dim + d], mixed radix with 32-bit carries) of the CH cubes starting
+// at local cube lh0 / global cube h0.  Returns the chunk's sample total; ends with a barrier.
+template <int NT, int CH, class dig_t>
+__device__ __forceinline__ long long chunk_setup(const EngineP& p, int64_t lh0, int64_t h0, long long* ex_s, int* n_s,
+                                                 dig_t* y0_s, uint32_t* base_s, long long* scan_s)
+{
+    constexpr int CPT = CH / NT;                                  // cubes per thread
+    static_assert(CH % NT == 0, "chunk must be a multiple of the CTA size");
+    const int tid = threadIdx.x, dim = p.map.dim;
+    if (tid < dim) base_s[tid] = (uint32_t)((h0 / p.cstride[tid]) % p.st.nstrat[tid]);
+    int n_mine[CPT];
+    long long mine = 0;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        const int c = tid * CPT + i;
+        n_mine[i] = (lh0 + c < p.st.nlocal) ? alloc_neval(p.al, lh0 + c) : 0;
+        mine += n_mine[i];
+    }
+    long long total;
+    long long ex = block_exscan<NT>(mine, scan_s, &total);         // contains __syncthreads
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        const int c = tid * CPT + i;
+        ex_s[c] = ex;
+        n_s[c] = n_mine[i];
+        ex += n_mine[i];
+        uint32_t carry = (uint32_t)c;                              // digits of cube h0+c: base digits plus c, with carries
+        for (int d = 0; d < dim; ++d) {
+            uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
+            uint32_t qd = v / ns;
+            y0_s[c * dim + d] = (dig_t)(v - qd * ns);
+            carry = qd;
+        }
+    }
+    if (tid == NT - 1) ex_s[CH] = total;
+    __syncthreads();
+    return total;
+}
+
+// cubes [c0, cend) of part `sub` of `nsub` of a chunk: those whose first sample lies in that share
+// of the chunk's samples (a cube is never split; broadcast reads of the shared prefix array)
+__device__ __forceinline__ void item_cubes(const long long* ex_s, int ch, long long total, int sub, int nsub, int& c0, int& cend)
+{
+    c0 = 0; cend = ch;
+    if (nsub <= 1) return;
+    const long long b0 = total * sub / nsub, b1 = total * (sub + 1) / nsub;
+    int lo = -1, hi = ch;                                          // first c with ex_s[c] >= b0
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b0) hi = mid; else lo = mid; }
+    c0 = hi;
+    lo = c0 - 1; hi = ch;                                          // first c with ex_s[c] >= b1
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b1) hi = mid; else lo = mid; }
+    cend = hi;
+}
+
+// ---------------------------------------------------------------------------------------------
 // the engine kernel
 // ---------------------------------------------------------------------------------------------
 // dynamic shared memory of k_engine<Src> (the host sizes the launch with the same function)
@@ -579,8 +652,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     constexpr int NT = Src::NT;
     constexpr int CH = Src::CH;
     constexpr int NW = NT / 32;
-    constexpr int CPT = CH / NT;                                  // cubes per thread in set-up
-    static_assert(CH % NT == 0 && CH % VB_CH == 0, "chunk must be a multiple of the CTA size and of the ABI chunk");
+    static_assert(CH % VB_CH == 0, "chunk must be a multiple of the ABI chunk");
     double* wf_s = vb_smem;                                       // [NF][cap]
     long long* ex_s = (long long*)(wf_s + (size_t)NF * p.cap);    // [CH + 1]
     HistW H;
@@ -617,21 +689,12 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     for (;;) {
         __syncthreads();                       // previous item fully consumed
         if (tid == 0) {
-            long long j = (long long)atomicAdd(p.work_counter, 1ull);
-            if (p.item_off == nullptr) {
-                next_s = p.chunk_begin + j;                        // one item per chunk
-                sub_s[0] = 0; sub_s[1] = 1;
-            } else if ((j += p.item_begin) >= p.item_end) {
-                next_s = p.chunk_end;
-            } else {
-                int64_t lo = p.chunk_begin, hi = p.chunk_end;      // item_off[lo] <= j < item_off[hi]
-                while (hi - lo > 1) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (p.item_off[mid] <= j) lo = mid; else hi = mid;
-                }
-                next_s = lo;
-                sub_s[0] = (int)(j - p.item_off[lo]);
-                sub_s[1] = (int)(p.item_off[lo + 1] - p.item_off[lo]);
+            const long long g = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);
+            if (g >= p.item_end) next_s = p.chunk_end;
+            else {
+                long long c; int sub, nsub;
+                locate_item(p, g, c, sub, nsub);
+                next_s = c; sub_s[0] = sub; sub_s[1] = nsub;
             }
         }
         __syncthreads();
@@ -680,48 +743,11 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
             }
             if (force) since_flush = 0;
         }
-        if (tid < dim) base_s[tid] = (uint32_t)((h0 / p.cstride[tid]) % p.st.nstrat[tid]);
-        int n_mine[CPT];
-        long long mine = 0;
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-            const int c = tid * CPT + i;
-            n_mine[i] = (lh0 + c < p.st.nlocal) ? alloc_neval(p.al, lh0 + c) : 0;
-            mine += n_mine[i];
-        }
-        long long total;
-        long long ex = block_exscan<NT>(mine, scan_s, &total);     // contains __syncthreads
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-            const int c = tid * CPT + i;
-            ex_s[c] = ex;
-            n_s[c] = n_mine[i];
-            ex += n_mine[i];
-            // mixed-radix digits of cube h0+c: base digits plus c, with carries
-            uint32_t carry = (uint32_t)c;
-            for (int d = 0; d < dim; ++d) {
-                uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
-                uint32_t qd = v / ns;
-                y0_s[c * dim + d] = (dig_t)(v - qd * ns);
-                carry = qd;
-            }
-        }
-        if (tid == NT - 1) ex_s[CH] = total;
-        __syncthreads();
+        const long long total = chunk_setup<NT, CH, dig_t>(p, lh0, h0, ex_s, n_s, y0_s, base_s, scan_s);
         const int64_t chunk_row = p.chunk_off ? p.chunk_off[lc] - p.row0 : 0;
 
-        // cubes of this item: those whose first sample lies in part `sub` of the chunk's samples
-        // (a cube is never split; all threads search the same shared array: broadcast reads)
-        int c0 = 0, cend = CH;
-        if (nsub > 1) {
-            const long long b0 = total * sub / nsub, b1 = total * (sub + 1) / nsub;
-            int lo = -1, hi = CH;                                  // first c with ex_s[c] >= b0
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b0) hi = mid; else lo = mid; }
-            c0 = hi;
-            lo = c0 - 1; hi = CH;                                  // first c with ex_s[c] >= b1
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b1) hi = mid; else lo = mid; }
-            cend = hi;
-        }
+        int c0, cend;
+        item_cubes(ex_s, CH, total, sub, nsub, c0, cend);
         since_flush += ex_s[cend] - ex_s[c0];
         while (c0 < cend) {
             const long long base = ex_s[c0];

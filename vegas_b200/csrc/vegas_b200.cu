@@ -705,39 +705,16 @@ __global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ Engine
     for (int64_t it = p.item_begin + blockIdx.x; it < p.item_end; it += gridDim.x) {
         __syncthreads();
         if (tid == 0) {
-            if (p.item_off == nullptr) { item_s[0] = it; item_s[1] = 0; item_s[2] = 1; }
-            else {
-                int64_t lo = p.chunk_begin, hi = p.chunk_end;      // item_off[lo] <= it < item_off[hi]
-                while (hi - lo > 1) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (p.item_off[mid] <= it) lo = mid; else hi = mid;
-                }
-                item_s[0] = lo; item_s[1] = it - p.item_off[lo]; item_s[2] = p.item_off[lo + 1] - p.item_off[lo];
-            }
+            long long c; int sb, ns;
+            locate_item(p, it, c, sb, ns);
+            item_s[0] = c; item_s[1] = sb; item_s[2] = ns;
         }
         __syncthreads();
         const int64_t lc = item_s[0];
         const long long sub = item_s[1], nsub = item_s[2];
         const int64_t lh0 = lc * VB_CH;
         const int64_t h0 = local_to_global(p.st, lh0);
-        const int n_mine = (lh0 + tid < p.st.nlocal) ? alloc_neval(p.al, lh0 + tid) : 0;
-        __syncthreads();
-        if (tid < dim) base_s[tid] = (uint32_t)((h0 / p.cstride[tid]) % p.st.nstrat[tid]);
-        long long total;
-        long long ex = block_exscan<VB_NT>(n_mine, scan_s, &total);
-        ex_s[tid] = ex;
-        n_s[tid] = n_mine;
-        if (tid == VB_NT - 1) ex_s[VB_CH] = total;
-        {
-            uint32_t carry = (uint32_t)tid;
-            for (int d = 0; d < dim; ++d) {
-                uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
-                uint32_t qd = v / ns;
-                y0_s[tid * dim + d] = v - qd * ns;
-                carry = qd;
-            }
-        }
-        __syncthreads();
+        const long long total = chunk_setup<VB_NT, VB_CH, uint32_t>(p, lh0, h0, ex_s, n_s, y0_s, base_s, scan_s);
         const int64_t chunk_row = p.chunk_off[lc] - p.row0;
         long long i0 = 0, i1 = total;                  // rows of this item
         if (nsub > 1) { i0 = total * sub / nsub; i1 = total * (sub + 1) / nsub; }   // by rows: no per-cube state here
@@ -812,44 +789,22 @@ __global__ void __launch_bounds__(VB_NT) k_sample_x(const __grid_constant__ Engi
     uint16_t* btile = (uint16_t*)(y0_s + VB_CH * dim) + (size_t)warp * 32 * dim;       // [32][dim]
     for (;;) {
         __syncthreads();
-        if (tid == 0) item_s[0] = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);   // items are claimed: CTAs finish together
-        __syncthreads();
-        const int64_t it = item_s[0];
-        if (it >= p.item_end) break;
-        __syncthreads();
-        if (tid == 0) {
-            if (p.item_off == nullptr) { item_s[0] = it; item_s[1] = 0; item_s[2] = 1; }
+        if (tid == 0) {                                  // items are claimed: CTAs finish together
+            const long long g = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);
+            if (g >= p.item_end) item_s[0] = -1;
             else {
-                int64_t lo = p.chunk_begin, hi = p.chunk_end;
-                while (hi - lo > 1) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (p.item_off[mid] <= it) lo = mid; else hi = mid;
-                }
-                item_s[0] = lo; item_s[1] = it - p.item_off[lo]; item_s[2] = p.item_off[lo + 1] - p.item_off[lo];
+                long long c; int sb, ns;
+                locate_item(p, g, c, sb, ns);
+                item_s[0] = c; item_s[1] = sb; item_s[2] = ns;
             }
         }
         __syncthreads();
         const int64_t lc = item_s[0];
+        if (lc < 0) break;
         const long long sub = item_s[1], nsub = item_s[2];
         const int64_t lh0 = lc * VB_CH;
         const int64_t h0 = local_to_global(p.st, lh0);
-        const int n_mine = (lh0 + tid < p.st.nlocal) ? alloc_neval(p.al, lh0 + tid) : 0;
-        if (tid < dim) base_s[tid] = (uint32_t)((h0 / p.cstride[tid]) % p.st.nstrat[tid]);
-        long long total;
-        long long ex = block_exscan<VB_NT>(n_mine, scan_s, &total);
-        ex_s[tid] = ex;
-        n_s[tid] = n_mine;
-        if (tid == VB_NT - 1) ex_s[VB_CH] = total;
-        {
-            uint32_t carry = (uint32_t)tid;
-            for (int d = 0; d < dim; ++d) {
-                uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
-                uint32_t qd = v / ns;
-                y0_s[tid * dim + d] = v - qd * ns;
-                carry = qd;
-            }
-        }
-        __syncthreads();
+        const long long total = chunk_setup<VB_NT, VB_CH, uint32_t>(p, lh0, h0, ex_s, n_s, y0_s, base_s, scan_s);
         const int64_t chunk_row = p.chunk_off[lc] - p.row0;
         long long i0 = 0, i1 = total;
         if (nsub > 1) { i0 = total * sub / nsub; i1 = total * (sub + 1) / nsub; }   // by rows: no per-cube state here
@@ -1211,7 +1166,7 @@ __device__ __forceinline__ uint32_t dy_mask(const DyP& q, double y)
 
 __global__ void __launch_bounds__(VB_ENT) k_dy_profile(const __grid_constant__ EngineP p, const __grid_constant__ DyP q)
 {
-    constexpr int NT = VB_ENT, NW = NT / 32, CH = VB_CH, CPT = CH / NT;
+    constexpr int NT = VB_ENT, NW = NT / 32, CH = VB_CH;
     __shared__ long long ex_s[CH + 1];
     __shared__ int n_s[CH];
     __shared__ long long scan_s[NW];
@@ -1229,13 +1184,12 @@ __global__ void __launch_bounds__(VB_ENT) k_dy_profile(const __grid_constant__ E
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            long long j = (long long)atomicAdd(p.work_counter, 1ull);
-            if (p.item_off == nullptr) { next_s = p.chunk_begin + j; sub_s[0] = 0; sub_s[1] = 1; }
-            else if ((j += p.item_begin) >= p.item_end) next_s = p.chunk_end;
+            const long long g = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);
+            if (g >= p.item_end) next_s = p.chunk_end;
             else {
-                int64_t lo = p.chunk_begin, hi = p.chunk_end;
-                while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (p.item_off[mid] <= j) lo = mid; else hi = mid; }
-                next_s = lo; sub_s[0] = (int)(j - p.item_off[lo]); sub_s[1] = (int)(p.item_off[lo + 1] - p.item_off[lo]);
+                long long c; int sb, ns;
+                locate_item(p, g, c, sb, ns);
+                next_s = c; sub_s[0] = sb; sub_s[1] = ns;
             }
         }
         __syncthreads();
@@ -1243,42 +1197,10 @@ __global__ void __launch_bounds__(VB_ENT) k_dy_profile(const __grid_constant__ E
         if (lc >= p.chunk_end) break;
         const int sub = sub_s[0], nsub = sub_s[1];
         const int64_t lh0 = lc * CH, h0 = local_to_global(p.st, lh0);
-        if (tid < dim) base_s[tid] = (uint32_t)((h0 / p.cstride[tid]) % p.st.nstrat[tid]);
-        int n_mine[CPT];
-        long long mine = 0;
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-            const int c = tid * CPT + i;
-            n_mine[i] = (lh0 + c < p.st.nlocal) ? alloc_neval(p.al, lh0 + c) : 0;
-            mine += n_mine[i];
-        }
-        long long total;
-        long long ex = block_exscan<NT>(mine, scan_s, &total);
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-            const int c = tid * CPT + i;
-            ex_s[c] = ex; n_s[c] = n_mine[i]; ex += n_mine[i];
-            uint32_t carry = (uint32_t)c;
-            for (int d = 0; d < dim; ++d) {
-                uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
-                uint32_t qd = v / ns;
-                y0_s[c * dim + d] = v - qd * ns;
-                carry = qd;
-            }
-        }
-        if (tid == NT - 1) ex_s[CH] = total;
-        __syncthreads();
+        const long long total = chunk_setup<NT, CH, uint32_t>(p, lh0, h0, ex_s, n_s, y0_s, base_s, scan_s);
         const int64_t chunk_row = p.chunk_off[lc] - p.row0;
-        int c0 = 0, cend = CH;
-        if (nsub > 1) {
-            const long long b0 = total * sub / nsub, b1 = total * (sub + 1) / nsub;
-            int lo = -1, hi = CH;
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b0) hi = mid; else lo = mid; }
-            c0 = hi;
-            lo = c0 - 1; hi = CH;
-            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ex_s[mid] >= b1) hi = mid; else lo = mid; }
-            cend = hi;
-        }
+        int c0, cend;
+        item_cubes(ex_s, CH, total, sub, nsub, c0, cend);
 
         // ---- small cubes: one thread per cube (warp-uniform loop: the warp reduces together)
         for (int cb = c0; cb < cend; cb += NT) {
