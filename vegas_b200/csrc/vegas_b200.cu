@@ -1,17 +1,7 @@
-// vegas_b200.cu -- C ABI of libvegas_b200.so (see include/vegas_b200.h) and the small kernels:
-// allocation pre-pass, chunk-offset scan, sample writer (unfused stage 1), AdaptiveMap array
-// methods, FP64 peak probe.
-#include <math.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include <string>
-#include <vector>
-
-#include "../../include/vegas_b200.h"
-#include "dispatch.h"
+// vegas_b200.cu -- C ABI of libvegas_b200.so (see include/vegas_b200.h): context, integrand registry,
+// allocation pre-pass (work items), engine launches, FP64 peak probe.  The samplers are in
+// sampler.cu, the AdaptiveMap methods in mapops.cu, the restratify profile in profile.cu.
+#include "ctx.h"
 
 static_assert(VB200_MAXDIM == VB_MAXD, "header/kernels disagree on MAXDIM");
 static_assert(VB200_CHUNK == VB_CH, "header/kernels disagree on chunk size");
@@ -19,7 +9,7 @@ static_assert(VB200_UPDATE_SIGF == VBF_UPDATE_SIGF && VB200_TRAIN == VBF_TRAIN &
               VB200_TRAIN_ERRORS == VBF_TRAIN_ERRORS && VB200_CORRELATE == VBF_CORRELATE, "flag mismatch");
 
 static thread_local std::string g_err;
-static int fail(int code, const char* fmt, ...)
+int vb_fail(int code, const char* fmt, ...)
 {
     char buf[512];
     va_list ap;
@@ -29,66 +19,6 @@ static int fail(int code, const char* fmt, ...)
     g_err = buf;
     return code;
 }
-#define CK(call)                                                                               \
-    do {                                                                                       \
-        cudaError_t e_ = (call);                                                               \
-        if (e_ != cudaSuccess) return fail(-2, "%s: %s", #call, cudaGetErrorString(e_));       \
-    } while (0)
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    cudaError_t ensure(size_t n)
-    {
-        if (n <= bytes) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; bytes = 0;
-        cudaError_t e = cudaMalloc(&p, n);
-        if (e == cudaSuccess) bytes = n;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
-};
-
-struct vb200_ctx {
-    int device = 0;
-    int sm_count = 0;
-    size_t smem_per_sm = 0, smem_per_block_optin = 0;
-    int last_grid = 0, last_bps = 0, last_wtot = 0, last_nt = 0, last_ch = 0;
-    bool light_hint = false;                              // the integrand is cheap: prefer the light engine geometry      // geometry of the most recent engine launch
-    int64_t last_smem = 0;
-    uint64_t seed = 0;
-    PhiloxKey key;
-    // map
-    bool have_map = false;
-    MapP map;
-    DevBuf grid;
-    // strata
-    bool have_strata = false;
-    StrataP st;
-    int64_t cstride[VB_MAXD];
-    int64_t nchunks = 0;
-    // plan
-    bool have_plan = false;
-    AllocP al;
-    int64_t plan_total = 0, plan_min = 0, plan_max = 0;
-    int64_t plan_max_chunk = 0, plan_items = 0;
-    int64_t nsuper = 0, plan_super_items = -1;            // light geometry: VB_LCH-cube chunks and their items (-1: not planned)
-    DevBuf super_items, super_item_off;
-    DevBuf chunk_tot, chunk_off, chunk_items, item_off, stats;
-    // the exclusive scans are made when first used: the fused path needs none of them unless a chunk was split
-    bool chunk_off_valid = false, item_off_valid = false, super_off_valid = false;
-    std::vector<long long> chunk_off_host;   // fetched lazily by the unfused path
-    std::vector<long long> item_off_host;    // same (only when some chunk was split: plan_items != nchunks)
-    // integrand
-    int fid = -1, nf = 0, nx0 = 0;
-    std::vector<char> functor;        // host copy of the functor struct
-    DevBuf fparams;                   // device arrays the functor points to
-    // scratch
-    DevBuf partials, scratch, counter;
-    DevBuf sigf_shadow;               // engine output of sigf while chunks are split into items (see run_engine)
-    int64_t launches = 0;
-};
 
 extern "C" int vb200_abi_version(void) { return VB200_ABI_VERSION; }
 extern "C" const char* vb200_last_error(void) { return g_err.c_str(); }
@@ -455,7 +385,7 @@ extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sig
 }
 
 // row offsets of the chunks (exclusive scan of the chunk totals), made on first use after a plan
-static int ensure_chunk_off(vb200_ctx* c, cudaStream_t st)
+int vb_ensure_chunk_off(vb200_ctx* c, cudaStream_t st)
 {
     if (c->chunk_off_valid) return 0;
     CK(cudaSetDevice(c->device));
@@ -470,10 +400,10 @@ static int ensure_chunk_off(vb200_ctx* c, cudaStream_t st)
     return 0;
 }
 
-static int fetch_chunk_off(vb200_ctx* c, cudaStream_t st = 0)
+int vb_fetch_chunk_off(vb200_ctx* c, cudaStream_t st)
 {
     if (!c->chunk_off_host.empty()) return 0;
-    int rc0 = ensure_chunk_off(c, st);
+    int rc0 = vb_ensure_chunk_off(c, st);
     if (rc0) return rc0;
     CK(cudaStreamSynchronize(st));
     CK(cudaSetDevice(c->device));
@@ -484,8 +414,7 @@ static int fetch_chunk_off(vb200_ctx* c, cudaStream_t st = 0)
 
 // work items of the local chunk range [chunk_begin, chunk_end) for the heavy geometry (and, for
 // whole-range launches, of the light geometry's chunks)
-struct ItemsSel { const int64_t* off[2]; int64_t begin[2], end[2]; };
-static int set_items(vb200_ctx* c, int64_t chunk_begin, int64_t chunk_end, ItemsSel& it, cudaStream_t st)
+int vb_set_items(vb200_ctx* c, int64_t chunk_begin, int64_t chunk_end, ItemsSel& it, cudaStream_t st)
 {
     it.off[0] = it.off[1] = nullptr;
     it.begin[0] = chunk_begin; it.end[0] = chunk_end;
@@ -528,7 +457,7 @@ extern "C" int vb200_chunk_offsets(vb200_ctx* c, int64_t* out_host, int64_t coun
     if (!c || !out_host) return fail(-1, "null argument");
     if (!c->have_plan) return fail(-1, "vb200_chunk_offsets: call vb200_plan first");
     if (count < 0 || count > c->nchunks + 1) return fail(-1, "vb200_chunk_offsets: count out of range");
-    int rc = fetch_chunk_off(c);
+    int rc = vb_fetch_chunk_off(c);
     if (rc) return rc;
     memcpy(out_host, c->chunk_off_host.data(), sizeof(int64_t) * (size_t)count);
     return 0;
@@ -599,7 +528,7 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     if (force == 0) light = false;
     if (force != 1 && c->st.nlocal < (int64_t)VB_LCH * 4 * c->sm_count) light = false;
     ItemsSel it;
-    int rc_items = set_items(c, p.chunk_begin, p.chunk_end, it, st);
+    int rc_items = vb_set_items(c, p.chunk_begin, p.chunk_end, it, st);
     if (rc_items) return rc_items;
     if (it.end[1] < 0) light = false;                  // light chunks were not planned (set_integrand after plan)
     cfg.light = light;
@@ -672,680 +601,13 @@ extern "C" int vb200_reduce(vb200_ctx* c, uint32_t itn, double beta, int flags, 
     if (chunk_begin < 0 || chunk_end > c->nchunks || chunk_begin > chunk_end) return fail(-1, "vb200_reduce: bad chunk range");
     p.chunk_begin = chunk_begin; p.chunk_end = chunk_end;
     p.chunk_off = (const int64_t*)c->chunk_off.p;
-    rc = fetch_chunk_off(c, (cudaStream_t)stream);
+    rc = vb_fetch_chunk_off(c, (cudaStream_t)stream);
     if (rc) return rc;
     p.row0 = c->chunk_off_host[(size_t)chunk_begin];
     p.fbuf = f_dev; p.wbuf = wgt_dev; p.bins = bins_dev;
     return run_engine(c, p, nf, false, acc_dev, (cudaStream_t)stream);
 }
 
-// ---------------------------------------------------------------------------------------------
-// unfused stage 1: write the samples (Integrator.random_batch, pyx:1732-1759)
-// ---------------------------------------------------------------------------------------------
-struct SampleOut {
-    double* x; double* wgt; double* y; double* jac1d; int64_t* hcube;
-    int x_transposed;
-    int64_t rows;      // rows in this batch (for the transposed layout)
-    double* u;         // raw uniforms (testing)
-    uint16_t* bins;    // [rows][dim] training bin of every sample (0xffff: none) for vb200_reduce
-};
-
-__global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ EngineP p, const __grid_constant__ SampleOut o)
-{
-    __shared__ long long ex_s[VB_CH + 1];
-    __shared__ int n_s[VB_CH];
-    __shared__ long long scan_s[VB_NT / 32];
-    __shared__ uint32_t base_s[VB_MAXD];
-    extern __shared__ uint32_t y0_s[];          // [VB_CH][dim]
-    __shared__ long long item_s[3];
-    const int tid = threadIdx.x;
-    const int dim = p.map.dim;
-    // work items as in k_engine (a chunk, or one of the nsub parts of a chunk the allocation piled
-    // samples onto), dealt round-robin: items are bounded in size, so this balances
-    for (int64_t it = p.item_begin + blockIdx.x; it < p.item_end; it += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) {
-            long long c; int sb, ns;
-            locate_item(p, it, c, sb, ns);
-            item_s[0] = c; item_s[1] = sb; item_s[2] = ns;
-        }
-        __syncthreads();
-        const int64_t lc = item_s[0];
-        const long long sub = item_s[1], nsub = item_s[2];
-        const int64_t lh0 = lc * VB_CH;
-        const int64_t h0 = local_to_global(p.st, lh0);
-        const long long total = chunk_setup<VB_NT, VB_CH, uint32_t>(p, lh0, h0, ex_s, n_s, y0_s, base_s, scan_s);
-        const int64_t chunk_row = p.chunk_off[lc] - p.row0;
-        long long i0 = 0, i1 = total;                  // rows of this item
-        if (nsub > 1) { i0 = total * sub / nsub; i1 = total * (sub + 1) / nsub; }   // by rows: no per-cube state here
-        for (long long i = i0 + tid; i < i1; i += VB_NT) {
-            int lo = 0, hi = VB_CH;
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (ex_s[mid] <= i) lo = mid; else hi = mid;
-            }
-            const int c = lo;
-            const uint32_t k = (uint32_t)(i - ex_s[c]);
-            const int n = n_s[c];
-            const int64_t h = h0 + c, row = chunk_row + i;
-            const uint32_t* y0 = y0_s + c * dim;
-            double jac = 1.0;
-            for (int pr = 0; 2 * pr < dim; ++pr) {
-                double u[2];
-                philox_pair(p.key, p.itn, h, k, pr, u[0], u[1]);
-                for (int e = 0; e < 2; ++e) {
-                    const int d = 2 * pr + e;
-                    if (d >= dim) break;
-                    if (o.u) { o.u[row * dim + d] = u[e]; continue; }
-                    double y = div_exact((double)y0[d] + u[e], p.st.dns[d], p.st.rns[d]);
-                    const int ni = p.map.ninc[d];
-                    const double* g = p.map.grid + (size_t)d * p.map.gstride;
-                    double t = __dmul_rn(y, (double)ni);
-                    int iy = __double2int_rd(t);
-                    double xv, j1;
-                    if (iy < ni) {
-                        double g0 = __ldg(g + iy), g1 = __ldg(g + iy + 1);
-                        double inc = g1 - g0;
-                        xv = __dadd_rn(g0, __dmul_rn(inc, __dsub_rn(t, (double)iy)));   // no FMA: bit-identical to pyx:354
-                        j1 = inc * (double)ni;
-                    } else {
-                        double g0 = __ldg(g + ni - 1), g1 = __ldg(g + ni);
-                        xv = g1;
-                        j1 = (g1 - g0) * (double)ni;
-                    }
-                    jac *= j1;
-                    if (o.x_transposed) o.x[(int64_t)d * o.rows + row] = xv;
-                    else o.x[row * dim + d] = xv;
-                    if (o.y) o.y[row * dim + d] = y;
-                    if (o.jac1d) o.jac1d[row * dim + d] = j1;
-                }
-            }
-            if (o.u) continue;
-            o.wgt[row] = jac * (p.dv_y / (double)n);
-            if (o.hcube) o.hcube[row] = h;
-        }
-    }
-}
-
-// The integration path's sampler: x[rows][dim] (or [dim][rows]), wgt[rows] and, optionally, the
-// samples' training bins.  Same items and arithmetic as k_sample; the differences are mechanical:
-// the axis loop is unrolled for D <= 10 (grid loads of all axes in flight together), and a warp's
-// 32 rows of x -- one contiguous block of the row-major array -- are staged in shared memory and
-// written out with full-line stores instead of 32 strided 8-byte stores per axis.
-template <int D, bool XT>
-__global__ void __launch_bounds__(VB_NT) k_sample_x(const __grid_constant__ EngineP p, const __grid_constant__ SampleOut o)
-{
-    __shared__ long long ex_s[VB_CH + 1];
-    __shared__ int n_s[VB_CH];
-    __shared__ long long scan_s[VB_NT / 32];
-    __shared__ uint32_t base_s[VB_MAXD];
-    __shared__ long long item_s[3];
-    extern __shared__ double sx_dyn[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int dim = p.map.dim;
-    const int S = dim | 1;                                       // odd row stride: conflict-free tile rows
-    double* tile = sx_dyn + (size_t)warp * 32 * S;               // [32][S] (row-major x only)
-    uint32_t* y0_s = (uint32_t*)(sx_dyn + (XT ? 0 : (size_t)(VB_NT / 32) * 32 * S));   // [VB_CH][dim]
-    uint16_t* btile = (uint16_t*)(y0_s + VB_CH * dim) + (size_t)warp * 32 * dim;       // [32][dim]
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {                                  // items are claimed: CTAs finish together
-            const long long g = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);
-            if (g >= p.item_end) item_s[0] = -1;
-            else {
-                long long c; int sb, ns;
-                locate_item(p, g, c, sb, ns);
-                item_s[0] = c; item_s[1] = sb; item_s[2] = ns;
-            }
-        }
-        __syncthreads();
-        const int64_t lc = item_s[0];
-        if (lc < 0) break;
-        const long long sub = item_s[1], nsub = item_s[2];
-        const int64_t lh0 = lc * VB_CH;
-        const int64_t h0 = local_to_global(p.st, lh0);
-        const long long total = chunk_setup<VB_NT, VB_CH, uint32_t>(p, lh0, h0, ex_s, n_s, y0_s, base_s, scan_s);
-        const int64_t chunk_row = p.chunk_off[lc] - p.row0;
-        long long i0 = 0, i1 = total;
-        if (nsub > 1) { i0 = total * sub / nsub; i1 = total * (sub + 1) / nsub; }   // by rows: no per-cube state here
-        for (long long ib = i0; ib < i1; ib += VB_NT) {           // warp-uniform trip count
-            const long long i = ib + tid;
-            const bool live = i < i1;
-            const int64_t row = chunk_row + i;
-            if (live) {
-                int lo = 0, hi = VB_CH;
-                while (hi - lo > 1) {
-                    int mid = (lo + hi) >> 1;
-                    if (ex_s[mid] <= i) lo = mid; else hi = mid;
-                }
-                const int c = lo;
-                const uint32_t k = (uint32_t)(i - ex_s[c]);
-                const int64_t h = h0 + c;
-                const uint32_t* y0 = y0_s + c * dim;
-                double jac = 1.0;
-                constexpr int UNR = D > 10 ? 1 : (D + 1) / 2;
-#pragma unroll UNR
-                for (int pr = 0; pr < (D + 1) / 2; ++pr) {
-                    if (2 * pr < dim) {
-                        double u[2];
-                        philox_pair(p.key, p.itn, h, k, pr, u[0], u[1]);
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int d = 2 * pr + e;
-                            if (d < D && d < dim) {
-                                const int ni = p.map.ninc[d];
-                                const double y = div_exact((double)y0[d] + u[e], p.st.dns[d], p.st.rns[d]);
-                                const double t = __dmul_rn(y, p.dni[d]);
-                                const int iy = __double2int_rd(t);
-                                const int ic = min(iy, ni - 1);
-                                const double* gp = p.map.grid + (size_t)d * p.map.gstride + ic;
-                                const double g0 = __ldg(gp), g1 = __ldg(gp + 1);
-                                const double inc = g1 - g0;
-                                const double xin = __dadd_rn(g0, __dmul_rn(inc, __dsub_rn(t, (double)iy)));   // no FMA: pyx:354
-                                const double xv = iy < ni ? xin : g1;                                         // pyx:357-359
-                                jac *= inc * p.dni[d];
-                                if (XT) o.x[(int64_t)d * o.rows + row] = xv;
-                                else tile[lane * S + d] = xv;
-                                if (o.bins) btile[lane * dim + d] = (y > 0.0 && y < 1.0) ? (uint16_t)ic : (uint16_t)0xffff;   // pyx:460
-                            }
-                        }
-                    }
-                }
-                o.wgt[row] = jac * (p.dv_y / (double)n_s[c]);
-            }
-            __syncwarp();
-            // the warp's rows are consecutive: one contiguous block of x (and of bins)
-            const long long wfirst = ib + (tid - lane);
-            const int nlive = (int)(i1 - wfirst < 32 ? (i1 - wfirst > 0 ? i1 - wfirst : 0) : 32);
-            const int64_t wrow = chunk_row + wfirst;
-            const int nel = nlive * dim;
-            if (!XT) {
-                double* dst = o.x + wrow * dim;
-                for (int e = lane; e < nel; e += 32) {
-                    const int r = e / dim;
-                    dst[e] = tile[r * S + (e - r * dim)];
-                }
-            }
-            if (o.bins) {
-                uint16_t* dst = o.bins + wrow * dim;
-                for (int e = lane; e < nel; e += 32) dst[e] = btile[e];
-            }
-            __syncwarp();
-        }
-    }
-}
-
-template <int D>
-static int launch_sample_x(const EngineP& p, const SampleOut& o, int grid, cudaStream_t st)
-{
-    const int dim = p.map.dim;
-    const size_t tile = o.x_transposed ? 0 : sizeof(double) * (size_t)(VB_NT / 32) * 32 * (dim | 1);
-    size_t smem = tile + sizeof(uint32_t) * (size_t)VB_CH * dim + (o.bins ? sizeof(uint16_t) * (size_t)VB_NT * dim : 0);
-    smem = (smem + 15) & ~(size_t)15;
-    cudaError_t e;
-    if (o.x_transposed) {
-        e = cudaFuncSetAttribute(k_sample_x<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return -(int)e - 1000;
-        k_sample_x<D, true><<<grid, VB_NT, smem, st>>>(p, o);
-    } else {
-        e = cudaFuncSetAttribute(k_sample_x<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return -(int)e - 1000;
-        k_sample_x<D, false><<<grid, VB_NT, smem, st>>>(p, o);
-    }
-    return 0;
-}
-
-static int sample_common(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, const SampleOut& o0, void* stream)
-{
-    if (!c->have_map || !c->have_strata) return fail(-1, "sample: map/strata not set");
-    if (!c->have_plan) return fail(-1, "sample: call vb200_plan first");
-    if (chunk_begin < 0 || chunk_end > c->nchunks || chunk_begin > chunk_end) return fail(-1, "sample: bad chunk range");
-    CK(cudaSetDevice(c->device));
-    if (chunk_begin == chunk_end) return 0;
-    EngineP p;
-    memset(&p, 0, sizeof p);
-    p.map = c->map; p.st = c->st; p.al = c->al; p.key = c->key;
-    p.itn = itn;
-    p.dv_y = 1.0 / (double)c->st.nhcube;
-    for (int d = 0; d < VB_MAXD; ++d) p.cstride[d] = c->cstride[d];
-    p.chunk_begin = chunk_begin; p.chunk_end = chunk_end;
-    p.chunk_off = (const int64_t*)c->chunk_off.p;
-    int rc = fetch_chunk_off(c, (cudaStream_t)stream);
-    if (rc) return rc;
-    long long r[2] = {c->chunk_off_host[(size_t)chunk_begin], c->chunk_off_host[(size_t)chunk_end]};
-    p.row0 = r[0];
-    SampleOut o = o0;
-    o.rows = r[1] - r[0];
-    ItemsSel it;
-    rc = set_items(c, chunk_begin, chunk_end, it, (cudaStream_t)stream);
-    if (rc) return rc;
-    p.item_off = it.off[0]; p.item_begin = it.begin[0]; p.item_end = it.end[0];
-    const int64_t nch = p.item_end - p.item_begin;
-    int64_t g = (int64_t)c->sm_count * 8;
-    if (g > nch) g = nch;
-    for (int d = 0; d < VB_MAXD; ++d) p.dni[d] = (double)c->map.ninc[d];
-    CK(c->counter.ensure(sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), (cudaStream_t)stream));
-    p.work_counter = (unsigned long long*)c->counter.p;
-    if (o.x && o.wgt && !o.y && !o.jac1d && !o.hcube && !o.u) {
-        // the integration path: x, wgt (+ training bins)
-        const int dim = c->map.dim;
-        int e = dim <= 4 ? launch_sample_x<4>(p, o, (int)g, (cudaStream_t)stream)
-              : dim <= 8 ? launch_sample_x<8>(p, o, (int)g, (cudaStream_t)stream)
-              : dim <= 10 ? launch_sample_x<10>(p, o, (int)g, (cudaStream_t)stream)
-                          : launch_sample_x<VB_MAXD>(p, o, (int)g, (cudaStream_t)stream);
-        if (e) return fail(-2, "sample: launch set-up failed (%s)", cudaGetErrorString((cudaError_t)(-(e + 1000))));
-    } else {
-        if (o.bins) return fail(-1, "sample: training bins are only written together with x and wgt alone");
-        size_t smem = sizeof(uint32_t) * (size_t)VB_CH * c->map.dim;
-        k_sample<<<(int)g, VB_NT, smem, (cudaStream_t)stream>>>(p, o);
-    }
-    c->launches += 1;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int vb200_sample(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* x_dev, double* wgt_dev,
-                            double* y_dev, double* jac1d_dev, int64_t* hcube_dev, uint16_t* bins_dev, int x_transposed, void* stream)
-{
-    if (!c || !x_dev || !wgt_dev) return fail(-1, "vb200_sample: null argument");
-    if (bins_dev)
-        for (int d = 0; d < c->map.dim; ++d)
-            if (c->map.ninc[d] > 0xffff) return fail(-1, "vb200_sample: training bins need ninc <= 65535");
-    SampleOut o;
-    memset(&o, 0, sizeof o);
-    o.x = x_dev; o.wgt = wgt_dev; o.y = y_dev; o.jac1d = jac1d_dev; o.hcube = hcube_dev; o.x_transposed = x_transposed;
-    o.bins = bins_dev;
-    return sample_common(c, itn, chunk_begin, chunk_end, o, stream);
-}
-
-extern "C" int vb200_uniforms(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* u_dev, void* stream)
-{
-    if (!c || !u_dev) return fail(-1, "vb200_uniforms: null argument");
-    SampleOut o;
-    memset(&o, 0, sizeof o);
-    o.u = u_dev;
-    return sample_common(c, itn, chunk_begin, chunk_end, o, stream);
-}
-
-// ---------------------------------------------------------------------------------------------
-// AdaptiveMap array methods
-// ---------------------------------------------------------------------------------------------
-__global__ void k_map(const MapP m, const double* y, double* x, double* jac, int64_t n, double* jac1d)
-{
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double j = 1.0;
-        for (int d = 0; d < m.dim; ++d) {
-            const int ni = m.ninc[d];
-            const double* g = m.grid + (size_t)d * m.gstride;
-            double t = __dmul_rn(y[i * m.dim + d], (double)ni);
-            int iy = (int)floor(t);
-            double j1;
-            if (iy < ni) {
-                // reference (pyx:351-356) would index out of bounds for y < 0; clamp like y == 0 side
-                if (iy < 0) iy = 0;
-                double g0 = g[iy], inc = g[iy + 1] - g0;
-                if (x) x[i * m.dim + d] = __dadd_rn(g0, __dmul_rn(inc, __dsub_rn(t, (double)iy)));
-                j1 = __dmul_rn(inc, (double)ni);
-            } else {
-                if (x) x[i * m.dim + d] = g[ni];
-                j1 = __dmul_rn(g[ni] - g[ni - 1], (double)ni);
-            }
-            j = __dmul_rn(j, j1);
-            if (jac1d) jac1d[i * m.dim + d] = j1;
-        }
-        if (jac) jac[i] = j;
-    }
-}
-
-__global__ void k_invmap(const MapP m, const double* x, double* y, double* jac, int64_t n)
-{
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double j = 1.0;
-        for (int d = 0; d < m.dim; ++d) {
-            const int ni = m.ninc[d];
-            const double* g = m.grid + (size_t)d * m.gstride;
-            const double xv = x[i * m.dim + d];
-            int lo = 0, hi = ni + 1;               // first index with g[idx] > xv (searchsorted right)
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (g[mid] <= xv) lo = mid + 1; else hi = mid;
-            }
-            if (lo > 0 && lo <= ni) {
-                int k = lo - 1;
-                double inc = g[k + 1] - g[k];
-                y[i * m.dim + d] = __ddiv_rn(__dadd_rn((double)k, __ddiv_rn(__dsub_rn(xv, g[k]), inc)), (double)ni);
-                j = __dmul_rn(j, __dmul_rn(inc, (double)ni));
-            } else if (lo <= 0) {
-                y[i * m.dim + d] = 0.0;
-                j = __dmul_rn(j, __dmul_rn(g[1] - g[0], (double)ni));
-            } else {
-                y[i * m.dim + d] = 1.0;
-                j = __dmul_rn(j, __dmul_rn(g[ni] - g[ni - 1], (double)ni));
-            }
-        }
-        jac[i] = j;
-    }
-}
-
-__global__ void k_add_training(const MapP m, const double* y, const double* f, int64_t n, double* sum_f,
-                               unsigned long long* n_f, int hstride)
-{
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double fv = fabs(f[i]);
-        for (int d = 0; d < m.dim; ++d) {
-            double yv = y[i * m.dim + d];
-            if (yv > 0.0 && yv < 1.0) {
-                int iy = (int)floor(__dmul_rn(yv, (double)m.ninc[d]));
-                atomicAdd(sum_f + (size_t)d * hstride + iy, fv);
-                atomicAdd(n_f + (size_t)d * hstride + iy, 1ull);
-            }
-        }
-    }
-}
-
-static int grid_for(vb200_ctx* c, int64_t n)
-{
-    int64_t g = (n + 255) / 256, cap = (int64_t)c->sm_count * 16;
-    if (g > cap) g = cap;
-    return (int)(g < 1 ? 1 : g);
-}
-
-extern "C" int vb200_map(vb200_ctx* c, const double* y, double* x, double* jac, int64_t n, void* stream)
-{
-    if (!c || !y || !x || !jac) return fail(-1, "vb200_map: null argument");
-    if (!c->have_map) return fail(-1, "vb200_map: no map set");
-    if (n <= 0) return 0;
-    CK(cudaSetDevice(c->device));
-    k_map<<<grid_for(c, n), 256, 0, (cudaStream_t)stream>>>(c->map, y, x, jac, n, nullptr);
-    c->launches += 1;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int vb200_jac1d(vb200_ctx* c, const double* y, double* jac1d, int64_t n, void* stream)
-{
-    if (!c || !y || !jac1d) return fail(-1, "vb200_jac1d: null argument");
-    if (!c->have_map) return fail(-1, "vb200_jac1d: no map set");
-    if (n <= 0) return 0;
-    CK(cudaSetDevice(c->device));
-    k_map<<<grid_for(c, n), 256, 0, (cudaStream_t)stream>>>(c->map, y, nullptr, nullptr, n, jac1d);
-    c->launches += 1;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int vb200_invmap(vb200_ctx* c, const double* x, double* y, double* jac, int64_t n, void* stream)
-{
-    if (!c || !y || !x || !jac) return fail(-1, "vb200_invmap: null argument");
-    if (!c->have_map) return fail(-1, "vb200_invmap: no map set");
-    if (n <= 0) return 0;
-    CK(cudaSetDevice(c->device));
-    k_invmap<<<grid_for(c, n), 256, 0, (cudaStream_t)stream>>>(c->map, x, y, jac, n);
-    c->launches += 1;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int vb200_add_training_data(vb200_ctx* c, const double* y, const double* f, int64_t n, double* sum_f,
-                                       uint64_t* n_f, int64_t hstride, void* stream)
-{
-    if (!c || !y || !f || !sum_f || !n_f) return fail(-1, "vb200_add_training_data: null argument");
-    if (!c->have_map) return fail(-1, "vb200_add_training_data: no map set");
-    for (int d = 0; d < c->map.dim; ++d)
-        if (c->map.ninc[d] > hstride) return fail(-1, "vb200_add_training_data: hstride too small");
-    if (n <= 0) return 0;
-    CK(cudaSetDevice(c->device));
-    k_add_training<<<grid_for(c, n), 256, 0, (cudaStream_t)stream>>>(c->map, y, f, n, sum_f, (unsigned long long*)n_f, (int)hstride);
-    c->launches += 1;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// built-in functor on buffers
-// ---------------------------------------------------------------------------------------------
-extern "C" int vb200_eval_integrand(vb200_ctx* c, const double* x_dev, int64_t rows, double* f_dev, void* stream)
-{
-    if (!c || !x_dev || !f_dev) return fail(-1, "vb200_eval_integrand: null argument");
-    if (c->fid < 0 || !c->have_map) return fail(-1, "vb200_eval_integrand: no integrand / map set");
-    if (rows <= 0) return 0;
-    CK(cudaSetDevice(c->device));
-    const void* f = c->functor.data();
-    const int dim = c->map.dim;
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    switch (c->fid) {
-    case VB200_F_POLY: rc = eval_poly(f, dim, x_dev, rows, f_dev, c->sm_count, st); break;
-    case VB200_F_GAUSS_MIX: rc = eval_gaussmix(f, dim, x_dev, rows, f_dev, c->sm_count, st); break;
-    case VB200_F_RIDGE: rc = eval_ridge(f, dim, x_dev, rows, f_dev, c->sm_count, st); break;
-    case VB200_F_PATHINT: rc = eval_pathint(f, c->nx0, dim, x_dev, rows, f_dev, c->sm_count, st); break;
-    default: rc = eval_genz(f, dim, x_dev, rows, f_dev, c->sm_count, st); break;
-    }
-    if (rc == -22) return fail(-4, "vb200_eval_integrand: no kernel compiled for dim=%d integrand=%d", dim, c->fid);
-    if (rc) return fail(-2, "vb200_eval_integrand: launch failed (%s)", cudaGetErrorString((cudaError_t)(-(rc + 1000))));
-    c->launches += 1;
-    return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Stratification profile (vegas.restratify, __init__.py:1314-1419): the auxiliary integrand there
-// has components dI[mu][i] = f(x) * [yst[i] <= y_mu <= yst[i+1]] (one-hot in each axis' y-bin), and
-// the iteration computes mean and variance of each through the usual per-hypercube two-pass
-// (pyx:2142-2186, correlate_integrals=False).  Here the D*ndy components are never materialised:
-// this kernel re-derives y from the Philox counter, takes w*f from the callback path's buffers and
-// accumulates, per hypercube, axis and OCCUPIED bin, exactly those two passes (a component that
-// is zero on every sample of a cube contributes nothing).  acc[(mu*ndy + i)*2 + {0,1}] += {mean, var}.
-//   small cubes (<= 32 samples): one thread per cube, samples in the reference's order;
-//   larger cubes: one warp per cube.
-// Sums are kept per warp in shared memory (only lane 0 of a warp writes its array), added to acc
-// with fp64 atomics at the end.
-// ---------------------------------------------------------------------------------------------
-#define VB_DY_MAX 32
-struct DyP {
-    int ndy;
-    double yst[VB_DY_MAX + 1];     // numpy.linspace(0, 1, ndy + 1)
-    const double* f; int fstride;  // f[row * fstride]  (component 0 of the integrand)
-    const double* w;               // wgt[row]
-    double* acc;                   // [dim][ndy][2]
-};
-
-// bins y belongs to (closed intervals as in the reference: a y on a boundary is in two bins)
-__device__ __forceinline__ uint32_t dy_mask(const DyP& q, double y)
-{
-    int i = __double2int_rd(y * (double)q.ndy);
-    i = max(0, min(i, q.ndy - 1));
-    uint32_t m = 0;
-#pragma unroll
-    for (int j = -1; j <= 1; ++j) {
-        const int b = i + j;
-        if (b >= 0 && b < q.ndy && q.yst[b] <= y && y <= q.yst[b + 1]) m |= 1u << b;
-    }
-    return m;
-}
-
-__global__ void __launch_bounds__(VB_ENT) k_dy_profile(const __grid_constant__ EngineP p, const __grid_constant__ DyP q)
-{
-    constexpr int NT = VB_ENT, NW = NT / 32, CH = VB_CH;
-    __shared__ long long ex_s[CH + 1];
-    __shared__ int n_s[CH];
-    __shared__ long long scan_s[NW];
-    __shared__ uint32_t base_s[VB_MAXD];
-    __shared__ long long next_s;
-    __shared__ int sub_s[2];
-    extern __shared__ double dy_dyn[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int dim = p.map.dim, ndy = q.ndy;
-    const int nacc = dim * ndy * 2;
-    double* accw = dy_dyn + (size_t)warp * nacc;                        // [dim][ndy][2] of this warp
-    uint32_t* y0_s = (uint32_t*)(dy_dyn + (size_t)NW * nacc);           // [CH][dim]
-    for (int i = tid; i < NW * nacc; i += NT) dy_dyn[i] = 0.0;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            const long long g = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);
-            if (g >= p.item_end) next_s = p.chunk_end;
-            else {
-                long long c; int sb, ns;
-                locate_item(p, g, c, sb, ns);
-                next_s = c; sub_s[0] = sb; sub_s[1] = ns;
-            }
-        }
-        __syncthreads();
-        const int64_t lc = next_s;
-        if (lc >= p.chunk_end) break;
-        const int sub = sub_s[0], nsub = sub_s[1];
-        const int64_t lh0 = lc * CH, h0 = local_to_global(p.st, lh0);
-        const long long total = chunk_setup<NT, CH, uint32_t>(p, lh0, h0, ex_s, n_s, y0_s, base_s, scan_s);
-        const int64_t chunk_row = p.chunk_off[lc] - p.row0;
-        int c0, cend;
-        item_cubes(ex_s, CH, total, sub, nsub, c0, cend);
-
-        // ---- small cubes: one thread per cube (warp-uniform loop: the warp reduces together)
-        for (int cb = c0; cb < cend; cb += NT) {
-            const int c = cb + tid;
-            const int n = (c < cend && n_s[c] <= 32) ? n_s[c] : 0;
-            const int64_t row = chunk_row + (c < CH ? ex_s[c] : 0);
-            const int64_t h = h0 + c;
-            double wf[32];
-            uint32_t mk[2][32];
-            for (int k = 0; k < n; ++k) wf[k] = q.w[row + k] * q.f[(row + k) * q.fstride];
-            for (int pr = 0; 2 * pr < dim; ++pr) {
-                for (int k = 0; k < n; ++k) {
-                    double ua, ub;
-                    philox_pair(p.key, p.itn, h, (uint32_t)k, pr, ua, ub);
-                    mk[0][k] = dy_mask(q, div_exact((double)y0_s[c * dim + 2 * pr] + ua, p.st.dns[2 * pr], p.st.rns[2 * pr]));
-                    mk[1][k] = (2 * pr + 1 < dim)
-                        ? dy_mask(q, div_exact((double)y0_s[c * dim + 2 * pr + 1] + ub, p.st.dns[2 * pr + 1], p.st.rns[2 * pr + 1])) : 0u;
-                }
-                for (int e = 0; e < 2 && 2 * pr + e < dim; ++e) {
-                    const int mu = 2 * pr + e;
-                    uint32_t um = 0;
-                    for (int k = 0; k < n; ++k) um |= mk[e][k];
-                    const uint32_t wum = __reduce_or_sync(0xffffffffu, um);
-                    for (int i = 0; i < ndy; ++i) {
-                        const uint32_t bit = 1u << i;
-                        if (!(wum & bit)) continue;                     // warp-uniform
-                        double madd = 0.0, vadd = 0.0;
-                        if (um & bit) {
-                            double S = 0.0;
-                            for (int k = 0; k < n; ++k) if (mk[e][k] & bit) S += wf[k];
-                            const double mS = S / (double)n, thr = VB_EPSILON * fabs(mS);
-                            double sd = 0.0, qq = 0.0;
-                            for (int k = 0; k < n; ++k) {
-                                double d = ((mk[e][k] & bit) ? wf[k] : 0.0) - mS;
-                                if (fabs(d) < thr) { qq += thr * thr; d = 0.0; } else qq += d * d;
-                                sd += d;
-                            }
-                            madd = S + sd;
-                            vadd = ((double)n * qq - sd * sd) / ((double)n - 1.0);
-                        }
-                        madd = warp_sum(madd);
-                        vadd = warp_sum(vadd);
-                        if (lane == 0) { accw[(mu * ndy + i) * 2] += madd; accw[(mu * ndy + i) * 2 + 1] += vadd; }
-                    }
-                }
-            }
-        }
-        // ---- larger cubes: one warp per cube
-        for (int c = c0 + warp; c < cend; c += NW) {
-            const int n = n_s[c];
-            if (n <= 32) continue;
-            const int64_t row = chunk_row + ex_s[c];
-            const int64_t h = h0 + c;
-            for (int mu = 0; mu < dim; ++mu) {
-                const int pr = mu >> 1;
-                const uint32_t y0 = y0_s[c * dim + mu];
-                uint32_t um = 0;
-                for (int k = lane; k < n; k += 32) {
-                    double ua, ub;
-                    philox_pair(p.key, p.itn, h, (uint32_t)k, pr, ua, ub);
-                    um |= dy_mask(q, div_exact((double)y0 + ((mu & 1) ? ub : ua), p.st.dns[mu], p.st.rns[mu]));
-                }
-                um = __reduce_or_sync(0xffffffffu, um);
-                for (int i = 0; i < ndy; ++i) {
-                    const uint32_t bit = 1u << i;
-                    if (!(um & bit)) continue;
-                    double S = 0.0;
-                    for (int k = lane; k < n; k += 32) {
-                        double ua, ub;
-                        philox_pair(p.key, p.itn, h, (uint32_t)k, pr, ua, ub);
-                        if (dy_mask(q, div_exact((double)y0 + ((mu & 1) ? ub : ua), p.st.dns[mu], p.st.rns[mu])) & bit)
-                            S += q.w[row + k] * q.f[(row + k) * q.fstride];
-                    }
-                    S = warp_sum(S);
-                    const double mS = S / (double)n, thr = VB_EPSILON * fabs(mS);
-                    double sd = 0.0, qq = 0.0;
-                    for (int k = lane; k < n; k += 32) {
-                        double ua, ub;
-                        philox_pair(p.key, p.itn, h, (uint32_t)k, pr, ua, ub);
-                        const bool in = dy_mask(q, div_exact((double)y0 + ((mu & 1) ? ub : ua), p.st.dns[mu], p.st.rns[mu])) & bit;
-                        double d = (in ? q.w[row + k] * q.f[(row + k) * q.fstride] : 0.0) - mS;
-                        if (fabs(d) < thr) { qq += thr * thr; d = 0.0; } else qq += d * d;
-                        sd += d;
-                    }
-                    sd = warp_sum(sd);
-                    qq = warp_sum(qq);
-                    if (lane == 0) {
-                        accw[(mu * ndy + i) * 2] += S + sd;
-                        accw[(mu * ndy + i) * 2 + 1] += ((double)n * qq - sd * sd) / ((double)n - 1.0);
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < nacc; i += NT) {
-        double t = 0.0;
-        for (int w = 0; w < NW; ++w) t += dy_dyn[(size_t)w * nacc + i];
-        if (t != 0.0) atomicAdd(q.acc + i, t);
-    }
-}
-
-extern "C" int vb200_dy_profile(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, const double* f_dev,
-                                int fstride, const double* wgt_dev, int ndy, const double* yst_host, double* acc_dev, void* stream)
-{
-    if (!c || !f_dev || !wgt_dev || !yst_host || !acc_dev) return fail(-1, "vb200_dy_profile: null argument");
-    if (!c->have_map || !c->have_strata || !c->have_plan) return fail(-1, "vb200_dy_profile: map/strata/plan not set");
-    if (ndy < 1 || ndy > VB_DY_MAX) return fail(-1, "vb200_dy_profile: ndy=%d outside 1..%d", ndy, VB_DY_MAX);
-    if (fstride < 1) return fail(-1, "vb200_dy_profile: fstride < 1");
-    if (chunk_begin < 0 || chunk_end > c->nchunks || chunk_begin > chunk_end) return fail(-1, "vb200_dy_profile: bad chunk range");
-    CK(cudaSetDevice(c->device));
-    if (chunk_begin == chunk_end) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    EngineP p;
-    memset(&p, 0, sizeof p);
-    p.map = c->map; p.st = c->st; p.al = c->al; p.key = c->key;
-    p.itn = itn;
-    for (int d = 0; d < VB_MAXD; ++d) p.cstride[d] = c->cstride[d];
-    p.chunk_begin = chunk_begin; p.chunk_end = chunk_end;
-    p.chunk_off = (const int64_t*)c->chunk_off.p;
-    int rc = fetch_chunk_off(c, st);
-    if (rc) return rc;
-    p.row0 = c->chunk_off_host[(size_t)chunk_begin];
-    ItemsSel it;
-    rc = set_items(c, chunk_begin, chunk_end, it, st);
-    if (rc) return rc;
-    p.item_off = it.off[0]; p.item_begin = it.begin[0]; p.item_end = it.end[0];
-    CK(c->counter.ensure(sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), st));
-    p.work_counter = (unsigned long long*)c->counter.p;
-    DyP q;
-    memset(&q, 0, sizeof q);
-    q.ndy = ndy;
-    for (int i = 0; i <= ndy; ++i) q.yst[i] = yst_host[i];
-    q.f = f_dev; q.fstride = fstride; q.w = wgt_dev; q.acc = acc_dev;
-    const int dim = c->map.dim;
-    size_t smem = sizeof(double) * (size_t)(VB_ENT / 32) * dim * ndy * 2 + sizeof(uint32_t) * (size_t)VB_CH * dim;
-    CK(cudaFuncSetAttribute(k_dy_profile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t g = (int64_t)c->sm_count * 4, nitems = p.item_end - p.item_begin;
-    if (g > nitems) g = nitems;
-    k_dy_profile<<<(int)g, VB_ENT, smem, st>>>(p, q);
-    c->launches += 1;
-    CK(cudaGetLastError());
-    return 0;
-}
 
 extern "C" int64_t vb200_launch_count(vb200_ctx* c) { return c ? c->launches : 0; }
 
@@ -1400,76 +662,3 @@ extern "C" int vb200_fp64_peak(int device, int iters, double* tflops_out, double
     return 0;
 }
 
-// ---------------------------------------------------------------------------------------------
-// AdaptiveMap.adapt (pyx:467-594): the once-per-iteration host step, O(dim * ninc).
-// Smooth the per-increment training averages, damp with alpha, then move the nodes so every new
-// increment holds an equal share.  `work` (one row, carried from axis to axis exactly like the
-// reference's avg_f array) starts at 1.  Nodes the walk never reaches are NaN.
-// ---------------------------------------------------------------------------------------------
-namespace {
-const double kTiny = 1e-257;     // 10**(min_10_exp + 50), pyx:34
-
-void smooth_and_damp(std::vector<double>& w, std::vector<double>& tmp, int64_t n, double alpha)
-{
-    tmp[0] = fabs(7. * w[0] + w[1]) / 8.;
-    tmp[n - 1] = fabs(7. * w[n - 1] + w[n - 2]) / 8.;
-    double total = tmp[0] + tmp[n - 1];
-    for (int64_t i = 1; i < n - 1; ++i) {
-        tmp[i] = fabs(6. * w[i] + w[i - 1] + w[i + 1]) / 8.;
-        total += tmp[i];
-    }
-    for (int64_t i = 0; i < n; ++i) {
-        double a = total > 0 ? tmp[i] / total + kTiny : kTiny;
-        if (a > 0 && a <= 0.99999999) a = pow(-(1 - a) / log(a), alpha);
-        w[i] = a;
-    }
-}
-
-void regrid_axis(const double* g, int64_t n_old, const std::vector<double>& w, int64_t n_new, double* out)
-{
-    for (int64_t i = 0; i <= n_new; ++i) out[i] = NAN;
-    out[0] = g[0];
-    out[n_new] = g[n_old];
-    double share = 0.;
-    for (int64_t i = 0; i < n_old; ++i) share += w[i];
-    share /= (double)n_new;
-    int64_t j = -1;
-    double acc = 0.;
-    for (int64_t i = 1; i < n_new; ++i) {
-        while (acc < share) {
-            if (++j >= n_old) return;              // ran out of old increments
-            acc += w[j];
-        }
-        acc -= share;
-        out[i] = g[j + 1] - (acc / w[j]) * (g[j + 1] - g[j]);
-    }
-}
-}  // namespace
-
-extern "C" int vb200_map_adapt(const double* grid_host, const int64_t* ninc, int dim, int64_t gstride,
-                               const double* sum_f_host, const double* n_f_host, int64_t hstride, double alpha,
-                               const int64_t* new_ninc, double* new_grid_host, int64_t ngstride)
-{
-    if (!grid_host || !ninc || !new_ninc || !new_grid_host) return fail(-1, "vb200_map_adapt: null argument");
-    int64_t widest = 1;
-    for (int d = 0; d < dim; ++d) {
-        if (ninc[d] < 1 || new_ninc[d] < 1 || ninc[d] + 1 > gstride || new_ninc[d] + 1 > ngstride)
-            return fail(-1, "vb200_map_adapt: bad ninc on axis %d", d);
-        if (ninc[d] > widest) widest = ninc[d];
-    }
-    const bool have = sum_f_host && n_f_host;
-    std::vector<double> w((size_t)widest, 1.0), tmp((size_t)widest);
-    for (int d = 0; d < dim; ++d) {
-        const int64_t n_old = ninc[d];
-        if (alpha != 0 && n_old > 1) {
-            if (have)
-                for (int64_t i = 0; i < n_old; ++i) {
-                    double cnt = n_f_host[d * hstride + i];
-                    w[i] = cnt > 0 ? sum_f_host[d * hstride + i] / cnt : 0.;
-                }
-            if (alpha > 0) smooth_and_damp(w, tmp, n_old, alpha);
-        }
-        regrid_axis(grid_host + d * gstride, n_old, w, new_ninc[d], new_grid_host + d * ngstride);
-    }
-    return 0;
-}
