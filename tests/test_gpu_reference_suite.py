@@ -298,3 +298,43 @@ def test_restratify_integrator():
     assert 5 * dr.sdev > dr.mean
     assert integ2.nstrat[0] > 5 * integ2.nstrat[-1] and integ2.nstrat[1] > 5 * integ2.nstrat[-1]
     assert integ.neval == integ2.neval
+
+
+def test_save_extend(tmp_path):
+    """tests:479-530: the save / saveall keywords pickle the running result (and the integrator);
+    the unpickled pair continues the integration and extends the saved result"""
+    import pickle
+    vegas = _v()
+    from vegas_b200._gv import gv
+
+    @vegas.rbatchintegrand
+    def g(p):
+        return p[0] ** 2 * 1.5 / 8
+
+    @vegas.rbatchintegrand
+    def ga(p):
+        return [p[0] ** 2 * 1.5, 1 + p[0] ** 2 * 1.5]
+
+    @vegas.rbatchintegrand
+    def gd(p):
+        return dict(x2=p[0] ** 2 * 1.5, one=[[1 + p[0] ** 2 * 1.5]])
+    fn = str(tmp_path / 'test-save.pkl')
+    itg = vegas.Integrator(2 * [[-1, 1]], nitn=2, neval=100, seed=21)
+    for _g in [g, ga, gd]:
+        r = itg(_g, save=fn)
+        with open(fn, 'rb') as ifile:
+            r1 = pickle.load(ifile)
+        assert str(r1) == str(r) and r1.summary() == r.summary()
+        if _g is not g:
+            assert str(gv.evalcorr(r1.flat[:])) == str(gv.evalcorr(r.flat[:]))
+    for _g in [g, ga, gd]:
+        r = itg(_g, saveall=fn)
+        with open(fn, 'rb') as ifile:
+            r1, itg1 = pickle.load(ifile)
+        assert str(r1) == str(r) and r1.summary() == r.summary()
+        assert itg1.settings() == itg.settings()
+        np.testing.assert_allclose(list(itg1.sigf), list(itg.sigf))
+        new_r = itg1(_g)
+        r1.extend(new_r)
+        assert r.nitn + new_r.nitn == r1.nitn
+        assert r.sum_neval + new_r.sum_neval == r1.sum_neval
