@@ -80,6 +80,30 @@ def test_add_training_data_and_adapt_vs_oracle():
 
 
 # ----------------------------------------------------------------------------- RNG + allocation
+def test_adapt_to_samples():
+    """AdaptiveMap.adapt_to_samples (pyx:728-804; reference test tests:131-140): invmap, training and
+    adapt on the device/host pair reproduce the oracle's loop, and the map concentrates where the
+    samples are"""
+    vegas = _vegas()
+    O = _oracle()
+    rng = np.random.default_rng(5)
+    x = rng.normal(0, .1, (1000, 2))
+    Fx = np.exp(-np.sum(x ** 2, axis=1) * 100 / 2)
+    m1 = vegas.AdaptiveMap([[0, 2], [0, 1]])
+    m1.adapt_to_samples(x, Fx, nitn=5)
+    assert list(m1.ninc) == [1000, 1000]
+    mo = O.Map([[0., 2.], [0., 1.]])
+    mo.adapt(ninc=100)
+    for _ in range(5):
+        y, jac = mo.invmap(x)
+        mo.add_training_data(y, (jac * Fx) ** 2)
+        mo.adapt(alpha=1.0, ninc=100)
+    mo.adapt(ninc=1000)
+    np.testing.assert_allclose(m1.grid, mo.grid[:, :m1.grid.shape[1]], rtol=1e-10, atol=1e-14)
+    m1.adapt(ninc=2)
+    np.testing.assert_allclose(np.asarray(m1.grid), [[0., 0.071, 2.0], [0., 0.073, 1.]], rtol=0.4)
+
+
 def test_philox_uniforms_bit_exact():
     import torch
     vegas = _vegas()

@@ -288,12 +288,21 @@ class AdaptiveMap(object):
             fx = np.asarray(f, dtype=float)
         if fx.ndim != 1 or fx.shape[0] != x.shape[0]:
             raise ValueError('shape of x and f(x) mismatch: {} vs {}'.format(x.shape, fx.shape))
+        # work with as many increments as the samples can resolve (pyx:783-787), then return to the
+        # integrator's usual number (maxinc_axis = 1000, or the map's own if larger; pyx:803-804)
+        old_ninc = max(int(max(self.ninc)), 1000)
+        tmp_ninc = int(min(old_ninc, x.shape[0] / 10.))
+        if tmp_ninc < 2:
+            raise ValueError('not enough samples: {}'.format(x.shape[0]))
         y = np.empty(x.shape, float)
         jac = np.empty(x.shape[0], float)
+        self.adapt(ninc=tmp_ninc)
         for _ in range(nitn):
             self.invmap(x, y, jac)
             self.add_training_data(y, (jac * fx) ** 2)
-            self.adapt(alpha=alpha)
+            self.adapt(alpha=alpha, ninc=tmp_ninc)
+        if tmp_ninc != old_ninc:
+            self.adapt(ninc=old_ninc)
 
     def show_grid(self, ngrid=40, axes=None, shrink=False, plotter=None):
         raise NotImplementedError('AdaptiveMap.show_grid (matplotlib plotting) is outside the sampling path '
