@@ -338,3 +338,45 @@ def test_save_extend(tmp_path):
         r1.extend(new_r)
         assert r.nitn + new_r.nitn == r1.nitn
         assert r.sum_neval + new_r.sum_neval == r1.sum_neval
+
+
+def test_ravg_pickle():
+    """tests:438-477: results rebuilt with vegas.ravg (with every form of rescale), pickled, and passed
+    through gvar's dumps/loads print the same numbers, summaries and correlations"""
+    import pickle
+    vegas = _v()
+    from vegas_b200._gv import gv
+
+    @vegas.rbatchintegrand
+    def g(p):
+        return p[0] ** 2 * 1.5 / 8
+
+    @vegas.rbatchintegrand
+    def ga(p):
+        return [p[0] ** 2 * 1.5, 1 + p[0] ** 2 * 1.5]
+
+    @vegas.rbatchintegrand
+    def gd(p):
+        return dict(x2=p[0] ** 2 * 1.5, one=[[1 + p[0] ** 2 * 1.5]])
+    itg = vegas.Integrator(2 * [[-1, 1]], nitn=2, neval=100, seed=22)
+    for _g in [g, ga, gd]:
+        r = itg(_g)
+
+        def same(rx, r=r):
+            assert str(rx) == str(r) and rx.summary() == r.summary()
+            assert abs(rx.chi2 - r.chi2) < 1e-7 * max(1., abs(r.chi2))
+            if _g is not g:
+                assert str(gv.evalcorr(rx.flat[:])) == str(gv.evalcorr(r.flat[:]))
+        same(vegas.ravg(r.itn_results))
+        same(vegas.ravg(r.itn_results, rescale=r.itn_results[0]))
+        same(vegas.ravg(r.itn_results, rescale=gv.mean(r.itn_results[0])))
+        same(vegas.ravg(r))
+        d3 = pickle.dumps(r)
+        same(r)                                   # r unchanged by pickling
+        same(pickle.loads(d3))
+        d4 = gv.dumps(r)
+        same(r)
+        same(gv.loads(d4))
+        r5 = vegas.ravg(r, weighted=False)
+        assert str(r5) != str(r)
+        same(r5, gv.loads(gv.dumps(r5)))

@@ -435,3 +435,40 @@ def test_ravg_function():
     assert abs(d['a'].mean - 1.05) < 1e-12
     with pytest.raises(ValueError):
         vegas.ravg([])
+
+
+def test_ravg_and_ravgarray_weighted_unweighted():
+    """reference tests:238-312: error of weighted / unweighted running averages of scalars and of
+    correlated arrays, degrees of freedom, Q"""
+    import vegas_b200 as vegas
+    from vegas_b200._gv import gv
+    rng = np.random.default_rng(123)
+    N = 30
+    mean = rng.uniform(-10., 10.)
+    ravg = vegas.RAvg()
+    for i in range(N):
+        ravg.add(gv.gvar(rng.normal(mean, 1.), 1.))
+        ravg.add(gv.gvar(rng.normal(mean, 0.1), 0.1))
+    np.testing.assert_allclose(ravg.sdev, 1 / (N * (1. / 1. + 1. / 0.01)) ** 0.5)
+    assert abs(ravg.mean - mean) < 5 * ravg.sdev and ravg.Q > 1e-3 and ravg.dof == 2 * N - 1
+    ravg = vegas.RAvg(weighted=False)
+    for i in range(N):
+        ravg.add(gv.gvar(rng.normal(mean, 0.1), 0.1))
+    np.testing.assert_allclose(ravg.sdev, 0.1 / N ** 0.5)
+    assert abs(ravg.mean - mean) < 5 * ravg.sdev and ravg.Q > 1e-3 and ravg.dof == N - 1
+    # arrays with correlations
+    mean = rng.uniform(-10., 10., (2,))
+    cov = np.array([[1., 0.5], [0.5, 2.]])
+    ravg = vegas.RAvgArray((1, 2))
+    for i in range(N):
+        ravg.add([gv.gvar(rng.multivariate_normal(mean, cov), cov)])
+        ravg.add([gv.gvar(rng.multivariate_normal(mean, cov / 10.), cov / 10.)])
+    np.testing.assert_allclose(gv.evalcov(ravg.flat), cov / (10. + 1.) / N, rtol=1e-10)
+    for i in range(2):
+        assert abs(mean[i] - ravg[0, i].mean) < 5 * ravg[0, i].sdev
+    assert ravg.dof == 4 * N - 2 and ravg.Q > 1e-3
+    ravg = vegas.RAvgArray((1, 2), weighted=False)
+    for i in range(N):
+        ravg.add([gv.gvar(rng.multivariate_normal(mean, cov / 10.), cov / 10.)])
+    np.testing.assert_allclose(gv.evalcov(ravg.flat), cov / 10. / N, rtol=1e-10)
+    assert ravg.dof == 2 * N - 2 and ravg.Q > 1e-3
