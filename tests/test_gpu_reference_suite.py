@@ -380,3 +380,15 @@ def test_ravg_pickle():
         r5 = vegas.ravg(r, weighted=False)
         assert str(r5) != str(r)
         same(r5, gv.loads(gv.dumps(r5)))
+
+
+def test_volume():
+    """tests:774-789: constants integrate to the volume exactly (zero variance), scalar and array"""
+    vegas = _v()
+    r = vegas.Integrator([[-1, 1], [0, 4]], seed=23)(lambda x: 2.)
+    np.testing.assert_allclose(r.mean, 16, rtol=1e-6)
+    assert r.sdev < 1e-6
+    r = vegas.Integrator([[-1, 1], [0, 4]], seed=24)(lambda x: [-1., 2.])
+    np.testing.assert_allclose(r[0].mean, -8, rtol=5e-2)
+    np.testing.assert_allclose(r[1].mean, 16, rtol=5e-2)
+    assert r[0].sdev < 1e-6 and r[1].sdev < 1e-6

@@ -472,3 +472,34 @@ def test_ravg_and_ravgarray_weighted_unweighted():
         ravg.add([gv.gvar(rng.multivariate_normal(mean, cov / 10.), cov / 10.)])
     np.testing.assert_allclose(gv.evalcov(ravg.flat), cov / 10. / N, rtol=1e-10)
     assert ravg.dof == 2 * N - 2 and ravg.Q > 1e-3
+
+
+def test_max_mem():
+    """reference tests:1401-1408: max_mem is enforced at construction and when neval is raised in the call"""
+    import vegas_b200 as vegas
+    with pytest.raises(MemoryError):
+        vegas.Integrator(3 * [(0, 1)], max_mem=10)
+    I = vegas.Integrator(3 * [(0, 1)], max_mem=12012, minimize_mem=True)
+    with pytest.raises(MemoryError):
+        I(lambda x: np.prod(x), neval=1e4)
+
+
+def test_rescaling():
+    """reference tests:535-552: weighted averages of components that differ by 50 orders of magnitude
+    (rescaling by the last result keeps the covariance matrix invertible)"""
+    import vegas_b200 as vegas
+    from vegas_b200._gv import gv
+    rng = np.random.default_rng(3)
+    x = gv.gvar(1, 0.001)
+    a = vegas.RAvgArray((2,))
+    for i in range(3):
+        xx = x - x.mean + rng.normal(1, 0.001)
+        a.add([xx, 1e50 * xx])
+    assert str(a[0] * 1e50) == str(a[1])
+    assert str(gv.evalcorr(a).flat[:]) == str(np.ones(4, float))
+    d = vegas.RAvgDict(dict(a=1., b=2.))
+    for i in range(3):
+        xx = x - x.mean + rng.normal(1, 0.001)
+        d.add(dict(a=xx, b=1e50 * xx))
+    assert str(d['a'] * 1e50) == str(d['b'])
+    assert str(gv.evalcorr(d.buf).flat[:]) == str(np.ones(4, float))
