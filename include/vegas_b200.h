@@ -73,8 +73,10 @@ int  vb200_set_integrand(vb200_ctx* ctx, int id, const void* params, size_t nbyt
 
 /* vegas+ allocation (pyx:1657-1662, 1692-1706): neval_hcube[h] = min(max_nh, (int)(sigf[h]*neval_sigf)
  * + min_nh) for this rank's cubes (sigf_dev == NULL: uniform_neval everywhere).  Writes the
- * per-cube counts to neval_hcube_dev if non-NULL, builds the per-chunk offsets used by
- * vb200_sample / vb200_reduce, and returns stats_host = {sum, min, max, nchunks}.  Synchronous. */
+ * per-cube counts to neval_hcube_dev if non-NULL, records the samples per 256-cube chunk and into
+ * how many work items each chunk is cut (chunks the allocation piled more than 4096 samples onto are
+ * shared by several CTAs), and returns stats_host = {sum, min, max, nchunks}.  The row offsets used by
+ * vb200_sample / vb200_reduce / vb200_dy_profile are derived on their first use.  Synchronous. */
 int  vb200_plan(vb200_ctx* ctx, const double* sigf_dev, double neval_sigf, int64_t min_neval_hcube,
                 int64_t max_neval_hcube, int64_t uniform_neval, int32_t* neval_hcube_dev,
                 int64_t stats_host[4], void* stream);
