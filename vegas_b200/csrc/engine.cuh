@@ -5,14 +5,16 @@
 //   item   = the unit the persistent CTAs claim from an atomic counter (so they all finish together):
 //            a whole chunk, or -- when the vegas+ allocation piled more than VB_ITEM samples onto one
 //            chunk (k_plan) -- one of m runs of its cubes holding ~1/m of its samples each.
-//   tile   = maximal run of cubes inside a chunk whose samples fit the shared-memory staging
-//            buffer (cap samples).  Cubes larger than cap are staged through global scratch.
+//   tile   = run of cubes inside an item whose samples fit the shared-memory staging buffer (cap
+//            samples; an item is cut into the fewest tiles of about equal size).  Cubes larger
+//            than cap are staged through global scratch.
 //   phase 1 (thread per SAMPLE): Philox -> stratified y -> AdaptiveMap -> integrand -> w*f staged
 //            in shared memory; training-histogram adds are issued here because
 //            fdv2 = (J f dv_y)^2 does not depend on the cube sums.
-//   phase 2 (thread per CUBE, warp per cube above VB_WARP_CUBE samples): the reference's two-pass
-//            mean/variance with its EPSILON clamp, in the reference's summation order, from the
-//            staged values; sigf[h] update; per-thread fp64 accumulators.
+//   phase 2 (thread per CUBE up to VB_WARP_CUBE samples; larger cubes shared by all warps of the
+//            CTA): the reference's two-pass mean/variance with its EPSILON clamp -- for the small
+//            cubes in the reference's summation order -- from the staged values; sigf[h] update;
+//            per-thread fp64 accumulators.
 // Reference: Integrator._random_batch (_vegas.pyx:1692-1759) + Integrator.__call__
 // (_vegas.pyx:2136-2197).
 #pragma once
