@@ -40,6 +40,9 @@ CASES = {
 # vegas.restratify (src/vegas/__init__.py:1313-1592): adapt for nitn_adapt iterations, then restratify
 RESTRATIFY = {
     'plain': dict(limits=4 * [[0., 1.]], f='two_axes', kw=dict(neval=20000), nitn_adapt=3, nitn=2, ndy=5, opt={}, seed=31),
+    'six_dims': dict(limits=6 * [[0., 1.]], f='two_axes', kw=dict(neval=40000), nitn_adapt=3, nitn=1, ndy=8, opt={}, seed=33),
+    'uneven': dict(limits=4 * [[0., 1.]], f='two_axes', kw=dict(neval=20000, nstrat=[12, 2, 5, 3]), nitn_adapt=3, nitn=1, ndy=5,
+                   opt=dict(below_avg_nstrat=1), seed=34),
     'damped': dict(limits=4 * [[0., 1.]], f='two_axes', kw=dict(neval=20000), nitn_adapt=3, nitn=1, ndy=4,
                    opt=dict(gamma=0.5, below_avg_nstrat=2), seed=32),
 }
