@@ -33,6 +33,10 @@ CASES = {
     'gauss2_batches': dict(limits=2 * [[0., 1.]], f='gauss', kw=dict(neval=4000, min_neval_batch=700), nitn=3, seed=16),
     'gauss2_bigcubes': dict(limits=2 * [[0., 1.]], f='gauss', kw=dict(neval=3000, nstrat=[3, 2]), nitn=3, seed=17),
     'const1': dict(limits=[[0., 1.]], f='const', kw=dict(neval=100, alpha=0.0), nitn=3, seed=18),
+    'gauss3_clamp': dict(limits=3 * [[0., 1.]], f='gauss', kw=dict(neval=4000, max_neval_hcube=15), nitn=3, seed=20),
+    'gauss2_frac50': dict(limits=2 * [[0., 1.]], f='gauss', kw=dict(neval=3000, neval_frac=0.5), nitn=3, seed=21),
+    'gauss3_uniform': dict(limits=3 * [[0., 1.]], f='gauss', kw=dict(neval=5000, uniform_nstrat=True), nitn=3, seed=22),
+    'gauss2_maxinc': dict(limits=2 * [[0., 1.]], f='gauss', kw=dict(neval=3000, maxinc_axis=40, alpha=1.2), nitn=3, seed=23),
     'gauss3_noadapt': dict(limits=3 * [[0., 1.]], f='gauss', kw=dict(neval=2000, adapt=False), nitn=2, seed=19),
 }
 

@@ -153,6 +153,12 @@ def _cases():
     return {
         'poly2': (2 * [[0., 2.]], F.Poly(0.5, [1.0, 2.0], [2, 3]), dict(neval=4000)),
         'gauss4': ([[-1., 1.]] + 3 * [[0., 1.]], F.GaussMix([4 * [0.5]], 100., 1013.2118364296088), dict(neval=10000)),
+        # the settings of the extra golden fixtures (tests/golden/cases.py): allocation clamp, neval_frac,
+        # uniform_nstrat, few increments with strong damping
+        'gauss3_clamp': (3 * [[0., 1.]], F.GaussMix([3 * [0.5]], 100., 1.0), dict(neval=4000, max_neval_hcube=15)),
+        'gauss2_frac50': (2 * [[0., 1.]], F.GaussMix([2 * [0.5]], 100., 1.0), dict(neval=3000, neval_frac=0.5)),
+        'gauss3_uniform': (3 * [[0., 1.]], F.GaussMix([3 * [0.5]], 100., 1.0), dict(neval=5000, uniform_nstrat=True)),
+        'gauss2_maxinc': (2 * [[0., 1.]], F.GaussMix([2 * [0.5]], 100., 1.0), dict(neval=3000, maxinc_axis=40, alpha=1.2)),
         'ridge8': (8 * [[0., 1.]], F.Ridge(8, N=17), dict(neval=60000)),
         'ridge8_shifted': (8 * [[0., 1.]], F.Ridge(8, N=21, shifted=True), dict(neval=60000)),
         'ridge6_pad': (6 * [[0., 1.]], F.Ridge(6, N=9), dict(neval=20000)),
@@ -169,7 +175,7 @@ def _cases():
     }
 
 
-CASES = ['poly2', 'gauss4', 'ridge8', 'ridge8_shifted', 'ridge6_pad', 'ridge4_nomap', 'genz10_pp', 'genz10_osc', 'genz3_corner', 'peaks20',
+CASES = ['poly2', 'gauss4', 'gauss3_clamp', 'gauss2_frac50', 'gauss3_uniform', 'gauss2_maxinc', 'ridge8', 'ridge8_shifted', 'ridge6_pad', 'ridge4_nomap', 'genz10_pp', 'genz10_osc', 'genz3_corner', 'peaks20',
          'pathint10', 'pathint8_nocorr']
 
 
