@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VB200_ABI_VERSION 2
+#define VB200_ABI_VERSION 3
 #define VB200_MAXDIM 32          /* largest number of integration dimensions */
 #define VB200_CHUNK 256          /* hypercubes per work chunk; slab sizes are multiples of this */
 
@@ -92,12 +92,20 @@ int  vb200_iterate_fused(vb200_ctx* ctx, uint32_t itn, double beta, int flags, d
 /* Unfused path, stage 1 (pyx:1732-1759, Integrator.random_batch): samples of local chunks
  * [chunk_begin, chunk_end) in hypercube order.  x_dev[rows][dim] (or [dim][rows] if x_transposed),
  * wgt_dev[rows]; y_dev, jac1d_dev ([rows][dim]) and hcube_dev are optional (NULL).
- * bins_dev (optional, only with y/jac1d/hcube NULL): [rows][dim] uint16, the increment
+ * bins_dev (optional): [rows][dim] uint16, the increment
  * floor(y*ninc) each sample trains (pyx:460-462; 0xffff: y on the boundary, skipped) -- hand it to
  * vb200_reduce to spare it the Philox replay that otherwise re-derives y. */
 int  vb200_sample(vb200_ctx* ctx, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* x_dev,
                   double* wgt_dev, double* y_dev, double* jac1d_dev, int64_t* hcube_dev,
                   uint16_t* bins_dev, int x_transposed, void* stream);
+/* The same with the uniforms supplied by the caller, u_dev[rows][dim] in hypercube order, instead of
+ * the engine's Philox stream: the reference's documented injection hook Integrator.ran_array_generator
+ * (pyx:1081-1086, 1676-1680, 1732).  Pass bins_dev on to vb200_reduce: with injected uniforms the
+ * reduce kernel cannot re-derive y from the Philox counter. */
+int  vb200_sample_from_uniforms(vb200_ctx* ctx, uint32_t itn, int64_t chunk_begin, int64_t chunk_end,
+                                const double* u_dev, double* x_dev, double* wgt_dev, double* y_dev,
+                                double* jac1d_dev, int64_t* hcube_dev, uint16_t* bins_dev,
+                                int x_transposed, void* stream);
 /* Unfused path, stage 2 (pyx:2136-2197): reduce f_dev[rows][nf] of the same chunk range.
  * bins_dev: the array vb200_sample wrote for the same range and iteration, or NULL. */
 int  vb200_reduce(vb200_ctx* ctx, uint32_t itn, double beta, int flags, int64_t chunk_begin,

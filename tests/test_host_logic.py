@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.vb200_abi_version() == 2
+    assert L.vb200_abi_version() == 3
     _lib.load()
 
 

@@ -12,6 +12,7 @@ all-reduced (NCCL over NVLink); every rank then performs the same host steps and
 same result.
 """
 import os
+import warnings
 
 import numpy as np
 
@@ -25,6 +26,25 @@ from ._results import VegasResult
 def _dist():
     import torch.distributed as dist
     return dist
+
+
+# reference settings that are accepted for API compatibility but change nothing here; each is
+# reported once per process the first time it is given a non-default value
+_NO_EFFECT = {
+    'gpu_pad': 'batches are not padded: the engine sizes its own launches (pyx:2103-2106, 2130-2131)',
+    'minimize_mem': 'sigf always lives in HBM; there is no h5py spill file (pyx:1430-1446)',
+    'nproc': 'there is no multiprocessing pool: samples are generated and reduced on the GPU, Python '
+             'integrands are evaluated in this process (pyx:1291-1307, 2108-2123)',
+    'sync_ran': 'the Philox stream is a pure function of (seed, iteration, hypercube, sample); the seed is '
+                'broadcast from rank 0',
+}
+_warned = set()
+
+
+def _warn_no_effect(name):
+    if name not in _warned:
+        _warned.add(name)
+        warnings.warn('vegas_b200: %s has no effect -- %s' % (name, _NO_EFFECT[name]), stacklevel=3)
 
 
 class Integrator(object):
@@ -131,9 +151,17 @@ class Integrator(object):
             odict[k] = getattr(self, k)
         odict['nstrat'] = np.asarray(self.nstrat)
         odict['sigf'] = np.asarray(self.sigf)
+        # engine settings and the Philox iteration counter: a restored integrator continues the stream
+        # instead of replaying the uniforms of the iterations already done
+        for k in Integrator.engine_defaults:
+            if k != 'device':
+                odict[k] = getattr(self, k)
+        odict['_itn_counter'] = self._itn_counter
         return (Integrator, (self.map,), odict)
 
     def __setstate__(self, odict):
+        odict = dict(odict)
+        self._itn_counter = int(odict.pop('_itn_counter', 0))
         self.set(odict)
 
     # ------------------------------------------------------------------ sigf: host view of device state
@@ -230,12 +258,16 @@ class Integrator(object):
                 self.nproc = kargs['nproc'] if kargs['nproc'] is not None else os.cpu_count()
                 if self.nproc is None:
                     self.nproc = 1
+                if self.nproc != 1:
+                    _warn_no_effect('nproc')
             elif k in Integrator.defaults:
                 old_val[k] = getattr(self, k)
                 try:
                     setattr(self, k, kargs[k])
                 except Exception:
                     setattr(self, k, type(old_val[k])(kargs[k]))
+                if k in _NO_EFFECT and kargs[k] != Integrator.defaults[k]:
+                    _warn_no_effect(k)
             elif k in Integrator.engine_defaults:
                 old_val[k] = getattr(self, k)
                 setattr(self, k, kargs[k])
@@ -571,7 +603,7 @@ class Integrator(object):
             wgt = torch.empty(rows, dtype=torch.float64, device=ctx.device)
             y = torch.empty_like(x) if yield_y else None
             hc = torch.empty(rows, dtype=torch.int64, device=ctx.device) if yield_hcube else None
-            ctx.sample(itn, c0, c1, x, wgt, y=y, hcube=hc)
+            ctx.sample(itn, c0, c1, x, wgt, y=y, hcube=hc, u=self._injected_uniforms(torch, ctx, rows))
             self._launches += 1
             ans = (x,)
             if yield_y:
@@ -617,6 +649,19 @@ class Integrator(object):
                 samples.shape = (-1,) + self.xsample.shape
         return wgts, samples
 
+    def _injected_uniforms(self, torch, ctx, rows):
+        """uniforms of one batch from the user's ``ran_array_generator`` (pyx:1081-1086, 1676-1680, 1732:
+        called once per batch with the shape ``(rows, dim)``; rows are consumed in hypercube order), as a
+        device tensor -- or None when the engine's Philox stream is used"""
+        if self.ran_array_generator is None:
+            return None
+        if self._rank_world()[1] > 1:
+            raise NotImplementedError('ran_array_generator is not supported with the hypercube range sharded over GPUs')
+        u = np.ascontiguousarray(self.ran_array_generator((rows, self.dim)), dtype=float)
+        if u.shape != (rows, self.dim):
+            raise ValueError('ran_array_generator returned shape %s, expected %s' % (u.shape, (rows, self.dim)))
+        return torch.from_numpy(u).to(ctx.device)
+
     def _next_itn(self):
         self._itn_counter += 1
         return self._itn_counter & 0xFFFFFF
@@ -651,7 +696,7 @@ class Integrator(object):
         # built-in functors are compiled for up to 20 dimensions; above that their numpy twins run
         # through the callback path like any other lbatch integrand
         device_fcn = fcn if (isinstance(fcn, DeviceIntegrand) and self.fused and not self.uses_jac
-                             and self.dim <= _lib.MAX_FUSED_DIM) else None
+                             and self.dim <= _lib.MAX_FUSED_DIM and self.ran_array_generator is None) else None
         std = self._make_std_integrand(fcn)
         nf = std.size
         ctx, torch = self._engine()
@@ -716,6 +761,11 @@ class Integrator(object):
                 total, nmax = int(hi[-1]), int(hm[1])
             self._set_neval_stats(total, nmax, adaptive, reduced=True)
             if int(hm[0]) != 0:
+                # the reference raises before touching sigf (pyx:2133-2134); the kernels have already
+                # overwritten it, so put the stratification back into a consistent state first
+                if self._sigf_dev is not None:
+                    self._sigf_dev.fill_(1.)
+                    self.sum_sigf = self._sigf_len
                 raise ValueError('integrand evaluates to nan')
             acc_h = hf[:nacc]
             sum_f_h, n_f_h = hf[nacc:].reshape(self.dim, hs), hi[:self.dim * hs].reshape(self.dim, hs)
@@ -765,13 +815,17 @@ class Integrator(object):
             jac1d = torch.empty_like(x) if self.uses_jac else None
             # training bins travel from the sampler to the reduce kernel (2 bytes per axis) instead of
             # being re-derived there from the Philox counter
+            u = self._injected_uniforms(torch, ctx, rows)
+            train = flags & (_lib.TRAIN | (_lib.TRAIN_ERRORS if u is not None else 0))
+            want_bins = (self.train_bins and not self.uses_jac) or u is not None    # injected uniforms cannot be replayed
+            if u is not None and train and int(np.max(self.map.ninc)) > 0xffff:
+                raise ValueError('ran_array_generator needs maxinc_axis <= 65535')
             bins = (torch.empty((rows, self.dim), dtype=torch.int16, device=ctx.device)
-                    if (flags & _lib.TRAIN) and self.train_bins and not self.uses_jac
-                    and int(np.max(self.map.ninc)) <= 0xffff else None)
+                    if train and want_bins and int(np.max(self.map.ninc)) <= 0xffff else None)
             if self._timing is not None:
                 tev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 tev[0].record()
-            ctx.sample(pitn, c0, c1, x, wgt, jac1d=jac1d, bins=bins)
+            ctx.sample(pitn, c0, c1, x, wgt, jac1d=jac1d, bins=bins, u=u)
             if self._timing is not None:
                 tev[1].record()
             if on_device:

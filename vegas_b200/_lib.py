@@ -23,7 +23,7 @@ SYMBOLS = (
     'vb200_set_map', 'vb200_set_strata', 'vb200_set_integrand', 'vb200_plan', 'vb200_chunk_offsets',
     'vb200_iterate_fused', 'vb200_sample', 'vb200_reduce', 'vb200_map', 'vb200_invmap', 'vb200_jac1d',
     'vb200_add_training_data', 'vb200_map_adapt', 'vb200_uniforms', 'vb200_fp64_peak', 'vb200_launch_count',
-    'vb200_last_launch', 'vb200_eval_integrand', 'vb200_dy_profile',
+    'vb200_last_launch', 'vb200_eval_integrand', 'vb200_dy_profile', 'vb200_sample_from_uniforms',
 )
 
 
@@ -84,6 +84,7 @@ def load():
     L.vb200_chunk_offsets.argtypes = [vp, vp, i64]
     L.vb200_iterate_fused.argtypes = [vp, u32, f64, i32, vp, vp, vp, vp, i64, vp, vp]
     L.vb200_sample.argtypes = [vp, u32, i64, i64, vp, vp, vp, vp, vp, vp, i32, vp]
+    L.vb200_sample_from_uniforms.argtypes = [vp, u32, i64, i64, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     L.vb200_reduce.argtypes = [vp, u32, f64, i32, i64, i64, vp, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp]
     L.vb200_map.argtypes = [vp, vp, vp, vp, i64, vp]
     L.vb200_invmap.argtypes = [vp, vp, vp, vp, i64, vp]
@@ -100,7 +101,7 @@ def load():
     for name in SYMBOLS:
         if name not in ('vb200_last_error', 'vb200_destroy', 'vb200_launch_count'):
             getattr(L, name).restype = i32
-    if L.vb200_abi_version() != 2:
+    if L.vb200_abi_version() != 3:
         raise VegasB200Error('vegas_b200: ABI version mismatch')
     _lib = L
     return L
@@ -187,7 +188,12 @@ class Context(object):
         check(self.L.vb200_iterate_fused(self.h, itn, float(beta), flags, _ptr(sigf), _ptr(acc), _ptr(sum_f),
                                          _ptr(n_f), hstride, _ptr(status), _stream()))
 
-    def sample(self, itn, c0, c1, x, wgt, y=None, jac1d=None, hcube=None, transposed=False, bins=None):
+    def sample(self, itn, c0, c1, x, wgt, y=None, jac1d=None, hcube=None, transposed=False, bins=None, u=None):
+        """``u``: uniforms [rows, dim] supplied by the caller (``ran_array_generator``) instead of Philox"""
+        if u is not None:
+            check(self.L.vb200_sample_from_uniforms(self.h, itn, c0, c1, _ptr(u), _ptr(x), _ptr(wgt), _ptr(y),
+                                                    _ptr(jac1d), _ptr(hcube), _ptr(bins), int(transposed), _stream()))
+            return
         check(self.L.vb200_sample(self.h, itn, c0, c1, _ptr(x), _ptr(wgt), _ptr(y), _ptr(jac1d), _ptr(hcube),
                                   _ptr(bins), int(transposed), _stream()))
 

@@ -80,27 +80,39 @@ __device__ __forceinline__ double div_exact(double a, double b, double rb)
 // exp() for W independent arguments evaluated in lock-step, so that the W dependent chains
 // interleave in the FP64 pipe.  Table-driven: x * 128/ln2 = 128 k + j + f, |f| <= 1/2;
 // r = x - (128 k + j) ln2/128 (two-step Cody-Waite, |r| <= ln2/256);
-// exp(x) = 2^k * T[j] * P(r) with T[j] = 2^(j/128) correctly rounded (128 doubles staged in shared
-// memory by the kernel prologue: per-lane indices would serialise in the constant cache) and P a
-// degree-5 near-minimax polynomial (relative error 1.7e-20).  10 FP64 instructions (8 DFMA, 1 DADD,
-// 1 DMUL) against 16 in CUDA's exp(); error <= 1.5 ulp.  Constants: tools/exp_table.py.
+// exp(x) = 2^k * T[j] * P(r) with T[j] = 2^(j/128) correctly rounded and P a degree-5 near-minimax
+// polynomial (relative error 1.7e-20).  10 FP64 instructions (8 DFMA, 1 DADD, 1 DMUL) against 16 in
+// CUDA's exp(); error <= 1.5 ulp.  Constants: tools/exp_table.py.
 // |x| >= 708 (overflow / underflow / denormal results, inf, NaN) takes the library exp().
+//
+// The table lives in shared memory (per-lane indices would serialise in the constant cache) in
+// VB_EXP_COPIES interleaved copies: entry j of copy l at [j * COPIES + l], lane L reads copy
+// L % COPIES.  With 16 copies (16 KB) the 16 lanes of a half-warp -- the unit an 8-byte shared load
+// is served in -- always hit 16 different bank pairs, whatever their j: no bank conflicts (a single
+// copy: 62 % of the kernel's shared-memory wavefronts were conflict replays, ncu round 1).
 // ---------------------------------------------------------------------------------------------
 #include "exp_table.inc"
+#ifndef VB_EXP_COPIES
+#define VB_EXP_COPIES 16
+#endif
 __constant__ double vb_exp_c[6] = VB_EXP_POLY;
 __device__ const double vb_exp_tab_g[128] = VB_EXP_TABLE;
-static __shared__ double vb_exp_tab_s[128];
+static __shared__ double vb_exp_tab_s[128 * VB_EXP_COPIES];
 
-// called by all threads of a CTA (>= 128 of them) before the first vb_exp*(); needs a barrier after
+// called by all threads of a CTA before the first vb_exp*(); needs a barrier after
 __device__ __forceinline__ void vb_exp_init()
 {
-    if (threadIdx.x < 128) vb_exp_tab_s[threadIdx.x] = vb_exp_tab_g[threadIdx.x];
+    for (int i = threadIdx.x; i < 128 * VB_EXP_COPIES; i += blockDim.x) vb_exp_tab_s[i] = vb_exp_tab_g[i / VB_EXP_COPIES];
 }
 
 template <int W>
 __device__ __forceinline__ void vb_exp_n(const double (&x)[W], double (&e)[W])
 {
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: rounds to nearest integer
+    constexpr int CSHIFT = VB_EXP_COPIES == 16 ? 7 : (VB_EXP_COPIES == 1 ? 3 : -1);   // log2(8 * COPIES)
+    static_assert(CSHIFT > 0, "VB_EXP_COPIES must be 1 or 16");
+    // this lane's copy of the table, as a shared-state-space address
+    const unsigned tab = (unsigned)__cvta_generic_to_shared(vb_exp_tab_s) + (threadIdx.x & (VB_EXP_COPIES - 1)) * 8u;
     double t[W], r[W], p[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) t[j] = __fma_rn(x[j], VB_EXP_INVL, MAGIC);
@@ -117,15 +129,21 @@ __device__ __forceinline__ void vb_exp_n(const double (&x)[W], double (&e)[W])
 #pragma unroll
         for (int j = 0; j < W; ++j) p[j] = __fma_rn(p[j], r[j], vb_exp_c[i]);
     }
-    bool rare = false;
+    unsigned big = 0;
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        const int n = __double2loint(t[j]);             // 128 k + j (two's complement in the low word)
-        p[j] = __dmul_rn(p[j], vb_exp_tab_s[n & 127]);
-        e[j] = __hiloint2double(__double2hiint(p[j]) + ((n >> 7) << 20), __double2loint(p[j]));
-        rare |= (__double2hiint(x[j]) & 0x7fffffff) >= 0x40862000;
+        const unsigned n = (unsigned)__double2loint(t[j]);   // 128 k + j (two's complement in the low word)
+        // 2 integer instructions each for the table address and the exponent (mask, multiply-add)
+        unsigned sa, hi;
+        double T;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(n & 127u), "n"(1 << CSHIFT), "r"(tab));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(sa));
+        p[j] = __dmul_rn(p[j], T);
+        asm("mad.lo.u32 %0, %1, 8192, %2;" : "=r"(hi) : "r"(n & ~127u), "r"((unsigned)__double2hiint(p[j])));
+        e[j] = __hiloint2double((int)hi, __double2loint(p[j]));
+        big = max(big, (unsigned)__double2hiint(x[j]) & 0x7fffffffu);
     }
-    if (rare) {                                            // some |x| >= 708: one branch for all W
+    if (big >= 0x40862000u) {                              // some |x| >= 708: one branch for all W
 #pragma unroll
         for (int j = 0; j < W; ++j)
             if ((__double2hiint(x[j]) & 0x7fffffff) >= 0x40862000) e[j] = exp(x[j]);
@@ -157,7 +175,17 @@ struct StrataP {              // stratification of y-space + this rank's share o
     int nstrat[VB_MAXD];
     double dns[VB_MAXD];      // (double) nstrat[d]
     double rns[VB_MAXD];      // RN(1 / nstrat[d])
+    uint32_t nsm[VB_MAXD];    // ceil(2^32 / nstrat[d]) for 2 <= nstrat[d] < 32768, else 0 (see digit_div)
 };
+
+// v / nstrat[d] for v < nstrat[d] + 65536 / 2 (a stratum digit plus a carry of at most a chunk): a
+// multiply-high by the precomputed reciprocal (exact while v * nstrat < 2^32), 0 or 1 for large strata
+// counts, v itself for a single stratum -- instead of the ~24-instruction 32-bit division
+__device__ __forceinline__ uint32_t digit_div(const StrataP& st, int d, uint32_t v)
+{
+    const uint32_t ns = (uint32_t)st.nstrat[d], m = st.nsm[d];
+    return m ? __umulhi(v, m) : (ns == 1u ? v : (v >= ns ? 1u : 0u));
+}
 
 struct AllocP {               // vegas+ allocation of samples to hypercubes (_vegas.pyx:1692-1706)
     const double* sigf;       // [nlocal] or nullptr when not adaptive

@@ -100,6 +100,7 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     const int lim = ((CH == VB_CH ? (NF > 4 ? 48 : 32) : 64) * 1024) / (8 * NF);   // many components: fewer, larger tiles (measured)
     if (cap > lim) cap = lim;
     if (cap < 256) cap = 256;
+    if (cap > 32 * NT) cap = 32 * NT;                               // k_engine's start-bit words: one per thread
     cfg.cap = p.cap = cap;
     if (CH != VB_CH) {
         // super-chunks: only whole-range launches (the fused path); slabs must be whole chunks
@@ -115,7 +116,7 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     const int max_grid = (int)(nwork < 0x7fffffff ? nwork : 0x7fffffff);
     // pass 1: residency without the windows (registers / staging buffer decide)
     vb_plan_windows(p, CH, 0, false);
-    size_t smem0 = engine_smem_bytes(NF, cap, CH, dim, 0, Src::GRIDW, DIGB);
+    size_t smem0 = engine_layout(p, NF, cap, CH, dim, Src::GRIDW, DIGB);
     // The kernel's attributes and its residency per shared-memory size are asked of the driver once
     // per (device, instantiation): these queries run twice per iteration otherwise, a visible share
     // of the ~0.5 ms an iteration costs at the reference's everyday sizes (neval = 1e4).
@@ -156,7 +157,7 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     if (budget > cap_bins) budget = cap_bins;
     vb_plan_windows(p, CH, budget, Src::GRIDW);
     cfg.wtot = p.wtot;
-    cfg.smem = engine_smem_bytes(NF, cap, CH, dim, p.wtot, Src::GRIDW, DIGB);
+    cfg.smem = engine_layout(p, NF, cap, CH, dim, Src::GRIDW, DIGB);
     e = residency(cfg.smem, bps);
     if (e != cudaSuccess) return -(int)e - 1000;
     if (bps < 1) return -24;
@@ -185,6 +186,11 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     if (dim_ <= DD) { FusedSrc<F, DD> s_{fobj}; return launch_engine(p, s_, cfg, st); }
 #define VB_CASE_L(F, fobj, DD)                                                                 \
     if (cfg.light && dim_ <= DD) { FusedSrc<F, DD, true, (DD <= VB_LGW_MAXD)> s_{fobj}; return launch_engine(p, s_, cfg, st); }
+// exact dimension: no axis predication (FusedSrc::sample)
+#define VB_CASE_DX(F, fobj, DD)                                                                \
+    if (dim_ == DD) { FusedSrc<F, DD, false, false, true> s_{fobj}; return launch_engine(p, s_, cfg, st); }
+#define VB_CASE_LX(F, fobj, DD)                                                                \
+    if (cfg.light && dim_ == DD) { FusedSrc<F, DD, true, (DD <= VB_LGW_MAXD), true> s_{fobj}; return launch_engine(p, s_, cfg, st); }
 
 
 // ---------------------------------------------------------------------------------------------

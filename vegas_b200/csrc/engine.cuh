@@ -58,6 +58,12 @@ struct EngineP {
     int woff[VB_MAXD];         // offset of axis d's window in the shared arrays
     int wtot;                  // total window bins (0: no shared histogram)
     double dni[VB_MAXD];       // (double) map.ninc[d]
+    // layout of the kernel's dynamic shared memory (engine_layout, filled by the launcher): byte offsets
+    // of the arrays, and per axis the element index of its window's first bin in the fp64 sums
+    // (vb_smem as double[]), the u32 counts (vb_smem as unsigned[]) and the grid nodes (double[])
+    int win_all;               // every axis has a window (GRIDW sources then read the map's grid from shared memory)
+    int o_ex, o_hsum, o_gw, o_dvn, o_n, o_hcnt, o_y0;
+    int hs_idx[VB_MAXD], hc_idx[VB_MAXD], gw_idx[VB_MAXD];
     // unfused path
     const double* fbuf;        // [rows][nf]
     const double* wbuf;        // [rows]
@@ -102,9 +108,6 @@ static __shared__ double vb_scratch_s[32];  // per-lane scratch slots (see hist_
 struct HistW {
     double* sum;        // [wtot]
     unsigned* cnt;      // [wtot]
-    int gw_off;         // index in vb_smem of the windows' grid nodes: axis d at gw_off + woff[d] + d .. + wcap[d] (GRIDW sources)
-    uint32_t sum_sa;    // sum / cnt as shared-state-space addresses for the explicit .shared atomics
-    uint32_t cnt_sa;
 };
 
 #define VB_NO_SLOT 0xffffffffu
@@ -115,146 +118,37 @@ __device__ __forceinline__ void hist_global(const EngineP& p, int d, int bin, do
     atomicAdd(p.n_f + (size_t)d * p.hstride + bin, 1ull);
 }
 
-// count the sample in its window slot and return the shared address of the slot's fp64 sum, or
-// VB_NO_SLOT after sending it to the global histogram (bin outside the window) / skipping it (bin < 0)
-__device__ __forceinline__ uint32_t hist_slot(const EngineP& p, const HistW& H, int d, int bin, double v)
-{
-    if (bin < 0) return VB_NO_SLOT;
-    const unsigned r = (unsigned)(bin - vb_wlo_s[d]);
-    if (r < (unsigned)p.wcap[d]) {
-        const unsigned i = (unsigned)p.woff[d] + r;
-        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(H.cnt_sa + 4u * i) : "memory");
-        return H.sum_sa + 8u * i;
-    }
-    hist_global(p, d, bin, v);
-    return VB_NO_SLOT;
-}
-
-// same for the code FusedSrc::sample keeps per axis: r < 2^31: slot r of the axis' window;
-// VB_NO_SLOT: no training point (y on the boundary); else 2^31 | bin for the global histogram
-__device__ __forceinline__ uint32_t hist_slot_code(const EngineP& p, const HistW& H, int d, unsigned code, double v)
+// One training point on axis d.  `code` < 2^31: slot of the axis' window; VB_NO_SLOT: none (y on the
+// boundary); else 2^31 | bin: outside the window, straight to the global histogram.
+// There is no native shared-memory fp64 add; on an address the compiler can prove to be shared
+// (vb_smem itself, not a pointer carried in a struct) atomicAdd(double) becomes the 4-instruction loop
+// LDS.64 / DADD / ATOMS.CAST.SPIN.64 / BRA -- measured (tools/atomics_bench.cu, B200, 8 axes per
+// sample, 125-bin windows): 6.8 SM-cycles per sample against 10.4 for round 1's hand-written PTX
+// loop running 4 compare-and-swaps in lock-step, 17.9 for a 128-bit CAS on {sum, count}, 15.2 with
+// __match_any_sync pre-aggregation, and a floor of 4.2 for the same updates without atomicity.
+__device__ __forceinline__ void hist_add_code(const EngineP& p, int d, unsigned code, double v)
 {
     if (code < 0x80000000u) {
-        const unsigned i = (unsigned)p.woff[d] + code;
-        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(H.cnt_sa + 4u * i) : "memory");
-        return H.sum_sa + 8u * i;
-    }
-    if (code != VB_NO_SLOT) hist_global(p, d, (int)(code & 0x7fffffffu), v);
-    return VB_NO_SLOT;
+        atomicAdd((unsigned*)vb_smem + (p.hc_idx[d] + (int)code), 1u);
+        atomicAdd(vb_smem + (p.hs_idx[d] + (int)code), v);
+    } else if (code != VB_NO_SLOT) hist_global(p, d, (int)(code & 0x7fffffffu), v);
 }
 
-__device__ __forceinline__ unsigned long long lds_u64(uint32_t sa)
+// training code of bin `bin` (>= 0) on axis d
+__device__ __forceinline__ unsigned hist_code(const EngineP& p, int d, int bin)
 {
-    unsigned long long v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(sa) : "memory");
-    return v;
+    const unsigned r = (unsigned)(bin - vb_wlo_s[d]);
+    return r < (unsigned)p.wcap[d] ? r : (0x80000000u | (unsigned)bin);
 }
 
-__device__ __forceinline__ unsigned long long cas_shared_u64(uint32_t sa, unsigned long long cmp, unsigned long long val)
+__device__ __forceinline__ void hist_add(const EngineP& p, const HistW&, int d, int bin, double v)
 {
-    unsigned long long old;
-    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(sa), "l"(cmp), "l"(val) : "memory");
-    return old;
+    if (bin >= 0) hist_add_code(p, d, hist_code(p, d, bin), v);
 }
 
-// fp64 adds of v to 4 shared slots (VB_NO_SLOT: none) in lock-step.  There is no native
-// shared-memory fp64 add, so each is a compare-and-swap loop; running the 4 loops side by side
-// overlaps their round trips.  Written in PTX: the C++ form of this loop compiles to ~4x the
-// instructions (64-bit compares through 32-bit halves, register shuffling, v rematerialised).
-// Lanes leave the loop at different times: callers re-converge with __syncwarp().
-__device__ __forceinline__ void hist_sum_slots4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, double v)
-{
-    // No predicated ld/atom here (ptxas answers those with ~0.5 KB of spills in this kernel): a slot
-    // that is finished, or was never there, is redirected to this lane's scratch slot, where the
-    // compare-and-swap is harmless.
-    const uint32_t dummy = (uint32_t)__cvta_generic_to_shared(vb_scratch_s) + 8u * (threadIdx.x & 31);
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p0, p1, p2, p3, t0, t1, t2, t3, q;\n\t"
-        ".reg .b32 a0, a1, a2, a3;\n\t"
-        ".reg .b64 o0, o1, o2, o3, s0, s1, s2, s3;\n\t"
-        ".reg .f64 f0, f1, f2, f3;\n\t"
-        "setp.ne.u32 p0, %0, 0xffffffff;\n\t"
-        "setp.ne.u32 p1, %1, 0xffffffff;\n\t"
-        "setp.ne.u32 p2, %2, 0xffffffff;\n\t"
-        "setp.ne.u32 p3, %3, 0xffffffff;\n\t"
-        "selp.b32 a0, %0, %5, p0;\n\t"
-        "selp.b32 a1, %1, %5, p1;\n\t"
-        "selp.b32 a2, %2, %5, p2;\n\t"
-        "selp.b32 a3, %3, %5, p3;\n\t"
-        "ld.shared.b64 o0, [a0];\n\t"
-        "ld.shared.b64 o1, [a1];\n\t"
-        "ld.shared.b64 o2, [a2];\n\t"
-        "ld.shared.b64 o3, [a3];\n"
-        "VB_CAS_LOOP:\n\t"
-        "mov.b64 f0, o0;\n\t"
-        "mov.b64 f1, o1;\n\t"
-        "mov.b64 f2, o2;\n\t"
-        "mov.b64 f3, o3;\n\t"
-        "add.rn.f64 f0, f0, %4;\n\t"
-        "add.rn.f64 f1, f1, %4;\n\t"
-        "add.rn.f64 f2, f2, %4;\n\t"
-        "add.rn.f64 f3, f3, %4;\n\t"
-        "mov.b64 s0, f0;\n\t"
-        "mov.b64 s1, f1;\n\t"
-        "mov.b64 s2, f2;\n\t"
-        "mov.b64 s3, f3;\n\t"
-        "atom.shared.cas.b64 s0, [a0], o0, s0;\n\t"
-        "atom.shared.cas.b64 s1, [a1], o1, s1;\n\t"
-        "atom.shared.cas.b64 s2, [a2], o2, s2;\n\t"
-        "atom.shared.cas.b64 s3, [a3], o3, s3;\n\t"
-        "setp.ne.b64 t0, s0, o0;\n\t"
-        "setp.ne.b64 t1, s1, o1;\n\t"
-        "setp.ne.b64 t2, s2, o2;\n\t"
-        "setp.ne.b64 t3, s3, o3;\n\t"
-        "and.pred p0, p0, t0;\n\t"
-        "and.pred p1, p1, t1;\n\t"
-        "and.pred p2, p2, t2;\n\t"
-        "and.pred p3, p3, t3;\n\t"
-        "mov.b64 o0, s0;\n\t"
-        "mov.b64 o1, s1;\n\t"
-        "mov.b64 o2, s2;\n\t"
-        "mov.b64 o3, s3;\n\t"
-        "selp.b32 a0, a0, %5, p0;\n\t"
-        "selp.b32 a1, a1, %5, p1;\n\t"
-        "selp.b32 a2, a2, %5, p2;\n\t"
-        "selp.b32 a3, a3, %5, p3;\n\t"
-        "or.pred q, p0, p1;\n\t"
-        "or.pred q, q, p2;\n\t"
-        "or.pred q, q, p3;\n\t"
-        "@q bra VB_CAS_LOOP;\n\t"
-        "}\n"
-        :: "r"(a0), "r"(a1), "r"(a2), "r"(a3), "d"(v), "r"(dummy) : "memory");
-}
-
-// one slot: plain loop
-__device__ __forceinline__ void hist_sum_slot1(uint32_t sa, double v)
-{
-    unsigned long long old = lds_u64(sa), seen;
-    for (;;) {
-        seen = cas_shared_u64(sa, old, (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)old), v)));
-        if (seen == old) break;
-        old = seen;
-    }
-}
-
-// one training point; callers sit in a warp-uniform loop that ends with __syncwarp()
-__device__ __forceinline__ void hist_add(const EngineP& p, const HistW& H, int d, int bin, double v)
-{
-    const uint32_t sa = hist_slot(p, H, d, bin, v);
-    if (sa != VB_NO_SLOT) hist_sum_slot1(sa, v);
-}
-
-// the same through the compiler's own atomics: for call sites in divergent code (phase 2)
 __device__ __forceinline__ void hist_add_divergent(const EngineP& p, const HistW& H, int d, int bin, double v)
 {
-    if (bin >= 0) {
-        const unsigned r = (unsigned)(bin - vb_wlo_s[d]);
-        if (r < (unsigned)p.wcap[d]) {
-            atomicAdd(H.sum + p.woff[d] + r, v);
-            atomicAdd(H.cnt + p.woff[d] + r, 1u);
-        } else hist_global(p, d, bin, v);
-    }
+    hist_add(p, H, d, bin, v);
 }
 
 // add the windows of the axes with need[d] != 0 (all axes when need == nullptr) to the global
@@ -281,8 +175,14 @@ __device__ __forceinline__ void hist_flush(const EngineP& p, const HistW& H, con
 // training point of a whole cube (adapt_to_errors, _vegas.pyx:2187-2193): y of its LAST sample
 template <class dig_t>
 static __device__ __noinline__ void train_cube(const EngineP& p, const HistW& H, int64_t h, uint32_t klast,
-                                               const dig_t* y0, double v)
+                                               const dig_t* y0, double v, int64_t row_last)
 {
+    if (p.bins != nullptr) {        // unfused path with the sampler's bins (uniforms injected by the caller: no Philox replay)
+        const uint16_t* b = p.bins + row_last * p.map.dim;
+        for (int d = 0; d < p.map.dim; ++d)
+            if (b[d] != 0xffffu) hist_add_divergent(p, H, d, (int)b[d], fabs(v));
+        return;
+    }
     for (int pr = 0; 2 * pr < p.map.dim; ++pr) {
         double ua, ub;
         philox_pair(p.key, p.itn, h, klast, pr, ua, ub);
@@ -310,7 +210,19 @@ static __device__ __noinline__ void train_cube(const EngineP& p, const HistW& H,
 #ifndef VB_LCH
 #define VB_LCH 512
 #endif
-template <class F, int D, bool LIGHT = false, bool GW = LIGHT>
+// what a source needs to know about one sample: its cube (n samples, dvn = dv_y / n, global index h,
+// stratum digits y0), its index k in the cube and its row in the batch buffers (unfused path)
+template <class dig_t>
+struct SampleRef {
+    int n;
+    double dvn;
+    int64_t h;
+    uint32_t k;
+    int64_t row;
+    const dig_t* y0;
+};
+
+template <class F, int D, bool LIGHT = false, bool GW = LIGHT, bool EXACT = false>
 struct FusedSrc {
     static constexpr int NF = F::NF;
     static constexpr int NT = LIGHT ? VB_LNT : VB_ENT;             // threads per CTA
@@ -318,19 +230,26 @@ struct FusedSrc {
 #ifndef VB_LMINB
 #define VB_LMINB 2
 #endif
-    static constexpr int MINB = LIGHT ? VB_LMINB : (F::NF == 1 ? 3 : 2);   // resident CTAs per SM the register budget is set for
+#ifndef VB_HMINB
+#define VB_HMINB 3
+#endif
+    static constexpr int MINB = LIGHT ? VB_LMINB : (F::NF == 1 ? VB_HMINB : 2);   // resident CTAs per SM the register budget is set for
     static constexpr bool GRIDW = GW;                              // grid windows in shared memory (light, D <= 10)
+    static constexpr bool USES_EXP = true;
     // stratum digits of a cube (light: narrow, to leave the shared memory to the histogram windows;
     // the host falls back to the heavy geometry when a digit does not fit)
     typedef typename std::conditional<LIGHT, typename std::conditional<(D > 10), uint8_t, uint16_t>::type, uint32_t>::type dig_t;
     F f;
-    __device__ __forceinline__ void sample(const EngineP& p, const HistW& H, int n, int64_t h, uint32_t k,
-                                           int64_t /*row*/, const dig_t* y0, double (&wf)[NF]) const
+    // Philox -> stratified y -> AdaptiveMap (pyx:310-360) for all axes of one sample.  WIN: every axis
+    // reads its grid nodes from the shared-memory window (callers guarantee the bins are inside);
+    // otherwise from global memory.  Returns false when WIN met a bin outside its window (the
+    // results are then meaningless and the caller redoes the sample with WIN = false).
+    template <bool WIN>
+    __device__ __forceinline__ bool map_axes(const EngineP& p, const SampleRef<dig_t>& r, int dim, double (&x)[D],
+                                             unsigned (&code)[D], double& jac_out) const
     {
-        const int dim = p.map.dim;
-        double x[D];
-        unsigned code[D];     // training slot of axis d, see hist_slot_code
         double jac = 1.0;
+        bool ok = true;
         // Above 10 dimensions the axis loops stay rolled (x[], code[] then live in local memory, which
         // is lane-interleaved and L1-resident): fully unrolled, the 20-D kernels were bound by
         // instruction fetch (ncu: stall_no_instruction on top).
@@ -340,59 +259,72 @@ struct FusedSrc {
         constexpr int UNR = D > 10 ? VB_ROLL_UNR : (D + 1) / 2;
 #pragma unroll UNR
         for (int pr = 0; pr < (D + 1) / 2; ++pr) {
-            if (2 * pr < dim) {
+            if (EXACT || 2 * pr < dim) {
                 double u[2];
-                philox_pair(p.key, p.itn, h, k, pr, u[0], u[1]);
+                philox_pair(p.key, p.itn, r.h, r.k, pr, u[0], u[1]);
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int d = 2 * pr + e;
-                    if (d < D && d < dim) {
+                    if (d < D && (EXACT || d < dim)) {
                         const int ni = p.map.ninc[d];
-                        const double y = div_exact((double)y0[d] + u[e], p.st.dns[d], p.st.rns[d]);
+                        const double yy = (double)r.y0[d] + u[e];
+                        const double y = div_exact(yy, p.st.dns[d], p.st.rns[d]);
                         const double t = __dmul_rn(y, p.dni[d]);
                         const int iy = __double2int_rd(t);
                         const int ic = min(iy, ni - 1);
-                        const unsigned r = (unsigned)(ic - vb_wlo_s[d]);
-                        const bool inw = r < (unsigned)p.wcap[d];
-                        const double* gp = p.map.grid + (size_t)d * p.map.gstride + ic;
+                        const unsigned w = (unsigned)(ic - vb_wlo_s[d]);
+                        const bool inw = w < (unsigned)p.wcap[d];
                         double g0, g1;
-                        if (GRIDW && __builtin_expect(inw, 1)) {
-                            const double* w = vb_smem + (H.gw_off + p.woff[d] + d) + r;
-                            g0 = w[0]; g1 = w[1];
+                        if (WIN) {
+                            const double* gw = vb_smem + (p.gw_idx[d] + (int)(inw ? w : 0u));
+                            g0 = gw[0]; g1 = gw[1];
+                            ok &= inw;
                         } else {
+                            const double* gp = p.map.grid + ((size_t)d * p.map.gstride + ic);
                             g0 = __ldg(gp); g1 = __ldg(gp + 1);
                         }
                         const double inc = g1 - g0;
                         const double xin = __dadd_rn(g0, __dmul_rn(inc, __dsub_rn(t, (double)iy)));   // no FMA: bit-identical to pyx:354
                         x[d] = iy < ni ? xin : g1;                                                     // pyx:357-359
                         jac *= inc * p.dni[d];
-                        code[d] = !(y > 0.0 && y < 1.0) ? VB_NO_SLOT : (inw ? r : (0x80000000u | (unsigned)ic));   // pyx:460
+                        // pyx:460 trains only 0 < y < 1.  y > 0 <=> y0 + u > 0; y < 1 <=> iy < ninc (y <= 1 - 2^-53
+                        // cannot round up to ninc in y * ninc, and y == 1 gives iy == ninc exactly)
+                        code[d] = (iy < ni && yy > 0.0) ? ((WIN || inw) ? w : (0x80000000u | (unsigned)ic)) : VB_NO_SLOT;
                     }
                 }
             }
         }
+        jac_out = jac;
+        return ok;
+    }
+
+    // EXACT: the run-time dimension equals D, so no axis is predicated and the compiler is free to
+    // interleave the D independent axis chains (Philox pair -> y -> bin -> x)
+    __device__ __forceinline__ void sample(const EngineP& p, const SampleRef<dig_t>& r, double (&wf)[NF]) const
+    {
+        const int dim = EXACT ? D : p.map.dim;
+        double x[D];
+        unsigned code[D];     // training slot of axis d, see hist_add_code
+        double jac;
+        // GRIDW sources: windows first; a sample with a bin outside them (an axis without a window, a
+        // chunk wrapping around an axis) is redone from global memory -- a real, rarely taken branch
+        // instead of predicated global-memory code on every axis
+        if (!GRIDW || !p.win_all || !__builtin_expect(map_axes<true>(p, r, dim, x, code, jac), 1))
+            map_axes<false>(p, r, dim, x, code, jac);
         double fx[NF];
         f(x, dim, fx);
-        double wgt = jac * (p.dv_y / (double)n);
+        const double wgt = jac * r.dvn;
         bool bad = false;
 #pragma unroll
         for (int s = 0; s < NF; ++s) { wf[s] = wgt * fx[s]; bad |= isnan(fx[s]); }
         if (bad) p.status[0] = 1;
         if (p.flags & VBF_TRAIN) {
-            double a = wf[0] * (double)n;
-            double fdv2 = __dmul_rn(a, a);
-            // 4 axes at a time: their CAS loops run side by side
-            constexpr int UNRH = D > 10 ? 1 : (D + 3) / 4;
+            const double a = wf[0] * (double)r.n;
+            const double fdv2 = __dmul_rn(a, a);
+            constexpr int UNRH = D > 10 ? 1 : D;
 #pragma unroll UNRH
-            for (int d0 = 0; d0 < D; d0 += 4) {
-                if (d0 < dim) {
-                    uint32_t sa[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        sa[j] = (d0 + j < D && d0 + j < dim) ? hist_slot_code(p, H, d0 + j, code[d0 + j < D ? d0 + j : 0], fdv2) : VB_NO_SLOT;
-                    hist_sum_slots4(sa[0], sa[1], sa[2], sa[3], fdv2);
-                }
-            }
+            for (int d = 0; d < D; ++d)
+                if (EXACT || d < dim) hist_add_code(p, d, code[d], fdv2);
         }
     }
 };
@@ -411,72 +343,39 @@ struct BufferSrc {
 #endif
     static constexpr int MINB = NF_ <= 4 ? VB_BUF_MINB_LO : VB_BUF_MINB_HI;
     static constexpr bool GRIDW = false;
+    static constexpr bool USES_EXP = false;
     typedef uint32_t dig_t;
-    __device__ __forceinline__ void sample(const EngineP& p, const HistW& H, int n, int64_t h, uint32_t k,
-                                           int64_t row, const dig_t* y0, double (&wf)[NF]) const
+    __device__ __forceinline__ void sample(const EngineP& p, const SampleRef<dig_t>& r, double (&wf)[NF]) const
     {
-        // every global load of the row is issued up front (the kernel is latency-bound on them): the
-        // training bins as packed pairs when the row is 4-byte aligned (even dim) and fits 8 words
-        const int dim_ = p.map.dim;
-        const bool packed = (p.flags & VBF_TRAIN) && p.bins != nullptr && !(dim_ & 1) && dim_ <= 16;
-        uint32_t bw[8];
-        if (packed) {
-            const uint32_t* b32 = (const uint32_t*)(p.bins + row * dim_);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bw[j] = 2 * j < dim_ ? __ldg(b32 + j) : 0xffffffffu;
-        }
+        const int dim = p.map.dim;
+        const int64_t row = r.row;
         const double wgt = p.wbuf[row];
-        // the training adds only need component 0: they come first, while little else is live
-        // (with 7 components in registers the CAS loops below were compiled around ~1.6 KB of spills)
+        double fx[NF];
+#pragma unroll
+        for (int s = 0; s < NF; ++s) fx[s] = p.fbuf[row * NF + s];
         if (p.flags & VBF_TRAIN) {
-            double a = (wgt * p.fbuf[row * NF]) * (double)n;
-            double fdv2 = a * a;
-            if (packed) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (4 * g < dim_) {
-                        uint32_t sa[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int d = 4 * g + j;
-                            const unsigned bv = (j & 1) ? (bw[2 * g + (j >> 1)] >> 16) : (bw[2 * g + (j >> 1)] & 0xffffu);
-                            sa[j] = hist_slot(p, H, d < dim_ ? d : 0, (d >= dim_ || bv == 0xffffu) ? -1 : (int)bv, fdv2);
-                        }
-                        if ((sa[0] & sa[1] & sa[2] & sa[3]) != VB_NO_SLOT)         // some bin of the group is in a window
-                            hist_sum_slots4(sa[0], sa[1], sa[2], sa[3], fdv2);
-                    }
-                }
-            } else if (p.bins != nullptr) {
-                // bins from the sampler; 4 axes at a time so their CAS loops run side by side
-                const int dim = p.map.dim;
+            const double a = (wgt * fx[0]) * (double)r.n;
+            const double fdv2 = a * a;
+            if (p.bins != nullptr) {
                 const uint16_t* b = p.bins + row * dim;
-#pragma unroll 1
-                for (int d0 = 0; d0 < dim; d0 += 4) {
-                    uint32_t sa[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int d = d0 + j;
-                        const unsigned bv = d < dim ? b[d] : 0xffffu;
-                        sa[j] = hist_slot(p, H, d < dim ? d : 0, bv == 0xffffu ? -1 : (int)bv, fdv2);
-                    }
-                    hist_sum_slots4(sa[0], sa[1], sa[2], sa[3], fdv2);
+                for (int d = 0; d < dim; ++d) {
+                    const unsigned bv = b[d];
+                    if (bv != 0xffffu) hist_add_code(p, d, hist_code(p, d, (int)bv), fdv2);
                 }
-            } else
-            for (int pr = 0; 2 * pr < p.map.dim; ++pr) {
-                double ua, ub;
-                philox_pair(p.key, p.itn, h, k, pr, ua, ub);
-                hist_add(p, H, 2 * pr, bin_of(p, 2 * pr, y0[2 * pr], ua, nullptr), fdv2);
-                if (2 * pr + 1 < p.map.dim)
-                    hist_add(p, H, 2 * pr + 1, bin_of(p, 2 * pr + 1, y0[2 * pr + 1], ub, nullptr), fdv2);
+            } else {
+                HistW H{};
+                for (int pr = 0; 2 * pr < dim; ++pr) {
+                    double ua, ub;
+                    philox_pair(p.key, p.itn, r.h, r.k, pr, ua, ub);
+                    hist_add(p, H, 2 * pr, bin_of(p, 2 * pr, r.y0[2 * pr], ua, nullptr), fdv2);
+                    if (2 * pr + 1 < dim)
+                        hist_add(p, H, 2 * pr + 1, bin_of(p, 2 * pr + 1, r.y0[2 * pr + 1], ub, nullptr), fdv2);
+                }
             }
         }
         bool bad = false;
 #pragma unroll
-        for (int s = 0; s < NF; ++s) {
-            double fx = p.fbuf[row * NF + s];
-            bad |= isnan(fx);
-            wf[s] = wgt * fx;
-        }
+        for (int s = 0; s < NF; ++s) { bad |= isnan(fx[s]); wf[s] = wgt * fx[s]; }
         if (bad) p.status[0] = 1;
     }
 };
@@ -546,14 +445,14 @@ __device__ __forceinline__ double cube_finish(CubeAcc<NF>& A, int n, const doubl
 
 template <int NF, class dig_t>
 __device__ __forceinline__ void cube_epilogue(const EngineP& p, const HistW& H, CubeAcc<NF>& A, double sigf2,
-                                              int64_t lh, int64_t h, int n, const dig_t* y0)
+                                              int64_t lh, int64_t h, int n, const dig_t* y0, int64_t row_last)
 {
     if (p.flags & VBF_UPDATE_SIGF) {
         double sg = pow(sigf2, p.beta_half);
         p.sigf_out[lh] = sg;
         A.sum_sigf += sg;
     }
-    if (p.flags & VBF_TRAIN_ERRORS) train_cube(p, H, h, (uint32_t)(n - 1), y0, sigf2);
+    if (p.flags & VBF_TRAIN_ERRORS) train_cube(p, H, h, (uint32_t)(n - 1), y0, sigf2, row_last);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -579,7 +478,7 @@ __device__ __forceinline__ void locate_item(const EngineP& p, long long g, long 
 // at local cube lh0 / global cube h0.  Returns the chunk's sample total; ends with a barrier.
 template <int NT, int CH, class dig_t>
 __device__ __forceinline__ long long chunk_setup(const EngineP& p, int64_t lh0, int64_t h0, long long* ex_s, int* n_s,
-                                                 dig_t* y0_s, uint32_t* base_s, long long* scan_s)
+                                                 dig_t* y0_s, uint32_t* base_s, long long* scan_s, double* dvn_s = nullptr)
 {
     constexpr int CPT = CH / NT;                                  // cubes per thread
     static_assert(CH % NT == 0, "chunk must be a multiple of the CTA size");
@@ -600,11 +499,12 @@ __device__ __forceinline__ long long chunk_setup(const EngineP& p, int64_t lh0, 
         const int c = tid * CPT + i;
         ex_s[c] = ex;
         n_s[c] = n_mine[i];
+        if (dvn_s) dvn_s[c] = p.dv_y / (double)n_mine[i];           // weight factor of the cube's samples (pyx:1746-1752), once per cube
         ex += n_mine[i];
         uint32_t carry = (uint32_t)c;                              // digits of cube h0+c: base digits plus c, with carries
         for (int d = 0; d < dim; ++d) {
-            uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
-            uint32_t qd = v / ns;
+            const uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
+            const uint32_t qd = digit_div(p.st, d, v);                // v < ns + CH
             y0_s[c * dim + d] = (dig_t)(v - qd * ns);
             carry = qd;
         }
@@ -632,16 +532,26 @@ __device__ __forceinline__ void item_cubes(const long long* ex_s, int ch, long l
 // ---------------------------------------------------------------------------------------------
 // the engine kernel
 // ---------------------------------------------------------------------------------------------
-// dynamic shared memory of k_engine<Src> (the host sizes the launch with the same function)
-__host__ __device__ inline size_t engine_smem_bytes(int nf, int cap, int ch, int dim, int wtot, bool gridw, int digbytes)
+// dynamic shared memory of k_engine<Src>: the launcher lays it out (byte offsets and the per-axis
+// window indices in p) and sizes the launch with the same function
+__host__ inline size_t engine_layout(EngineP& p, int nf, int cap, int ch, int dim, bool gridw, int digbytes)
 {
-    size_t b = sizeof(double) * (size_t)nf * cap            // wf_s   staged w*f
-             + sizeof(long long) * (size_t)(ch + 1)         // ex_s   exclusive scan of the cubes' sample counts
-             + sizeof(double) * (size_t)wtot                // H.sum
-             + (gridw ? sizeof(double) * (size_t)(wtot + dim) : 0)   // grid nodes of the windows
-             + sizeof(int) * (size_t)ch                     // n_s
-             + sizeof(unsigned) * (size_t)wtot              // H.cnt
-             + (size_t)digbytes * ch * dim;                 // y0_s   stratum digits
+    const int wtot = p.wtot;
+    size_t b = sizeof(double) * (size_t)nf * cap;           // wf_s   staged w*f
+    p.o_ex = (int)b;    b += sizeof(long long) * (size_t)(ch + 1);      // ex_s   exclusive scan of the cubes' sample counts
+    p.o_hsum = (int)b;  b += sizeof(double) * (size_t)wtot;             // H.sum
+    p.o_gw = (int)b;    b += gridw ? sizeof(double) * (size_t)(wtot + dim) : 0;   // grid nodes of the windows
+    p.o_dvn = (int)b;   b += sizeof(double) * (size_t)ch;               // dvn_s  dv_y / n per cube
+    p.o_n = (int)b;     b += sizeof(int) * (size_t)ch;                  // n_s
+    p.o_hcnt = (int)b;  b += sizeof(unsigned) * (size_t)wtot;           // H.cnt
+    p.o_y0 = (int)b;    b += (size_t)digbytes * ch * dim;               // y0_s   stratum digits
+    for (int d = 0; d < VB_MAXD; ++d) {
+        p.hs_idx[d] = p.o_hsum / 8 + p.woff[d];
+        p.hc_idx[d] = p.o_hcnt / 4 + p.woff[d];
+        p.gw_idx[d] = p.o_gw / 8 + p.woff[d] + d;
+    }
+    p.win_all = wtot > 0;
+    for (int d = 0; d < dim; ++d) if (p.wcap[d] == 0) p.win_all = 0;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -655,14 +565,16 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     constexpr int CH = Src::CH;
     constexpr int NW = NT / 32;
     static_assert(CH % VB_CH == 0, "chunk must be a multiple of the ABI chunk");
+    char* const smem_b = (char*)vb_smem;
     double* wf_s = vb_smem;                                       // [NF][cap]
-    long long* ex_s = (long long*)(wf_s + (size_t)NF * p.cap);    // [CH + 1]
+    long long* ex_s = (long long*)(smem_b + p.o_ex);              // [CH + 1]
     HistW H;
-    H.sum = (double*)(ex_s + CH + 1);                             // [wtot]
-    double* gw_s = H.sum + p.wtot;                                // [wtot + dim] (GRIDW)
-    int* n_s = (int*)(gw_s + (Src::GRIDW ? p.wtot + p.map.dim : 0));   // [CH]
-    H.cnt = (unsigned*)(n_s + CH);                                // [wtot]
-    dig_t* y0_s = (dig_t*)(H.cnt + p.wtot);                       // [CH][dim]
+    H.sum = (double*)(smem_b + p.o_hsum);                         // [wtot]
+    double* gw_s = (double*)(smem_b + p.o_gw);                    // [wtot + dim] (GRIDW)
+    double* dvn_s = (double*)(smem_b + p.o_dvn);                  // [CH]
+    int* n_s = (int*)(smem_b + p.o_n);                            // [CH]
+    H.cnt = (unsigned*)(smem_b + p.o_hcnt);                       // [wtot]
+    dig_t* y0_s = (dig_t*)(smem_b + p.o_y0);                      // [CH][dim]
     __shared__ long long scan_s[NW];
     __shared__ double red_s[NW];
     __shared__ uint32_t base_s[VB_MAXD];
@@ -671,6 +583,10 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     __shared__ int nlarge_s, large_s[VB_LARGE_MAX];
     __shared__ double p1_s[VB_LARGE_G * NW * NF], p2_s[VB_LARGE_G * NW * (NF + NV)];
     __shared__ int wnew_s[VB_MAXD], wneed_s[VB_MAXD];
+    // cube of a sample without searching: bit j of sb_s[w] is set when a cube starts at sample 32 w + j
+    // of the tile, pc_s[w] counts the starts before word w
+    __shared__ uint32_t sb_s[NT + 1];
+    __shared__ int pc_s[NT + 1];
     int* const wlo_s = vb_wlo_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -678,11 +594,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     const bool correlate = (p.flags & VBF_CORRELATE) != 0;
     CubeAcc<NF> A;
     A.clear();
-    H.gw_off = (int)(gw_s - vb_smem);
-    H.sum_sa = (uint32_t)__cvta_generic_to_shared(H.sum);
-    H.cnt_sa = (uint32_t)__cvta_generic_to_shared(H.cnt);
-    static_assert(NT >= 128, "vb_exp_init needs 128 threads");
-    vb_exp_init();                                                // visible after the first barrier of the chunk loop
+    if (Src::USES_EXP) vb_exp_init();                             // visible after the first barrier of the chunk loop
     for (int i = tid; i < p.wtot; i += NT) { H.sum[i] = 0.0; H.cnt[i] = 0u; }
     if (tid < VB_MAXD) wlo_s[tid] = -0x40000000;                   // no window yet: the first chunk installs them
     long long since_flush = 0;                                    // samples added since the last full flush
@@ -745,7 +657,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
             }
             if (force) since_flush = 0;
         }
-        const long long total = chunk_setup<NT, CH, dig_t>(p, lh0, h0, ex_s, n_s, y0_s, base_s, scan_s);
+        const long long total = chunk_setup<NT, CH, dig_t>(p, lh0, h0, ex_s, n_s, y0_s, base_s, scan_s, dvn_s);
         const int64_t chunk_row = p.chunk_off ? p.chunk_off[lc] - p.row0 : 0;
 
         int c0, cend;
@@ -783,7 +695,8 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
                     const int k = kb + tid;
                     if (k < n) {
                         double w[NF];
-                        src.sample(p, H, n, h, (uint32_t)k, chunk_row + base + k, y0_s + c0 * dim, w);
+                        const SampleRef<dig_t> sr{n, dvn_s[c0], h, (uint32_t)k, chunk_row + base + k, y0_s + c0 * dim};
+                        src.sample(p, sr, w);
 #pragma unroll
                         for (int s = 0; s < NF; ++s) { gs[s * p.scratch_stride + k] = w[s]; S[s] += w[s]; }
                     }
@@ -840,7 +753,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
                         for (int v = 0; v < NV; ++v) q[v] += p2_s[w * (NF + NV) + NF + v];
                     }
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
-                    cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c0, h, n, y0_s + c0 * dim);
+                    cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c0, h, n, y0_s + c0 * dim, chunk_row + base + n - 1);
                 }
                 __syncthreads();
                 c0 += 1;
@@ -848,26 +761,40 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
             }
             const int Tt = (int)(ex_s[c1] - base);
 
+            // ---- which cube does sample i of the tile belong to?  Start bits + their running count per
+            // 32-sample word replace a per-sample binary search of the prefix array (round 1: 8 % of the
+            // light kernel's instructions).  Cubes with samples are contiguous (only the padding cubes
+            // after the rank's last one are empty), so the j-th start is cube c0 + j.
+            const int nword = (Tt + 31) >> 5;                      // <= NT (launcher: cap <= 32 NT)
+            if (tid <= nword) sb_s[tid] = 0u;
+            __syncthreads();
+            for (int c = c0 + tid; c < c1; c += NT)
+                if (n_s[c] > 0) {
+                    const int o = (int)(ex_s[c] - base);
+                    atomicOr(&sb_s[o >> 5], 1u << (o & 31));
+                }
+            __syncthreads();
+            {
+                long long tot_unused;
+                const long long ex = block_exscan<NT>((long long)(tid < nword ? __popc(sb_s[tid]) : 0), scan_s, &tot_unused);
+                if (tid < nword) pc_s[tid] = (int)ex;
+            }
+            __syncthreads();
+
             // ---- phase 1: one thread per sample
             for (int ib = 0; ib < Tt; ib += NT) {                  // warp-uniform trip count
                 const int i = ib + tid;
                 if (i < Tt) {
-                    // offsets inside a tile fit 32 bits: search on the low words of the prefix array
-                    const unsigned* exl = (const unsigned*)ex_s;
-                    const unsigned bl = (unsigned)base;
-                    int lo = c0, hi = c1;
-                    while (hi - lo > 1) {
-                        int mid = (lo + hi) >> 1;
-                        if ((int)(exl[2 * mid] - bl) <= i) lo = mid; else hi = mid;
-                    }
-                    const int c = lo;
-                    const int k = i - (int)(exl[2 * c] - bl);
+                    const uint32_t m = sb_s[i >> 5] & (0xffffffffu >> (31 - lane));    // starts at or before this lane (word = the warp's 32 samples)
+                    const int c = c0 + pc_s[i >> 5] + __popc(m) - 1;
+                    const int k = i - (int)((unsigned)ex_s[c] - (unsigned)base);       // offsets inside a tile fit 32 bits
                     double w[NF];
-                    src.sample(p, H, n_s[c], h0 + c, (uint32_t)k, chunk_row + base + i, y0_s + c * dim, w);
+                    const SampleRef<dig_t> sr{n_s[c], dvn_s[c], h0 + c, (uint32_t)k, chunk_row + base + i, y0_s + c * dim};
+                    src.sample(p, sr, w);
 #pragma unroll
                     for (int s = 0; s < NF; ++s) wf_s[(size_t)s * p.cap + i] = w[s];
                 }
-                __syncwarp();                                      // lanes leave the histogram CAS loops at different times
+                __syncwarp();                                      // lanes leave the histogram loops at different times
             }
             if (tid == 0) nlarge_s = 0;
             __syncthreads();
@@ -894,7 +821,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
                         pass2_sample<NF>(w, m, correlate, sd, q);
                     }
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
-                    cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
+                    cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim, chunk_row + ex_s[c] + n - 1);
                 } else if (n > VB_WARP_CUBE) {
                     large_s[atomicAdd(&nlarge_s, 1)] = c;          // at most cap / (VB_WARP_CUBE + 1) per tile
                 }
@@ -969,7 +896,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
                         for (int v = 0; v < NV; ++v) q[v] += p2_s[(tid * NW + w) * (NF + NV) + NF + v];
                     }
                     double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
-                    cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim);
+                    cube_epilogue<NF, dig_t>(p, H, A, sigf2, lh0 + c, h0 + c, n, y0_s + c * dim, chunk_row + ex_s[c] + n - 1);
                 }
                 __syncthreads();
             }

@@ -8,7 +8,7 @@ int launch_fused_gaussmix_heavy(const EngineP& p, const void* functor, LaunchCfg
 int launch_fused_ridge_heavy(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st);
 int launch_fused_genz_heavy(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st);
 
-#define LIGHT_(F, f) VB_CASE_L(F, f, 4) VB_CASE_L(F, f, 8) VB_CASE_L(F, f, 10) VB_CASE_L(F, f, 16) VB_CASE_L(F, f, 20)
+#define LIGHT_(F, f) VB_CASE_LX(F, f, 4) VB_CASE_LX(F, f, 8) VB_CASE_LX(F, f, 10) VB_CASE_L(F, f, 4) VB_CASE_L(F, f, 8) VB_CASE_L(F, f, 10) VB_CASE_L(F, f, 16) VB_CASE_L(F, f, 20)
 
 template <class F>
 static int light_or(const EngineP& p, const F& f, LaunchCfg& cfg, cudaStream_t st)

@@ -71,15 +71,56 @@ struct FGaussMix {
 //         the argument is -(a V) - (sqrt(aD)(xbar-c))^2, two FP64 instructions per term instead of
 //         2D+1.  xs[k] = sqrt(a D) x0[k] is precomputed on the host.
 // W terms are evaluated in lock-step so their exp() chains interleave in the FP64 pipe.
+//
+// The centres travel in the kernel parameters (cpar: constant bank) when there are at most
+// VB_RIDGE_PMAX of them: the term loop is warp-uniform, so each centre reaches the FP64
+// instructions as a uniform-register operand -- no per-thread loads, no registers holding the next
+// group's centres (round 1 read them through __ldg with an 8-deep register prefetch: 32 registers
+// and 4e9 L1 sectors per launch).  cpar is padded with copies of the last centre up to a multiple of
+// the lock-step width; the padded terms are evaluated and dropped.  Longer ridges read x0 / xs
+// from global memory.
 #ifndef VB_RIDGE_W
 #define VB_RIDGE_W 8
 #endif
+#define VB_RIDGE_PMAX 1024
 struct FRidge {
     static constexpr int NF = 1;
     const double* x0;   // [n] device
     const double* xs;   // [n] device: sqrt(a*dim) * x0[k]   (mode 1)
     int n, mode;
     double a, norm;
+    double scale;       // norm / n
+    int npar;           // n when the centres are in cpar, else 0
+    double cpar[VB_RIDGE_PMAX + 8];   // x0 (mode 0) / xs (mode 1), padded
+
+    // terms [0, n) from the parameter bank, W at a time
+    template <int D, bool CHECK, int W>
+    __device__ __forceinline__ double sum_axis_order_par(const double (&x)[D], int dim) const
+    {
+        double s0 = 0.0, s1 = 0.0;
+        for (int k = 0; k < npar; k += W) {
+            double q[W], e[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) q[j] = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                if (!CHECK || d < dim) {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) { double t = x[d] - cpar[k + j]; q[j] = fma(t, t, q[j]); }
+                }
+#pragma unroll
+            for (int j = 0; j < W; ++j) q[j] *= -a;
+            vb_exp_n<W>(q, e);
+            if (k + W <= npar) {
+#pragma unroll
+                for (int j = 0; j < W; j += 2) { s0 += e[j]; s1 += e[j + 1]; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < W; ++j) if (k + j < npar) s0 += e[j];
+            }
+        }
+        return s0 + s1;
+    }
 
     template <int D, bool CHECK>
     __device__ __forceinline__ double sum_axis_order(const double (&x)[D], int dim) const
@@ -136,16 +177,27 @@ struct FRidge {
         double s[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) s[j] = 0.0;
-        int k = 0;
-        for (; k + W <= n; k += W) {
-            double q[W], e[W];
+        if (npar > 0) {
+            for (int k = 0; k < npar; k += W) {
+                double q[W], e[W];
 #pragma unroll
-            for (int j = 0; j < W; ++j) { double t = xb - __ldg(xs + k + j); q[j] = fma(-t, t, mV); }
-            vb_exp_n<W>(q, e);
+                for (int j = 0; j < W; ++j) { double t = xb - cpar[k + j]; q[j] = fma(-t, t, mV); }
+                vb_exp_n<W>(q, e);
 #pragma unroll
-            for (int j = 0; j < W; ++j) s[j] += e[j];
+                for (int j = 0; j < W; ++j) if (k + W <= npar || k + j < npar) s[j] += e[j];
+            }
+        } else {
+            int k = 0;
+            for (; k + W <= n; k += W) {
+                double q[W], e[W];
+#pragma unroll
+                for (int j = 0; j < W; ++j) { double t = xb - __ldg(xs + k + j); q[j] = fma(-t, t, mV); }
+                vb_exp_n<W>(q, e);
+#pragma unroll
+                for (int j = 0; j < W; ++j) s[j] += e[j];
+            }
+            for (; k < n; ++k) { double t = xb - __ldg(xs + k); s[0] += vb_exp(fma(-t, t, mV)); }
         }
-        for (; k < n; ++k) { double t = xb - __ldg(xs + k); s[0] += vb_exp(fma(-t, t, mV)); }
         double tot = s[0];
 #pragma unroll
         for (int j = 1; j < W; ++j) tot += s[j];
@@ -157,21 +209,29 @@ struct FRidge {
     {
         double tot;
         if (mode == 1) tot = sum_shifted<D>(x, dim);
+        else if (npar > 0) tot = dim == D ? sum_axis_order_par<D, false, VB_RIDGE_W>(x, dim) : sum_axis_order_par<D, true, VB_RIDGE_W>(x, dim);
         else if (dim == D) tot = sum_axis_order<D, false>(x, dim);
         else tot = sum_axis_order<D, true>(x, dim);
-        f[0] = tot / (double)n * norm;
+        f[0] = tot * scale;
     }
 };
 
-// The same ridge (mode 0) for the light engine geometry, whose one big CTA per SM leaves 128
-// registers per thread: terms 4 at a time in lock-step (FRidge's 8-wide loop needs ~160), then the
-// scalar tail.  Used for short ridges (n <= 128), where the sampler around the integrand is a large
-// part of the work.
+// The same ridge (mode 0) for the light engine geometry, whose CTAs leave ~128 registers per thread:
+// terms 4 at a time in lock-step (FRidge's 8-wide loop needs more).  Used for short ridges, where the
+// sampler around the integrand is a large part of the work.
+#ifndef VB_RIDGE_LW
+#define VB_RIDGE_LW 4
+#endif
 struct FRidgeLight : FRidge {
     template <int D>
     __device__ __forceinline__ void operator()(const double (&x)[D], int dim, double (&f)[1]) const
     {
-        constexpr int W = 4;
+        constexpr int W = VB_RIDGE_LW;
+        if (npar > 0) {
+            const double tot = dim == D ? sum_axis_order_par<D, false, W>(x, dim) : sum_axis_order_par<D, true, W>(x, dim);
+            f[0] = tot * scale;
+            return;
+        }
         double s0 = 0.0, s1 = 0.0;
         int k = 0;
         for (; k + W <= n; k += W) {
@@ -187,8 +247,8 @@ struct FRidgeLight : FRidge {
 #pragma unroll
             for (int j = 0; j < W; ++j) q[j] *= -a;
             vb_exp_n<W>(q, e);
-            s0 += e[0] + e[2];
-            s1 += e[1] + e[3];
+#pragma unroll
+            for (int j = 0; j < W; j += 2) { s0 += e[j]; s1 += e[j + 1]; }
         }
         for (; k < n; ++k) {
             const double c = __ldg(x0 + k);
@@ -198,7 +258,7 @@ struct FRidgeLight : FRidge {
                 if (d < dim) { double t = x[d] - c; q = fma(t, t, q); }
             s0 += vb_exp(-a * q);
         }
-        f[0] = (s0 + s1) / (double)n * norm;
+        f[0] = (s0 + s1) * scale;
     }
 };
 

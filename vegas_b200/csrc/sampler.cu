@@ -11,7 +11,18 @@ struct SampleOut {
     int64_t rows;      // rows in this batch (for the transposed layout)
     double* u;         // raw uniforms (testing)
     uint16_t* bins;    // [rows][dim] training bin of every sample (0xffff: none) for vb200_reduce
+    const double* u_in; // [rows][dim] uniforms supplied by the caller (Integrator.ran_array_generator, pyx:1676-1680, 1732) instead of Philox
 };
+
+// the two uniforms of axis pair pr of a sample: the caller's (row-major u_in) or Philox
+__device__ __forceinline__ void uniforms_of(const EngineP& p, const SampleOut& o, int64_t h, uint32_t k, int64_t row, int pr, int dim,
+                                            double& ua, double& ub)
+{
+    if (o.u_in) {
+        ua = o.u_in[row * dim + 2 * pr];
+        ub = 2 * pr + 1 < dim ? o.u_in[row * dim + 2 * pr + 1] : 0.0;
+    } else philox_pair(p.key, p.itn, h, k, pr, ua, ub);
+}
 
 __global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ EngineP p, const __grid_constant__ SampleOut o)
 {
@@ -55,12 +66,16 @@ __global__ void __launch_bounds__(VB_NT) k_sample(const __grid_constant__ Engine
             double jac = 1.0;
             for (int pr = 0; 2 * pr < dim; ++pr) {
                 double u[2];
-                philox_pair(p.key, p.itn, h, k, pr, u[0], u[1]);
+                uniforms_of(p, o, h, k, row, pr, dim, u[0], u[1]);
                 for (int e = 0; e < 2; ++e) {
                     const int d = 2 * pr + e;
                     if (d >= dim) break;
                     if (o.u) { o.u[row * dim + d] = u[e]; continue; }
                     double y = div_exact((double)y0[d] + u[e], p.st.dns[d], p.st.rns[d]);
+                    if (o.bins) {
+                        const int ib = min(__double2int_rd(__dmul_rn(y, (double)p.map.ninc[d])), p.map.ninc[d] - 1);
+                        o.bins[row * dim + d] = (y > 0.0 && y < 1.0) ? (uint16_t)ib : (uint16_t)0xffff;   // pyx:460
+                    }
                     const int ni = p.map.ninc[d];
                     const double* g = p.map.grid + (size_t)d * p.map.gstride;
                     double t = __dmul_rn(y, (double)ni);
@@ -151,7 +166,7 @@ __global__ void __launch_bounds__(VB_NT) k_sample_x(const __grid_constant__ Engi
                 for (int pr = 0; pr < (D + 1) / 2; ++pr) {
                     if (2 * pr < dim) {
                         double u[2];
-                        philox_pair(p.key, p.itn, h, k, pr, u[0], u[1]);
+                        uniforms_of(p, o, h, k, row, pr, dim, u[0], u[1]);
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int d = 2 * pr + e;
@@ -259,7 +274,6 @@ static int sample_common(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_
                           : launch_sample_x<VB_MAXD>(p, o, (int)g, (cudaStream_t)stream);
         if (e) return fail(-2, "sample: launch set-up failed (%s)", cudaGetErrorString((cudaError_t)(-(e + 1000))));
     } else {
-        if (o.bins) return fail(-1, "sample: training bins are only written together with x and wgt alone");
         size_t smem = sizeof(uint32_t) * (size_t)VB_CH * c->map.dim;
         k_sample<<<(int)g, VB_NT, smem, (cudaStream_t)stream>>>(p, o);
     }
@@ -268,8 +282,8 @@ static int sample_common(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_
     return 0;
 }
 
-extern "C" int vb200_sample(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* x_dev, double* wgt_dev,
-                            double* y_dev, double* jac1d_dev, int64_t* hcube_dev, uint16_t* bins_dev, int x_transposed, void* stream)
+static int sample_entry(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, const double* u_dev, double* x_dev, double* wgt_dev,
+                        double* y_dev, double* jac1d_dev, int64_t* hcube_dev, uint16_t* bins_dev, int x_transposed, void* stream)
 {
     if (!c || !x_dev || !wgt_dev) return fail(-1, "vb200_sample: null argument");
     if (bins_dev)
@@ -279,7 +293,22 @@ extern "C" int vb200_sample(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int
     memset(&o, 0, sizeof o);
     o.x = x_dev; o.wgt = wgt_dev; o.y = y_dev; o.jac1d = jac1d_dev; o.hcube = hcube_dev; o.x_transposed = x_transposed;
     o.bins = bins_dev;
+    o.u_in = u_dev;
     return sample_common(c, itn, chunk_begin, chunk_end, o, stream);
+}
+
+extern "C" int vb200_sample(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* x_dev, double* wgt_dev,
+                            double* y_dev, double* jac1d_dev, int64_t* hcube_dev, uint16_t* bins_dev, int x_transposed, void* stream)
+{
+    return sample_entry(c, itn, chunk_begin, chunk_end, nullptr, x_dev, wgt_dev, y_dev, jac1d_dev, hcube_dev, bins_dev, x_transposed, stream);
+}
+
+extern "C" int vb200_sample_from_uniforms(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, const double* u_dev,
+                                          double* x_dev, double* wgt_dev, double* y_dev, double* jac1d_dev, int64_t* hcube_dev,
+                                          uint16_t* bins_dev, int x_transposed, void* stream)
+{
+    if (!u_dev) return fail(-1, "vb200_sample_from_uniforms: u_dev is NULL");
+    return sample_entry(c, itn, chunk_begin, chunk_end, u_dev, x_dev, wgt_dev, y_dev, jac1d_dev, hcube_dev, bins_dev, x_transposed, stream);
 }
 
 extern "C" int vb200_uniforms(vb200_ctx* c, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* u_dev, void* stream)

@@ -106,6 +106,7 @@ extern "C" int vb200_set_strata(vb200_ctx* c, const int64_t* nstrat, int dim, in
         s.nstrat[d] = d < dim ? (int)nstrat[d] : 1;
         s.dns[d] = (double)s.nstrat[d];
         s.rns[d] = 1.0 / s.dns[d];
+        s.nsm[d] = (s.nstrat[d] >= 2 && s.nstrat[d] < 32768) ? (uint32_t)((0xffffffffull / (uint64_t)s.nstrat[d]) + 1ull) : 0u;
         if (d >= dim) c->cstride[d] = nh;
     }
     // dense local index space: my slabs in global order; only the globally last slab is partial
@@ -169,7 +170,16 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         CK(cudaMemcpy(c->fparams.p, q->x0_host, bytes, cudaMemcpyHostToDevice));
         CK(cudaMemcpy((char*)c->fparams.p + bytes, xs.data(), bytes, cudaMemcpyHostToDevice));
         FRidge f;
+        memset(&f, 0, sizeof f);
         f.x0 = (const double*)c->fparams.p; f.xs = f.x0 + q->n; f.n = q->n; f.mode = q->mode; f.a = q->a; f.norm = q->norm;
+        f.scale = q->norm / (double)q->n;
+        // up to VB_RIDGE_PMAX centres ride in the kernel parameters (padded with the last one to whole lock-step groups)
+        f.npar = (q->n <= VB_RIDGE_PMAX && vb_env_int("VB200_RIDGE_PAR", 1)) ? q->n : 0;
+        if (f.npar)
+            for (int k = 0; k < VB_RIDGE_PMAX + 8; ++k) {
+                const int kk = k < q->n ? k : q->n - 1;
+                f.cpar[k] = q->mode == 1 ? xs[kk] : q->x0_host[kk];
+            }
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
         c->light_hint = q->n <= vb_env_int("VB200_RIDGE_LIGHT_N", 48) && q->mode == 0;   // FRidgeLight: 4-wide lock-step
