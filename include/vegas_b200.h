@@ -81,6 +81,18 @@ int  vb200_plan(vb200_ctx* ctx, const double* sigf_dev, double neval_sigf, int64
                 int64_t max_neval_hcube, int64_t uniform_neval, int32_t* neval_hcube_dev,
                 int64_t stats_host[4], void* stream);
 int  vb200_chunk_offsets(vb200_ctx* ctx, int64_t* out_host, int64_t count);   /* count <= nchunks+1 */
+/* The same pre-pass for the NEXT iteration without a host round trip, launched right after an
+ * iteration's kernels: neval_sigf = neval_scaled / *sum_sigf_dev is formed on the device from the
+ * sum_sigf the iteration has just produced (acc_dev[nf + nf(nf+1)/2], after the all-reduce when the
+ * hypercube range is sharded), and the six statistics {sum, min, max, largest chunk, work items, work
+ * items of the 512-cube geometry} go to stats_dev, which the caller copies to the host together with
+ * the iteration's results.  Asynchronous; the context has no valid plan until vb200_plan_commit
+ * installs those statistics (host values) with the neval_sigf the host computed from the same sum_sigf
+ * (pyx:1657-1662: identical double arithmetic), or vb200_plan replaces the pre-pass. */
+int  vb200_plan_ahead(vb200_ctx* ctx, const double* sigf_dev, const double* sum_sigf_dev, double neval_scaled,
+                      int64_t min_neval_hcube, int64_t max_neval_hcube, int64_t uniform_neval,
+                      int64_t* stats_dev, void* stream);
+int  vb200_plan_commit(vb200_ctx* ctx, double neval_sigf, const int64_t stats_host[6], int64_t stats_out[4]);
 
 /* One fused iteration over this rank's cubes with the built-in integrand (pyx:2096-2197 in one
  * kernel).  acc_dev (+=): mean[nf], var lower triangle [nf(nf+1)/2] (row-major s>=t), sum_sigf.

@@ -49,16 +49,21 @@ def _worker(rank, world, port, q):
     idx = _local_cubes(NH, SLAB, rank, world)
     acc, sum_f, n_f, tot, mx = _partials(idx)
     status = torch.zeros(1, dtype=torch.int32)
-    # the packed form Integrator.__call__ uses must give the same answers
-    from vegas_b200._integrator import exchange_iteration
-    buf_f = torch.cat([acc, sum_f.reshape(-1)]).clone()
-    buf_i = torch.cat([n_f.reshape(-1), torch.tensor([tot])]).clone()
-    buf_m = torch.tensor([0, mx], dtype=torch.int64)
-    exchange_iteration(buf_f, buf_i, buf_m)
+    # the packed form Integrator.__call__ uses -- ONE fp64 SUM all-reduce per iteration -- must give the same answers
+    from vegas_b200._integrator import exchange_iteration, pack_iteration
+    nacc, nh = 3, DIM * NINC
+    buf_f = torch.zeros(nacc + 2 * nh + 2 + world, dtype=torch.float64)
+    buf_f[:nacc] = acc
+    buf_f[nacc:nacc + nh] = sum_f.reshape(-1)
+    nan_flag = torch.tensor([1 if rank == 1 else 0], dtype=torch.int32)          # rank 1 saw a NaN
+    pack_iteration(buf_f, nacc, nh, n_f, nan_flag, tot, mx, rank)
+    exchange_iteration(buf_f)
     allreduce_iteration(acc, sum_f, n_f, status)
     tot, mx = allreduce_neval_stats(tot, mx, 'cpu')
-    assert torch.equal(buf_f[:3], acc) and torch.equal(buf_f[3:].reshape(DIM, NINC), sum_f)
-    assert torch.equal(buf_i[:-1].reshape(DIM, NINC), n_f) and int(buf_i[-1]) == tot and int(buf_m[1]) == mx
+    assert torch.equal(buf_f[:3], acc) and torch.equal(buf_f[3:3 + nh].reshape(DIM, NINC), sum_f)
+    assert torch.equal(buf_f[3 + nh:3 + 2 * nh].reshape(DIM, NINC).to(torch.int64), n_f)
+    tail = buf_f[3 + 2 * nh:]
+    assert int(tail[0]) == tot and int(tail[1]) == 1 and int(tail[2:].max()) == mx
     # every rank runs the same deterministic host adapt on the reduced histogram
     m = vegas.AdaptiveMap(DIM * [[0., 1.]], ninc=NINC)
     m._accumulate_training(sum_f.numpy(), n_f.numpy())

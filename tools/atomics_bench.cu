@@ -126,6 +126,112 @@ __global__ void __launch_bounds__(256) k_hist(double* out, int W, int iters)
     if (t == 1.2345) out[0] = t;
 }
 
+// MODE 9 prototype: no fp64 atomics at all.  The last warp of the CTA OWNS the sums: sum word i belongs to
+// its lane i % 32, and every update of it is executed by that lane with plain LDS / DADD / STS.  The
+// other warps push {slot, value} into the owner lane's ring (slot reserved with a native u32 atomic,
+// value stored first, then -- after one __threadfence_block per sample -- the slot word, which doubles
+// as the "entry is valid" flag); counts stay native u32 reds.
+template <int QCAP>
+__global__ void __launch_bounds__(256) k_hist_owner(double* out, int W, int iters)
+{
+    double* ssum = sm;                                   // [D][W]
+    unsigned* scnt = (unsigned*)(sm + D * W);            // [D][W]
+    __shared__ uint4 q[32][QCAP];                        // {value lo, value hi, slot, sequence number}: one 16-byte store per push
+    __shared__ unsigned qtail[32];
+    __shared__ unsigned done_s;
+    for (int i = threadIdx.x; i < D * W; i += blockDim.x) { ssum[i] = 0; scnt[i] = 0; }
+    for (int i = threadIdx.x; i < 32 * QCAP; i += blockDim.x) (&q[0][0])[i] = make_uint4(0, 0, 0, (unsigned)(i % QCAP));   // cell sequence numbers (bounded MPSC queue after Vyukov)
+    if (threadIdx.x < 32) qtail[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) done_s = 0u;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    double acc = 0;
+    if (warp < nwarp - 1) {
+        uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+        // the 7 producer warps do the work of 8: same samples per CTA as the other modes
+        const int my_iters = (iters * nwarp + (nwarp - 2 - warp)) / (nwarp - 1);
+        for (int it = 0; it < my_iters; ++it) {
+            int b[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) b[d] = d * W + (int)(((unsigned long long)rng(s) * (unsigned)W) >> 32);
+            const double v = 1.0 + (double)(s & 1023) * 1e-6;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                atomicAdd(scnt + b[d], 1u);
+                const int o = b[d] & 31;
+                const unsigned tk = atomicAdd(&qtail[o], 1u);             // ticket: cell tk % QCAP, in lap tk / QCAP
+                const unsigned pos = tk % QCAP;
+                const unsigned ea = (unsigned)__cvta_generic_to_shared(&q[o][pos]);
+                // wait-and-store as ONE PTX loop with the store predicated inside it: a lane writes as soon as its
+                // own slot is free.  (Written in C++ the compiler moves the store behind the loop's reconvergence
+                // point, so the lanes of a warp hold their entries back until the slowest lane's slot frees -- and
+                // the owner, who consumes in order, can be waiting for exactly those: deadlock, observed.)
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 z;\n"
+                             "QPUSH:\n\tld.volatile.shared.u32 z, [%0+12];\n\tsetp.eq.u32 p, z, %5;\n\t"
+                             "@p st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t@!p bra QPUSH;\n\t}"
+                             :: "r"(ea), "r"((unsigned)__double2loint(v)), "r"((unsigned)__double2hiint(v)), "r"((unsigned)b[d]), "r"(tk + 1u), "r"(tk)
+                             : "memory");
+            }
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(&done_s, 1u);
+    } else {
+        unsigned head = 0;
+        bool last = false;
+        for (;;) {
+            const bool fin = *(volatile unsigned*)&done_s == (unsigned)(nwarp - 1);
+            for (;;) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(&q[lane][head % QCAP]);
+                uint4 ent;
+                asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ent.x), "=r"(ent.y), "=r"(ent.z), "=r"(ent.w) : "r"(sa) : "memory");
+                if (ent.w != head + 1u) break;                             // the cell's ticket has not been filled yet
+                asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(sa + 12u), "r"(head + (unsigned)QCAP) : "memory");   // free it for the next lap
+                ssum[ent.z] += __hiloint2double((int)ent.y, (int)ent.x);
+                ++head;
+            }
+            if (__all_sync(0xffffffffu, last)) break;
+            last = fin;
+        }
+    }
+    __syncthreads();
+    double t = acc;
+    for (int i = threadIdx.x; i < D * W; i += blockDim.x) t += ssum[i] + (double)scnt[i];
+    double cs = 0;                                       // every add is ~1: sums and counts must agree
+    for (int i = threadIdx.x; i < D * W; i += blockDim.x) cs += ssum[i] - (double)scnt[i];
+    if (t == 1.2345) out[0] = t;
+    if (fabs(cs) > 0.01 * D * W) atomicAdd(out + 1, 1.0);    // updates were lost
+}
+
+template <int QCAP>
+static int run_owner(int sms, int W, int nt, int bps, double mhz, double* out)
+{
+    auto kern = k_hist_owner<QCAP>;
+    const int iters = 2000;
+    size_t smem = (size_t)D * W * 12 + 512;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem));
+    if (occ < bps) { printf("%-28s W=%4d nt=%3d x%d: does not fit (occ %d)\n", "owner-warp queues", W, nt, bps, occ); return 0; }
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    CK(cudaMemset(out, 0, 16));
+    kern<<<sms * bps, nt, smem>>>(out, W, iters / 10);
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(a);
+    kern<<<sms * bps, nt, smem>>>(out, W, iters);
+    cudaEventRecord(b);
+    CK(cudaEventSynchronize(b));
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    double bad[2];
+    CK(cudaMemcpy(bad, out, 16, cudaMemcpyDeviceToHost));
+    const double nsamp = (double)sms * bps * nt * iters;
+    printf("%-28s W=%4d nt=%3d x%d: %8.3f ms  %7.2f ps/sample  %6.2f cyc/sample/SM   (threads flagging lost updates: %.0f)\n",
+           QCAP == 16 ? "owner-warp queues cap 16" : (QCAP == 32 ? "owner-warp queues cap 32" : "owner-warp queues cap 64"), W, nt, bps, ms, ms * 1e9 / nsamp, ms * 1e-3 * mhz * 1e6 * sms / nsamp, bad[1]);
+    return 0;
+}
+
 template <int MODE>
 static int run(const char* name, int sms, int W, int nt, int bps, double mhz, double* out)
 {
@@ -153,17 +259,21 @@ static int run(const char* name, int sms, int W, int nt, int bps, double mhz, do
 
 int main(int argc, char** argv)
 {
+    setvbuf(stdout, nullptr, _IONBF, 0);
     const double mhz = argc > 1 ? atof(argv[1]) : 1965.0;
     cudaDeviceProp pr;
     CK(cudaGetDeviceProperties(&pr, 0));
     const int sms = pr.multiProcessorCount;
     printf("device %s  SMs %d  (cycles at %.0f MHz)\n", pr.name, sms, mhz);
     double* out;
-    CK(cudaMalloc(&out, 8));
+    CK(cudaMalloc(&out, 16));
+    const bool only_owner = argc > 2;
     for (int W : {125, 1000}) {
         for (int cfg = 0; cfg < 3; ++cfg) {
             const int nt = cfg == 2 ? 128 : 256, bps = cfg == 0 ? 2 : (cfg == 1 ? 3 : 4);
             if (W == 1000 && cfg != 0) continue;
+            if (nt == 256 && (run_owner<16>(sms, W, nt, bps, mhz, out) || run_owner<32>(sms, W, nt, bps, mhz, out) || run_owner<64>(sms, W, nt, bps, mhz, out))) return 1;
+            if (only_owner) continue;
             if (run<0>("rng only", sms, W, nt, bps, mhz, out)) return 1;
             if (run<1>("u32 red", sms, W, nt, bps, mhz, out)) return 1;
             if (run<2>("f64 atomicAdd (CAST.SPIN)", sms, W, nt, bps, mhz, out)) return 1;

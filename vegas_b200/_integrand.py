@@ -113,6 +113,25 @@ class DeviceIntegrand(object):
         """repack the flat [nf] result (objects) into the integrand's output structure"""
         return buf
 
+    def device_twin(self, dim, device=None):
+        """This integrand as a ``@devicebatchintegrand``: ``f(x)`` runs the library functor on the HBM
+        buffer ``x[n, dim]`` (``vb200_eval_integrand``) and returns ``f[n]`` / ``f[n, nf]`` in HBM -- the
+        device batch callback route of ``Integrator.__call__`` (sample -> callback -> reduce) with the
+        same arithmetic as the fused kernel."""
+        import torch
+        from . import _lib
+        ctx = _lib.Context(device)
+        ctx.set_map(np.tile([0., 1.], (dim, 1)), np.ones(dim, np.int64))      # the functor only needs the dimension
+        params, keep = self.params(dim)
+        nf = ctx.set_integrand(self.fid, params, keep=(params, keep))
+
+        def f(x):
+            out = torch.empty((x.shape[0], nf), dtype=torch.float64, device=x.device)
+            ctx.eval_integrand(x.contiguous(), out)
+            return out if nf > 1 else out[:, 0]
+        f._ctx = ctx
+        return devicebatchintegrand(f)
+
 
 # --------------------------------------------------------------------------- standard form
 class _Base(object):

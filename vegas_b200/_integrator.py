@@ -102,6 +102,7 @@ class Integrator(object):
         self._sigf_len = 0
         self._itn_counter = 0
         self._launches = 0
+        self._plan_ahead = None  # (key, statistics) of an allocation pre-pass launched ahead of the next iteration
         self._trace = None      # test hook: called with the raw per-iteration sums before adapt
         self._timing = None     # bench hook: list receiving per-iteration CUDA-event pairs
         self._unfused_events = []   # bench hook: (events around sample / callback / reduce, rows) per batch
@@ -544,17 +545,43 @@ class Integrator(object):
             self._sigf_host = self._get_sigf()
             self._sigf_dev = None
 
-    def _plan(self, ctx, neval_hcube_out=None):
-        """vegas+ allocation for the coming iteration (pyx:1657-1706) -> (local total, max)"""
+    def _plan_args(self):
         adaptive = self.beta > 0 and self.nhcube > 1 and not self.adapt_to_errors
         neval_sigf = (self.neval_frac * self.neval / self.sum_sigf
                       if self.beta > 0 and self.sum_sigf > 0 and not self.adapt_to_errors else 0.0)
         max_nh = max(self.max_neval_hcube, self.min_neval_hcube)
-        total, nmin, nmax, nchunks = ctx.plan(self._sigf_dev if adaptive else None, neval_sigf,
-                                             self.min_neval_hcube, max_nh, int(self.neval / self.nhcube),
-                                             neval_hcube_out)
+        return adaptive, neval_sigf, max_nh, int(self.neval / self.nhcube)
+
+    def _plan_key(self, ctx, neval_sigf, max_nh, uniform):
+        """everything the allocation pre-pass depends on: a pre-pass launched ahead of time is used only
+        when none of it has changed since"""
+        return (id(ctx), getattr(ctx, 'integrand_serial', 0), self._ctx_strata,
+                None if self._sigf_dev is None else self._sigf_dev.data_ptr(),
+                float(neval_sigf), int(self.min_neval_hcube), int(max_nh), int(uniform))
+
+    def _plan(self, ctx, neval_hcube_out=None):
+        """vegas+ allocation for the coming iteration (pyx:1657-1706) -> (local total, max).  The
+        pre-pass over sigf is normally already done: it was launched behind the previous iteration's
+        kernels (``_plan_next``) and its statistics came back with that iteration's results."""
+        adaptive, neval_sigf, max_nh, uniform = self._plan_args()
+        ahead, self._plan_ahead = self._plan_ahead, None
+        if (ahead is not None and adaptive and neval_hcube_out is None
+                and ahead[0] == self._plan_key(ctx, neval_sigf, max_nh, uniform)):
+            total, nmin, nmax, nchunks = ctx.plan_commit(neval_sigf, ahead[1])
+        else:
+            total, nmin, nmax, nchunks = ctx.plan(self._sigf_dev if adaptive else None, neval_sigf,
+                                                 self.min_neval_hcube, max_nh, uniform, neval_hcube_out)
         self._nchunks = nchunks
         return total, nmax, adaptive
+
+    def _plan_next(self, ctx, sum_sigf_dev, stats_dev):
+        """launch the pre-pass of the NEXT iteration behind this one's kernels (``vb200_plan_ahead``):
+        the new sigf and sum_sigf are final on the device, so the host round trip ``vb200_plan`` needs
+        (launch, copy back, synchronise) disappears from the iteration"""
+        adaptive, _, max_nh, uniform = self._plan_args()
+        ctx.plan_ahead(self._sigf_dev, sum_sigf_dev, self.neval_frac * self.neval, self.min_neval_hcube, max_nh,
+                       uniform, stats_dev)
+        self._launches += 1
 
     def _flags(self, nf):
         f = 0
@@ -714,19 +741,19 @@ class Integrator(object):
                 self.analyzer.begin(itn, self)
             ctx, torch = self._engine()          # map / sigf may have changed
             hs = int(self.map.inc.shape[1])
-            # device buffers of the iteration, packed by reduction type so that sharded runs need
-            # three collectives and every run one device-to-host copy:
-            #   buf_f (fp64, SUM):  [mean, cov, sum_sigf | sum_f]     buf_i (int64, SUM): [n_f | samples]
-            #   buf_m (int64, MAX): [NaN flag, max samples per hypercube]
-            nacc = nf + nv + 1
-            n_bf, n_bi = nacc + self.dim * hs, self.dim * hs + 1
-            raw = torch.zeros(8 * (n_bf + n_bi + 2), dtype=torch.uint8, device=dev)     # one allocation, one D2H copy
+            # One allocation and one device-to-host copy per iteration:
+            #   buf_f (fp64):  [mean, cov, sum_sigf | sum_f | n_f as fp64 | samples, NaN count, max samples per
+            #                   hypercube of rank 0 .. world-1]   -- the part a sharded run all-reduces (SUM), once
+            #   buf_i (int64): [n_f | NaN flag | statistics of the next iteration's allocation pre-pass]
+            nacc, nh = nf + nv + 1, self.dim * hs
+            n_bf, n_bi = nacc + 2 * nh + 2 + world, nh + 1 + 6
+            raw = torch.zeros(8 * (n_bf + n_bi), dtype=torch.uint8, device=dev)
             buf_f = raw[:8 * n_bf].view(torch.float64)
-            buf_i = raw[8 * n_bf:8 * (n_bf + n_bi)].view(torch.int64)
-            buf_m = raw[8 * (n_bf + n_bi):].view(torch.int64)
-            acc, sum_f = buf_f[:nacc], buf_f[nacc:].view(self.dim, hs)
-            n_f = buf_i[:self.dim * hs].view(self.dim, hs)
-            status = buf_m[:1].view(torch.int32)              # the kernels set its low word
+            buf_i = raw[8 * n_bf:].view(torch.int64)
+            acc, sum_f = buf_f[:nacc], buf_f[nacc:nacc + nh].view(self.dim, hs)
+            n_f = buf_i[:nh].view(self.dim, hs)
+            status = buf_i[nh:nh + 1].view(torch.int32)       # the kernels set its low word
+            stats_next = buf_i[nh + 1:]
             if self._timing is not None:
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 ev[0].record()
@@ -748,19 +775,26 @@ class Integrator(object):
             if self._timing is not None:
                 ev[2].record()
             if world > 1:
-                buf_i[-1:].fill_(int(total))
-                buf_m[1:].fill_(int(nmax))
-                exchange_iteration(buf_f, buf_i, buf_m)
+                pack_iteration(buf_f, nacc, nh, n_f, status, total, nmax, rank)
+                exchange_iteration(buf_f)
+            # the next iteration's allocation pre-pass rides behind this one (sum_sigf is final on the device)
+            plan_next = ((flags & _lib.UPDATE_SIGF) and itn + 1 < self.nitn and self._sigf_dev is not None
+                         and not os.environ.get('VB200_NO_PLAN_AHEAD'))     # (developer switch)
+            if plan_next:
+                self._plan_next(ctx, acc[nf + nv:], stats_next)
             if self._timing is not None:
                 ev[3].record()
                 self._timing.append((ev, total))
             hraw = raw.cpu().numpy()
-            hf, hi, hm = (hraw[:8 * n_bf].view(np.float64), hraw[8 * n_bf:8 * (n_bf + n_bi)].view(np.int64),
-                          hraw[8 * (n_bf + n_bi):].view(np.int64))
+            hf, hi = hraw[:8 * n_bf].view(np.float64), hraw[8 * n_bf:].view(np.int64)
+            nan_seen = int(hi[nh]) != 0
+            n_f_h = hi[:nh]
             if world > 1:
-                total, nmax = int(hi[-1]), int(hm[1])
+                tail = hf[nacc + 2 * nh:]
+                total, nan_seen, nmax = int(tail[0]), tail[1] != 0, int(np.max(tail[2:]))
+                n_f_h = hf[nacc + nh:nacc + 2 * nh].astype(np.int64)      # counts < 2^53: exact in fp64
             self._set_neval_stats(total, nmax, adaptive, reduced=True)
-            if int(hm[0]) != 0:
+            if nan_seen:
                 # the reference raises before touching sigf (pyx:2133-2134); the kernels have already
                 # overwritten it, so put the stratification back into a consistent state first
                 if self._sigf_dev is not None:
@@ -768,7 +802,7 @@ class Integrator(object):
                     self.sum_sigf = self._sigf_len
                 raise ValueError('integrand evaluates to nan')
             acc_h = hf[:nacc]
-            sum_f_h, n_f_h = hf[nacc:].reshape(self.dim, hs), hi[:self.dim * hs].reshape(self.dim, hs)
+            sum_f_h, n_f_h = hf[nacc:nacc + nh].reshape(self.dim, hs), n_f_h.reshape(self.dim, hs)
             mean = acc_h[:nf].copy()
             if self.correlate_integrals:
                 var = np.zeros((nf, nf), float)
@@ -785,6 +819,9 @@ class Integrator(object):
             if self.beta > 0 and not self.adapt_to_errors and self.adapt:
                 if sum_sigf > 0:
                     self.sum_sigf = sum_sigf
+                    if plan_next:
+                        _, neval_sigf, max_nh, uniform = self._plan_args()
+                        self._plan_ahead = (self._plan_key(ctx, neval_sigf, max_nh, uniform), hi[nh + 1:nh + 7].copy())
                 else:
                     # integrand appears to be a constant => even distribution of points
                     if self._sigf_dev is not None:
@@ -864,13 +901,23 @@ def allreduce_iteration(acc, sum_f, n_f, status):
     dist.all_reduce(status, op=dist.ReduceOp.MAX)
 
 
-def exchange_iteration(buf_f, buf_i, buf_m):
-    """The same exchange on the packed buffers of ``Integrator.__call__``: fp64 sums, integer sums
-    (training counts, samples), and maxima (NaN flag, largest hypercube) -- three collectives."""
-    dist = _dist()
-    dist.all_reduce(buf_f)
-    dist.all_reduce(buf_i)
-    dist.all_reduce(buf_m, op=dist.ReduceOp.MAX)
+def pack_iteration(buf_f, nacc, nh, n_f, status, total, nmax, rank):
+    """Bring everything a sharded iteration exchanges into the one fp64 buffer that is all-reduced:
+    the training counts (integers below 2^53 are exact in fp64), this rank's samples, its NaN flag, and
+    its largest hypercube in slot ``rank`` of a per-rank tail (a SUM over one-hot slots is a gather,
+    from which the host takes the maximum)."""
+    buf_f[nacc + nh:nacc + 2 * nh].copy_(n_f.reshape(-1))
+    tail = buf_f[nacc + 2 * nh:]
+    tail[0] = float(total)
+    tail[1:2].copy_(status[:1])
+    tail[2 + rank] = float(nmax)
+
+
+def exchange_iteration(buf_f):
+    """The one exchange step of a sharded iteration: a single SUM all-reduce of the packed fp64
+    buffer ``[mean, cov, sum_sigf | sum_f | n_f | samples, NaN count, max samples per hypercube by rank]``
+    (NCCL over NVLink on GPUs; gloo in the CPU tests).  In place; every rank ends with identical values."""
+    _dist().all_reduce(buf_f)
 
 
 def allreduce_neval_stats(total, nmax, device):
@@ -884,9 +931,20 @@ def allreduce_neval_stats(total, nmax, device):
     return int(tot.item()), int(mx.item())
 
 
+def _slab_rot(ls, world):
+    """rotation of the rank order in round ``ls`` of the slab deal (csrc/common.cuh: slab_rot)"""
+    return (((ls * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF) >> 40) % world
+
+
 def _local_cubes(nhcube, slab, rank, world):
     """global hypercube indices owned by ``rank`` in local order (host mirror of the device's
     block-cyclic ``local_to_global``)"""
     nslab = -(-nhcube // slab)
-    idx = [np.arange(s * slab, min((s + 1) * slab, nhcube)) for s in range(rank, nslab, world)]
+    if world == 1:
+        return np.arange(nhcube)
+    idx = []
+    for ls in range(-(-nslab // world)):
+        s = ls * world + (rank + _slab_rot(ls, world)) % world
+        if s < nslab:
+            idx.append(np.arange(s * slab, min((s + 1) * slab, nhcube)))
     return np.concatenate(idx) if idx else np.zeros(0, np.int64)

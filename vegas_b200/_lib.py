@@ -24,6 +24,7 @@ SYMBOLS = (
     'vb200_iterate_fused', 'vb200_sample', 'vb200_reduce', 'vb200_map', 'vb200_invmap', 'vb200_jac1d',
     'vb200_add_training_data', 'vb200_map_adapt', 'vb200_uniforms', 'vb200_fp64_peak', 'vb200_launch_count',
     'vb200_last_launch', 'vb200_eval_integrand', 'vb200_dy_profile', 'vb200_sample_from_uniforms',
+    'vb200_plan_ahead', 'vb200_plan_commit',
 )
 
 
@@ -82,6 +83,8 @@ def load():
     L.vb200_set_integrand.argtypes = [vp, i32, vp, ctypes.c_size_t, ctypes.POINTER(i32)]
     L.vb200_plan.argtypes = [vp, vp, f64, i64, i64, i64, vp, pi64, vp]
     L.vb200_chunk_offsets.argtypes = [vp, vp, i64]
+    L.vb200_plan_ahead.argtypes = [vp, vp, vp, f64, i64, i64, i64, vp, vp]
+    L.vb200_plan_commit.argtypes = [vp, f64, pi64, pi64]
     L.vb200_iterate_fused.argtypes = [vp, u32, f64, i32, vp, vp, vp, vp, i64, vp, vp]
     L.vb200_sample.argtypes = [vp, u32, i64, i64, vp, vp, vp, vp, vp, vp, i32, vp]
     L.vb200_sample_from_uniforms.argtypes = [vp, u32, i64, i64, vp, vp, vp, vp, vp, vp, vp, i32, vp]
@@ -168,6 +171,7 @@ class Context(object):
     def set_integrand(self, fid, params, keep=None):
         nf = ctypes.c_int()
         self._keep = keep
+        self.integrand_serial = getattr(self, 'integrand_serial', 0) + 1
         check(self.L.vb200_set_integrand(self.h, fid, ctypes.byref(params), ctypes.sizeof(params),
                                          ctypes.byref(nf)))
         return nf.value
@@ -178,6 +182,18 @@ class Context(object):
         check(self.L.vb200_plan(self.h, _ptr(sigf), float(neval_sigf), int(min_nh), int(max_nh),
                                 int(uniform_neval), _ptr(neval_hcube), stats, _stream()))
         return stats[0], stats[1], stats[2], stats[3]
+
+    def plan_ahead(self, sigf, sum_sigf_dev, neval_scaled, min_nh, max_nh, uniform_neval, stats_dev):
+        """launch the allocation pre-pass of the NEXT iteration (no host round trip); statistics -> stats_dev[6]"""
+        check(self.L.vb200_plan_ahead(self.h, _ptr(sigf), _ptr(sum_sigf_dev), float(neval_scaled), int(min_nh), int(max_nh),
+                                      int(uniform_neval), _ptr(stats_dev), _stream()))
+
+    def plan_commit(self, neval_sigf, stats6):
+        """install the statistics of the pre-pass ``plan_ahead`` launched (host copies)"""
+        a = (ctypes.c_int64 * 6)(*[int(v) for v in stats6])
+        out = (ctypes.c_int64 * 4)()
+        check(self.L.vb200_plan_commit(self.h, float(neval_sigf), a, out))
+        return out[0], out[1], out[2], out[3]
 
     def chunk_offsets(self, count):
         out = np.empty(count, np.int64)

@@ -41,6 +41,7 @@ struct vb200_ctx {
     int sm_count = 0;
     size_t smem_per_sm = 0, smem_per_block_optin = 0;
     int last_grid = 0, last_bps = 0, last_wtot = 0, last_nt = 0, last_ch = 0;
+    bool very_light = false;                              // ... and only a handful of flops per sample (launch_engine: staging capacity)
     bool light_hint = false;                              // the integrand is cheap: prefer the light engine geometry      // geometry of the most recent engine launch
     int64_t last_smem = 0;
     uint64_t seed = 0;
@@ -59,6 +60,7 @@ struct vb200_ctx {
     AllocP al;
     int64_t plan_total = 0, plan_min = 0, plan_max = 0;
     int64_t plan_max_chunk = 0, plan_items = 0;
+    bool plan_light = false;                              // the launched pre-pass also planned the light geometry's chunks
     int64_t nsuper = 0, plan_super_items = -1;            // light geometry: VB_LCH-cube chunks and their items (-1: not planned)
     DevBuf super_items, super_item_off;
     DevBuf chunk_tot, chunk_off, chunk_items, item_off, stats;

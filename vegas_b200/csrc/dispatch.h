@@ -17,6 +17,7 @@ struct LaunchCfg {
     int sm_count;
     size_t smem_per_sm, smem_optin;   // device limits
     bool light;                       // use the light geometry (fused sources only)
+    bool very_light;                  // the integrand is a handful of flops: the sampler is the whole kernel
     // work items of the launch's chunk range, per geometry ([0]: VB_CH-cube chunks, [1]: VB_LCH-cube
     // chunks, whole range only); item_off == nullptr: one item per chunk
     const int64_t* item_off[2];
@@ -94,9 +95,10 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     EngineP p = p_in;
     const int dim = p.map.dim;
     cfg.nt = NT; cfg.ch = CH;
-    // staging capacity: 16 samples per thread (heavy) / 20 (light: a 512-cube chunk then usually
-    // is one tile; measured better than leaving the room to the histogram windows)
-    int cap = vb_env_int(CH == VB_CH ? "VB200_CAP" : "VB200_LCAP", (CH != VB_CH ? 20 : 16) * NT);
+    // staging capacity: 16 samples per thread (heavy); light: 20 (a 512-cube chunk then usually is one tile: fewer
+    // barriers) unless the integrand is only a handful of flops -- then 8, which leaves room for the histogram and
+    // grid windows of ALL axes of the 8-D benchmark (N = 1 ridge: 5.96 ms against 6.4 ms; N = 30: 11.3 against 10.7)
+    int cap = vb_env_int(CH == VB_CH ? "VB200_CAP" : "VB200_LCAP", (CH != VB_CH ? (cfg.very_light ? 8 : 20) : 16) * NT);
     const int lim = ((CH == VB_CH ? (NF > 4 ? 48 : 32) : 64) * 1024) / (8 * NF);   // many components: fewer, larger tiles (measured)
     if (cap > lim) cap = lim;
     if (cap < 256) cap = 256;

@@ -101,7 +101,6 @@ __device__ __forceinline__ int bin_floor(const EngineP& p, int d, int digit)
 // (axes whose window did not fit, chunks that wrap around an axis) go straight to global memory.
 extern __shared__ double vb_smem[];        // dynamic shared memory of the engine kernel
 static __shared__ int vb_wlo_s[VB_MAXD];   // first bin of the current window of each axis
-static __shared__ double vb_scratch_s[32];  // per-lane scratch slots (see hist_sum_slots4)
 // (file-scope declarations so that every access compiles to LDS / ATOMS: through generic pointers
 //  carried in a struct the compiler falls back to generic loads and the slower generic ATOM forms)
 
@@ -231,11 +230,12 @@ struct FusedSrc {
 #define VB_LMINB 2
 #endif
 #ifndef VB_HMINB
-#define VB_HMINB 3
+#define VB_HMINB 4          // heavy: 4 CTAs of 128 threads per SM at 128 registers (no spills; 173 ms against 178 ms at 3 x 165)
 #endif
     static constexpr int MINB = LIGHT ? VB_LMINB : (F::NF == 1 ? VB_HMINB : 2);   // resident CTAs per SM the register budget is set for
     static constexpr bool GRIDW = GW;                              // grid windows in shared memory (light, D <= 10)
     static constexpr bool USES_EXP = true;
+    static constexpr bool CLAIM = !LIGHT;                          // phase 1: warps claim 32-sample words dynamically
     // stratum digits of a cube (light: narrow, to leave the shared memory to the histogram windows;
     // the host falls back to the heavy geometry when a digit does not fit)
     typedef typename std::conditional<LIGHT, typename std::conditional<(D > 10), uint8_t, uint16_t>::type, uint32_t>::type dig_t;
@@ -321,10 +321,12 @@ struct FusedSrc {
         if (p.flags & VBF_TRAIN) {
             const double a = wf[0] * (double)r.n;
             const double fdv2 = __dmul_rn(a, a);
-            constexpr int UNRH = D > 10 ? 1 : D;
+            {
+                constexpr int UNRH = D > 10 ? 1 : D;
 #pragma unroll UNRH
-            for (int d = 0; d < D; ++d)
-                if (EXACT || d < dim) hist_add_code(p, d, code[d], fdv2);
+                for (int d = 0; d < D; ++d)
+                    if (EXACT || d < dim) hist_add_code(p, d, code[d], fdv2);
+            }
         }
     }
 };
@@ -344,6 +346,7 @@ struct BufferSrc {
     static constexpr int MINB = NF_ <= 4 ? VB_BUF_MINB_LO : VB_BUF_MINB_HI;
     static constexpr bool GRIDW = false;
     static constexpr bool USES_EXP = false;
+    static constexpr bool CLAIM = true;
     typedef uint32_t dig_t;
     __device__ __forceinline__ void sample(const EngineP& p, const SampleRef<dig_t>& r, double (&wf)[NF]) const
     {
@@ -587,6 +590,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     // of the tile, pc_s[w] counts the starts before word w
     __shared__ uint32_t sb_s[NT + 1];
     __shared__ int pc_s[NT + 1];
+    __shared__ int word_s;                                          // next unclaimed word of the tile (phase 1)
     int* const wlo_s = vb_wlo_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -767,6 +771,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
             // after the rank's last one are empty), so the j-th start is cube c0 + j.
             const int nword = (Tt + 31) >> 5;                      // <= NT (launcher: cap <= 32 NT)
             if (tid <= nword) sb_s[tid] = 0u;
+            if (tid == 0) word_s = 0;
             __syncthreads();
             for (int c = c0 + tid; c < c1; c += NT)
                 if (n_s[c] > 0) {
@@ -781,9 +786,20 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
             }
             __syncthreads();
 
-            // ---- phase 1: one thread per sample
-            for (int ib = 0; ib < Tt; ib += NT) {                  // warp-uniform trip count
-                const int i = ib + tid;
+            // ---- phase 1: one thread per sample.  Warps CLAIM the tile's 32-sample words one at a time
+            // (a shared counter) instead of striding over them: a static split leaves the warps that run
+            // faster -- their sub-partition is shared with other CTAs' warps -- waiting at the barrier
+            // below for the slowest one (ncu, N = 1000 ridge: 12 % of all warp samples sat there, the
+            // FP64 pipe 83 % busy); with claiming they all finish within one word of each other.
+            // (Sampler-bound kernels keep the static stride: N = 1 ridge 6.1 ms against 6.8 ms with claiming.)
+            for (int wd_static = warp;; wd_static += NW) {
+                int wd = wd_static;
+                if (Src::CLAIM) {
+                    if (lane == 0) wd = atomicAdd(&word_s, 1);
+                    wd = __shfl_sync(0xffffffffu, wd, 0);
+                }
+                if (wd >= nword) break;
+                const int i = (wd << 5) + lane;
                 if (i < Tt) {
                     const uint32_t m = sb_s[i >> 5] & (0xffffffffu >> (31 - lane));    // starts at or before this lane (word = the warp's 32 samples)
                     const int c = c0 + pc_s[i >> 5] + __popc(m) - 1;

@@ -1,6 +1,9 @@
 // fused_light.cu -- engine instantiations of the light geometry (two 256-thread CTAs per SM, grid and
 // histogram windows shared by all its warps) for the cheap built-in integrands, and the
 // light-or-heavy choice of every family.
+// one copy of the exp table here: the 15 KB the conflict-free 16-copy layout costs are worth more as
+// histogram / grid windows to these sampler-bound kernels (B200, N = 1 ridge: 5.96 ms against 6.20 ms)
+#define VB_EXP_COPIES 1
 #include "dispatch.h"
 
 int launch_fused_poly_heavy(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st);

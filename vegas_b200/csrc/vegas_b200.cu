@@ -110,10 +110,14 @@ extern "C" int vb200_set_strata(vb200_ctx* c, const int64_t* nstrat, int dim, in
         if (d >= dim) c->cstride[d] = nh;
     }
     // dense local index space: my slabs in global order; only the globally last slab is partial
-    int64_t nslab = (nh + slab - 1) / slab;
-    int64_t mine = nslab / world + ((nslab % world) > rank ? 1 : 0);
+    // (rounds of `world` slabs, each dealt in rotated rank order: common.cuh, slab_rot)
+    const int64_t nslab = (nh + slab - 1) / slab;
+    const int64_t rounds = nslab / world, rem = nslab % world;
+    const bool extra = rem > 0 && (rank + slab_rot(rounds, world)) % world < rem;     // a slab of the incomplete last round
+    const int64_t mine = rounds + (extra ? 1 : 0);
     int64_t nlocal = mine * slab;
-    if (mine > 0 && (nslab - 1) % world == rank) nlocal -= nslab * slab - nh;
+    const int64_t last_round = (nslab - 1) / world;
+    if (mine > 0 && (rank + slab_rot(last_round, world)) % world == (nslab - 1) % world) nlocal -= nslab * slab - nh;
     s.nlocal = nlocal;
     c->nchunks = (nlocal + VB_CH - 1) / VB_CH;
     c->have_strata = true;
@@ -133,6 +137,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
     const int dim = c->map.dim;
     c->fid = -1;
     c->light_hint = false;
+    c->very_light = false;
     switch (id) {
     case VB200_F_POLY: {
         if (nbytes != sizeof(vb200_poly_t)) return fail(-1, "poly: params size %zu != %zu", nbytes, sizeof(vb200_poly_t));
@@ -142,7 +147,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         for (int d = 0; d < VB_MAXD; ++d) { f.c[d] = q->c[d]; f.p[d] = q->p[d]; }
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
-        c->light_hint = true;
+        c->light_hint = c->very_light = true;
         break;
     }
     case VB200_F_GAUSS_MIX: {
@@ -157,6 +162,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
         c->light_hint = q->npeak <= 4;
+        c->very_light = q->npeak <= 2;
         break;
     }
     case VB200_F_RIDGE: {
@@ -183,6 +189,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
         c->light_hint = q->n <= vb_env_int("VB200_RIDGE_LIGHT_N", 48) && q->mode == 0;   // FRidgeLight: 4-wide lock-step
+        c->very_light = c->light_hint && q->n <= 4;
         break;
     }
     case VB200_F_GENZ_OSC: case VB200_F_GENZ_PRODPEAK: case VB200_F_GENZ_CORNER:
@@ -194,7 +201,7 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
         for (int d = 0; d < VB_MAXD; ++d) { f.a[d] = q->a[d]; f.u[d] = q->u[d]; }
         c->functor.assign((char*)&f, (char*)&f + sizeof f);
         c->nf = 1;
-        c->light_hint = true;
+        c->light_hint = c->very_light = true;
         break;
     }
     case VB200_F_PATHINT: {
@@ -235,10 +242,13 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
 // chunk_items[lc] = work items chunk lc is cut into: 1, or ceil(total / item_samples) when the vegas+
 // allocation piled more than item_samples samples onto its cubes (engine.cuh, "items").  The engine
 // never splits a cube (items that no cube starts in are empty); the samplers split by rows.
+// sum_sigf_dev != nullptr (planning ahead, vb200_plan_ahead): neval_sigf = neval_scaled / *sum_sigf_dev is
+// formed here, with the same correctly rounded division the host performs once it has read sum_sigf back
 __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t nchunks, int32_t* neval_out,
                                                 long long* chunk_tot, long long* chunk_items, long long item_samples,
-                                                long long* stats)
+                                                long long* stats, const double* sum_sigf_dev, double neval_scaled)
 {
+    if (sum_sigf_dev) al.neval_sigf = __ddiv_rn(neval_scaled, *sum_sigf_dev);
     __shared__ long long red[VB_NT / 32];
     __shared__ int rmin[VB_NT / 32], rmax[VB_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -335,10 +345,11 @@ __global__ void k_super_items(const long long* chunk_tot, int64_t nchunks, int g
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd((unsigned long long*)&stats[5], (unsigned long long)mine);
 }
 
-extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sigf, int64_t min_nh, int64_t max_nh,
-                          int64_t uniform_neval, int32_t* neval_hcube_dev, int64_t stats_host[4], void* stream)
+// launch the allocation pre-pass; statistics (6 int64, see above) go to stats_dev.  No synchronisation.
+static int plan_launch(vb200_ctx* c, const double* sigf_dev, double neval_sigf, const double* sum_sigf_dev, double neval_scaled,
+                       int64_t min_nh, int64_t max_nh, int64_t uniform_neval, int32_t* neval_hcube_dev, long long* stats_dev,
+                       cudaStream_t st)
 {
-    if (!c) return fail(-1, "null context");
     if (!c->have_strata) return fail(-1, "vb200_plan: call vb200_set_strata first");
     if (min_nh < 1 || min_nh > 0x7fffffff || uniform_neval > 0x7fffffff)
         return fail(-1, "vb200_plan: min_neval_hcube / uniform_neval out of int32 range");
@@ -346,26 +357,25 @@ extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sig
     if (max_nh > 0x7fffffff) max_nh = 0x7fffffff;
     if (!sigf_dev && uniform_neval < 1) return fail(-1, "vb200_plan: uniform_neval < 1");
     CK(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
     c->al.sigf = sigf_dev;
     c->al.neval_sigf = neval_sigf;
     c->al.min_neval_hcube = (int)min_nh;
     c->al.max_neval_hcube = (int)max_nh;
     c->al.uniform_neval = (int)uniform_neval;
+    c->have_plan = false;                                       // until vb200_plan / vb200_plan_commit install the statistics
     const int64_t nch = c->nchunks;
     CK(c->chunk_tot.ensure(sizeof(long long) * (size_t)(nch + 1)));
     CK(c->chunk_off.ensure(sizeof(long long) * (size_t)(nch + 1)));
     CK(c->chunk_items.ensure(sizeof(long long) * (size_t)(nch + 1)));
     CK(c->item_off.ensure(sizeof(long long) * (size_t)(nch + 1)));
-    CK(c->stats.ensure(sizeof(long long) * 6));
     long long item_samples = vb_env_int("VB200_ITEM", VB_ITEM);
     if (item_samples < 256) item_samples = 256;
-    long long init[6] = {0, 0x7fffffffffffffffLL, 0, 0, 0, 0};
-    CK(cudaMemcpyAsync(c->stats.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+    const long long init[6] = {0, 0x7fffffffffffffffLL, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(stats_dev, init, sizeof init, cudaMemcpyHostToDevice, st));
     if (nch > 0) {
         int grid = (int)(nch < (int64_t)c->sm_count * 8 ? nch : (int64_t)c->sm_count * 8);
         k_plan<<<grid, VB_NT, 0, st>>>(c->st, c->al, nch, neval_hcube_dev, (long long*)c->chunk_tot.p,
-                                       (long long*)c->chunk_items.p, item_samples, (long long*)c->stats.p);
+                                       (long long*)c->chunk_items.p, item_samples, stats_dev, sum_sigf_dev, neval_scaled);
         c->launches += 1;
         if (c->light_hint) {
             const int group = VB_LCH / VB_CH;
@@ -374,15 +384,22 @@ extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sig
             CK(c->super_item_off.ensure(sizeof(long long) * (size_t)(c->nsuper + 1)));
             k_super_items<<<(int)((c->nsuper + 255) / 256 < 1024 ? (c->nsuper + 255) / 256 : 1024), 256, 0, st>>>(
                 (const long long*)c->chunk_tot.p, nch, group, item_samples * group, VB_LCH, c->nsuper, (long long*)c->super_items.p,
-                (long long*)c->stats.p);
+                stats_dev);
             c->launches += 1;
         }
         CK(cudaGetLastError());
     }
+    c->plan_light = c->light_hint;
+    return 0;
+}
+
+// install the statistics of the launched pre-pass (host values) in the context
+static void plan_install(vb200_ctx* c, const long long out_in[6])
+{
     long long out[6];
-    CK(cudaMemcpyAsync(out, c->stats.p, sizeof out, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    c->plan_super_items = (c->light_hint && nch > 0) ? out[5] : -1;
+    memcpy(out, out_in, sizeof out);
+    const int64_t nch = c->nchunks;
+    c->plan_super_items = (c->plan_light && nch > 0) ? out[5] : -1;
     if (nch == 0) out[1] = 0;
     c->plan_total = out[0]; c->plan_min = out[1]; c->plan_max = out[2]; c->plan_max_chunk = out[3];
     c->plan_items = out[4];
@@ -390,7 +407,42 @@ extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sig
     c->chunk_off_valid = c->item_off_valid = c->super_off_valid = false;
     c->chunk_off_host.clear();
     c->item_off_host.clear();
-    if (stats_host) { stats_host[0] = out[0]; stats_host[1] = out[1]; stats_host[2] = out[2]; stats_host[3] = nch; }
+}
+
+extern "C" int vb200_plan(vb200_ctx* c, const double* sigf_dev, double neval_sigf, int64_t min_nh, int64_t max_nh,
+                          int64_t uniform_neval, int32_t* neval_hcube_dev, int64_t stats_host[4], void* stream)
+{
+    if (!c) return fail(-1, "null context");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    CK(c->stats.ensure(sizeof(long long) * 6));
+    int rc = plan_launch(c, sigf_dev, neval_sigf, nullptr, 0.0, min_nh, max_nh, uniform_neval, neval_hcube_dev, (long long*)c->stats.p, st);
+    if (rc) return rc;
+    long long out[6];
+    CK(cudaMemcpyAsync(out, c->stats.p, sizeof out, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    plan_install(c, out);
+    if (stats_host) { stats_host[0] = c->plan_total; stats_host[1] = c->plan_min; stats_host[2] = c->plan_max; stats_host[3] = c->nchunks; }
+    return 0;
+}
+
+extern "C" int vb200_plan_ahead(vb200_ctx* c, const double* sigf_dev, const double* sum_sigf_dev, double neval_scaled,
+                                int64_t min_nh, int64_t max_nh, int64_t uniform_neval, int64_t* stats_dev, void* stream)
+{
+    if (!c || !sigf_dev || !sum_sigf_dev || !stats_dev) return fail(-1, "vb200_plan_ahead: null argument");
+    return plan_launch(c, sigf_dev, 0.0, sum_sigf_dev, neval_scaled, min_nh, max_nh, uniform_neval, nullptr, (long long*)stats_dev,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int vb200_plan_commit(vb200_ctx* c, double neval_sigf, const int64_t stats_host[6], int64_t stats_out[4])
+{
+    if (!c || !stats_host) return fail(-1, "vb200_plan_commit: null argument");
+    if (c->have_plan) return fail(-1, "vb200_plan_commit: no pre-pass is waiting (call vb200_plan_ahead first)");
+    c->al.neval_sigf = neval_sigf;
+    long long out[6];
+    for (int i = 0; i < 6; ++i) out[i] = stats_host[i];
+    plan_install(c, out);
+    if (stats_out) { stats_out[0] = c->plan_total; stats_out[1] = c->plan_min; stats_out[2] = c->plan_max; stats_out[3] = c->nchunks; }
     return 0;
 }
 
@@ -542,6 +594,7 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     if (rc_items) return rc_items;
     if (it.end[1] < 0) light = false;                  // light chunks were not planned (set_integrand after plan)
     cfg.light = light;
+    cfg.very_light = c->very_light;
     for (int g = 0; g < 2; ++g) { cfg.item_off[g] = it.off[g]; cfg.item_begin[g] = it.begin[g]; cfg.item_end[g] = it.end[g]; }
     auto launch = [&](cudaStream_t s) { return fused ? do_launch_fused(c, p, cfg, s) : launch_buffer(p, nf, cfg, s); };
     int grid = launch(VB_DRYRUN);
