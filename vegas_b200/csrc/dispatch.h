@@ -37,6 +37,8 @@ int launch_fused_ridge(const EngineP& p, const void* functor, LaunchCfg& cfg, cu
 int launch_fused_genz(const EngineP& p, const void* functor, LaunchCfg& cfg, cudaStream_t st);
 int launch_fused_pathint(const EngineP& p, const void* functor, int nx0, LaunchCfg& cfg, cudaStream_t st);
 int launch_buffer(const EngineP& p, int nf, LaunchCfg& cfg, cudaStream_t st);
+int launch_reduce(const EngineP& p, int nf, LaunchCfg& cfg, cudaStream_t st);   // k_reduce<NF> (reduce.cuh): TMA-staged rows
+bool reduce_bulk_ok(const EngineP& p);
 
 // dry-run variants: only compute the geometry (cfg outputs, grid size) so the caller can size
 // scratch before the real launch.  Implemented by passing st == (cudaStream_t)-1.

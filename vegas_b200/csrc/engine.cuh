@@ -70,6 +70,9 @@ struct EngineP {
     const uint16_t* bins;      // [rows][dim] training bins written by the sampler (nullptr: replay Philox)
     const int64_t* chunk_off;  // [nchunks+1] exclusive scan of samples per chunk
     int64_t row0;              // chunk_off[chunk_begin]
+    // k_reduce (reduce.cuh): rows of the launch's batch buffers, and the layout of one shared-memory stage
+    int64_t batch_rows;
+    int st_w, st_b, st_bytes;  // byte offsets of wgt / bins inside a stage, stage size
 };
 
 __device__ __forceinline__ int tri(int s, int t) { return s * (s + 1) / 2 + t; }
@@ -99,7 +102,7 @@ __device__ __forceinline__ int bin_floor(const EngineP& p, int d, int digit)
 // window per axis, [lo[d], lo[d] + wcap[d]), and flushes it to the global histogram with fp64 /
 // u64 atomics only when a newly claimed chunk needs a different window.  Bins outside the window
 // (axes whose window did not fit, chunks that wrap around an axis) go straight to global memory.
-extern __shared__ double vb_smem[];        // dynamic shared memory of the engine kernel
+extern __shared__ __align__(16) double vb_smem[];   // dynamic shared memory of the engine kernel (16-byte aligned: bulk-copy destination)
 static __shared__ int vb_wlo_s[VB_MAXD];   // first bin of the current window of each axis
 // (file-scope declarations so that every access compiles to LDS / ATOMS: through generic pointers
 //  carried in a struct the compiler falls back to generic loads and the slower generic ATOM forms)
@@ -169,6 +172,42 @@ __device__ __forceinline__ void hist_flush(const EngineP& p, const HistW& H, con
             }
         }
     }
+}
+
+// whole CTA: bring the windows to the strata the CH cubes starting at global cube h0 touch; the windows
+// that have to move (or all of them when `force`) are flushed to the global histogram first.
+// wneed_s[d] tells the caller which ones moved (to wnew_s[d]).  Contains barriers.
+template <int NT>
+__device__ __forceinline__ void hist_move_windows(const EngineP& p, const HistW& H, int64_t h0, int CH, bool force,
+                                                  int* wnew_s, int* wneed_s)
+{
+    const int tid = threadIdx.x, dim = p.map.dim;
+    int* const wlo_s = vb_wlo_s;
+    if (tid < dim) {
+        const int d = tid;
+        int need = 0, lo_bin = 0;
+        if (p.wcap[d] > 0) {
+            const int64_t a = h0 / p.cstride[d], b = (h0 + CH - 1) / p.cstride[d];
+            const int64_t ns = p.st.nstrat[d];
+            int dlo = 0, dhi = (int)ns - 1;
+            if (b - a + 1 < ns) {
+                dlo = (int)(a % ns);
+                const int e = (int)(b % ns);
+                if (e >= dlo) dhi = e;                     // else the chunk wraps: keep [dlo, ns-1]
+            }
+            lo_bin = bin_floor(p, d, dlo);
+            int hi_bin = bin_floor(p, d, dhi + 1);
+            if (hi_bin > lo_bin + p.wcap[d] - 1) hi_bin = lo_bin + p.wcap[d] - 1;
+            const int cur = wlo_s[d];
+            need = (force || lo_bin < cur || hi_bin >= cur + p.wcap[d]) ? 1 : 0;
+        }
+        wneed_s[d] = need;
+        wnew_s[d] = lo_bin;
+    }
+    __syncthreads();
+    hist_flush<NT>(p, H, wneed_s);
+    __syncthreads();
+    if (tid < dim && wneed_s[tid]) wlo_s[tid] = wnew_s[tid];
 }
 
 // training point of a whole cube (adapt_to_errors, _vegas.pyx:2187-2193): y of its LAST sample
@@ -505,6 +544,7 @@ __device__ __forceinline__ long long chunk_setup(const EngineP& p, int64_t lh0, 
         if (dvn_s) dvn_s[c] = p.dv_y / (double)n_mine[i];           // weight factor of the cube's samples (pyx:1746-1752), once per cube
         ex += n_mine[i];
         uint32_t carry = (uint32_t)c;                              // digits of cube h0+c: base digits plus c, with carries
+        if (y0_s != nullptr)
         for (int d = 0; d < dim; ++d) {
             const uint32_t v = base_s[d] + carry, ns = (uint32_t)p.st.nstrat[d];
             const uint32_t qd = digit_div(p.st, d, v);                // v < ns + CH
@@ -624,31 +664,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
         if (p.wtot > 0) {
             // ---- move the windows to this chunk's strata (flush the histogram of the ones that change)
             const bool force = since_flush > 0x40000000LL;         // keep the u32 counts far from overflow
-            if (tid < dim) {
-                const int d = tid;
-                int need = 0, lo_bin = 0;
-                if (p.wcap[d] > 0) {
-                    const int64_t a = h0 / p.cstride[d], b = (h0 + CH - 1) / p.cstride[d];
-                    const int64_t ns = p.st.nstrat[d];
-                    int dlo = 0, dhi = (int)ns - 1;
-                    if (b - a + 1 < ns) {
-                        dlo = (int)(a % ns);
-                        const int e = (int)(b % ns);
-                        if (e >= dlo) dhi = e;                     // else the chunk wraps: keep [dlo, ns-1]
-                    }
-                    lo_bin = bin_floor(p, d, dlo);
-                    int hi_bin = bin_floor(p, d, dhi + 1);
-                    if (hi_bin > lo_bin + p.wcap[d] - 1) hi_bin = lo_bin + p.wcap[d] - 1;
-                    const int cur = wlo_s[d];
-                    need = (force || lo_bin < cur || hi_bin >= cur + p.wcap[d]) ? 1 : 0;
-                }
-                wneed_s[d] = need;
-                wnew_s[d] = lo_bin;
-            }
-            __syncthreads();
-            hist_flush<NT>(p, H, wneed_s);
-            __syncthreads();
-            if (tid < dim && wneed_s[tid]) wlo_s[tid] = wnew_s[tid];
+            hist_move_windows<NT>(p, H, h0, CH, force, wnew_s, wneed_s);
             if (Src::GRIDW) {
                 // grid nodes lo .. lo + wcap of the moved windows (nodes past the axis end repeat the last one)
                 for (int d = 0; d < dim; ++d) {

@@ -596,7 +596,8 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     cfg.light = light;
     cfg.very_light = c->very_light;
     for (int g = 0; g < 2; ++g) { cfg.item_off[g] = it.off[g]; cfg.item_begin[g] = it.begin[g]; cfg.item_end[g] = it.end[g]; }
-    auto launch = [&](cudaStream_t s) { return fused ? do_launch_fused(c, p, cfg, s) : launch_buffer(p, nf, cfg, s); };
+    const bool bulk = !fused && reduce_bulk_ok(p);
+    auto launch = [&](cudaStream_t s) { return fused ? do_launch_fused(c, p, cfg, s) : (bulk ? launch_reduce(p, nf, cfg, s) : launch_buffer(p, nf, cfg, s)); };
     int grid = launch(VB_DRYRUN);
     if (grid == -22) return fail(-4, "engine: no kernel compiled for dim=%d nf=%d integrand=%d", p.map.dim, nf, c->fid);
     if (grid < 0) return fail(-2, "engine: occupancy query failed (%d)", grid);
@@ -667,6 +668,7 @@ extern "C" int vb200_reduce(vb200_ctx* c, uint32_t itn, double beta, int flags, 
     rc = vb_fetch_chunk_off(c, (cudaStream_t)stream);
     if (rc) return rc;
     p.row0 = c->chunk_off_host[(size_t)chunk_begin];
+    p.batch_rows = c->chunk_off_host[(size_t)chunk_end] - p.row0;
     p.fbuf = f_dev; p.wbuf = wgt_dev; p.bins = bins_dev;
     return run_engine(c, p, nf, false, acc_dev, (cudaStream_t)stream);
 }
