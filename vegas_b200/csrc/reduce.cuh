@@ -6,21 +6,34 @@
 // traffic: 8 NF + 8 + 2 dim bytes per row, read once.
 //
 // Round 1 reduced these buffers with the fused engine's kernel and a source that loaded each row
-// with per-thread global loads: latency-bound (ncu: 18 % warp occupancy at 168 registers, 4 % of the
-// HBM copy bandwidth for 7 outputs).  Here the rows arrive by TMA:
+// with per-thread global loads.  Here the rows arrive by TMA:
 //   * persistent CTAs claim work items (chunks of 256 hypercubes, or parts of chunks the vegas+
-//     allocation piled samples onto) exactly as k_engine does;
-//   * an item's rows are cut into TILES of whole hypercubes (<= CAP rows); each tile is fetched with
-//     three 1-D bulk copies (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes: f, wgt,
-//     bins) into one of two shared-memory stages, completion signalled on the stage's mbarrier; the
-//     copy of tile t+1 is in flight while tile t is reduced;
+//     allocation piled samples onto) as k_engine does -- one item AHEAD, so the claim's round trip to
+//     L2, the chunk search and the chunk's row offset hide behind the previous item;
+//   * an item's rows are cut into TILES of whole hypercubes (cubes binned by their first row in
+//     buckets of 2/3 CAP rows; ballot + popc ranks, no serial walk); each tile is fetched with three
+//     1-D bulk copies (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes: f, wgt, bins)
+//     into one of two shared-memory stages, completion signalled on the stage's mbarrier; the copy of
+//     tile t+1 is in flight while tile t is reduced;
 //   * phase A (thread per row): w*f in place, NaN check, training-histogram adds from the bins;
 //     phase B: the reference's two-pass mean / variance per hypercube from the staged tile (thread per
-//     cube up to VB_WARP_CUBE samples, a warp per larger cube);
+//     cube up to VB_RWARP_CUBE rows, a warp per larger cube, claimed from a counter);
 //   * hypercubes larger than a tile are streamed from HBM twice by the whole CTA (second pass hits L2).
 // The accumulators, the histogram windows and the sigf update are the engine's (engine.cuh).
+//
+// What the measurements say (B200, one 8.4M-row batch): with one output the kernel
+// takes 0.77 ms with training, 0.25 ms without -- the dim shared-memory fp64 adds per row (a CAS loop each:
+// there is no native shared fp64 add) are two thirds of it, the same cost the fused kernel pays.  Two
+// restructurings were measured and dropped: strips of consecutive rows per thread with per-cube sums
+// through shared atomics (balanced, but 4 extra CAS adds per row: 0.83 ms), and warp-autonomous pipelines
+// with one pair of stages per warp (no CTA barriers inside an item, but half-empty warps: 0.91 ms).
 #pragma once
 #include "engine.cuh"
+
+// cubes with more rows than this are reduced by a whole warp
+#ifndef VB_RWARP_CUBE
+#define VB_RWARP_CUBE 64     // measured on B200 (8-D, one output, vegas+ allocation 2..1271 rows per cube): 24 -> 0.85 ms, 40 -> 0.81, 64 -> 0.77 per 8.4M rows
+#endif
 
 template <int NF>
 struct ReduceGeom {
@@ -63,13 +76,13 @@ __device__ __forceinline__ void fence_proxy_async()
 }
 
 // dynamic shared memory of k_reduce<NF> (launcher and kernel use the same function)
-__host__ inline size_t reduce_layout(EngineP& p, int nf, int capa, int ch, int dim, int maxt)
+__host__ inline size_t reduce_layout(EngineP& p, int nf, int capa, int ch, int dim, int maxt, bool stage_bins)
 {
     const int wtot = p.wtot;
     // one stage: f [capa][nf] fp64 | wgt [capa] fp64 | bins [capa][dim] u16
     p.st_w = (int)(sizeof(double) * (size_t)capa * nf);
     p.st_b = p.st_w + (int)(sizeof(double) * (size_t)capa);
-    p.st_bytes = (p.st_b + 2 * capa * dim + 15) & ~15;
+    p.st_bytes = (p.st_b + (stage_bins ? 2 * capa * dim : 0) + 15) & ~15;
     size_t b = 2 * (size_t)p.st_bytes;
     p.o_ex = (int)b;    b += sizeof(long long) * (size_t)(ch + 1);
     p.o_hsum = (int)b;  b += sizeof(double) * (size_t)wtot;
@@ -104,8 +117,9 @@ __global__ void __launch_bounds__(256, ReduceGeom<NF>::MINB) k_reduce(const __gr
     __shared__ long long scan_s[NW];
     __shared__ double red_s[NW];
     __shared__ uint32_t base_s[VB_MAXD];
-    __shared__ long long next_s;
-    __shared__ int sub_s[2], ntile_s;
+    __shared__ long long next_s, row_s;
+    __shared__ int wcnt_s[NW];
+    __shared__ int sub_s[2], ntile_s, lclaim_s;
     __shared__ int nlarge_s, large_s[VB_LARGE_MAX];
     __shared__ double p1_s[NW * NF], p2_s[NW * (NF + NV)];              // block reduction of a giant cube's sums
     __shared__ int wnew_s[VB_MAXD], wneed_s[VB_MAXD];
@@ -167,20 +181,39 @@ __global__ void __launch_bounds__(256, ReduceGeom<NF>::MINB) k_reduce(const __gr
         __syncthreads();
     };
 
-    for (;;) {
-        __syncthreads();                       // previous item fully consumed; barriers initialised
-        if (tid == 0) {
-            const long long g = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);
-            if (g >= p.item_end) next_s = p.chunk_end;
-            else {
-                long long c; int sub, nsub;
-                locate_item(p, g, c, sub, nsub);
-                next_s = c; sub_s[0] = sub; sub_s[1] = nsub;
+    // Work items are claimed one ahead: thread 0 asks for item k+1 when item k starts and looks at the
+    // answer (the atomic's round trip to L2, the chunk search, the chunk's row offset) when item k is done.
+    const long long extra_items = p.item_off ? (p.item_end - p.item_begin) - (p.chunk_end - p.chunk_begin) : 0;
+    auto resolve = [&](long long g) {                             // thread 0: which chunk is item g, where do its rows start?
+        if (g >= p.item_end) { next_s = p.chunk_end; return; }
+        long long c; int sub = 0, nsub = 1;
+        if (p.item_off == nullptr) c = g;
+        else {
+            // chunk j holds at least one item, so chunk(g) <= chunk_begin + (g - item_begin), and it is at
+            // most `extra_items` (the number of additional parts of split chunks) below that
+            long long hi = p.chunk_begin + (g - p.item_begin) + 1;
+            if (hi > p.chunk_end) hi = p.chunk_end;
+            long long lo = hi - 1 - extra_items;
+            if (lo < p.chunk_begin) lo = p.chunk_begin;             // item_off[lo] <= g < item_off[hi]
+            while (hi - lo > 1) {
+                const long long mid = (lo + hi) >> 1;
+                if (p.item_off[mid] <= g) lo = mid; else hi = mid;
             }
+            c = lo;
+            sub = (int)(g - p.item_off[lo]);
+            nsub = (int)(p.item_off[lo + 1] - p.item_off[lo]);
         }
-        __syncthreads();
+        next_s = c; sub_s[0] = sub; sub_s[1] = nsub;
+        row_s = p.chunk_off[c] - p.row0;
+    };
+    if (tid == 0) resolve(p.item_begin + (long long)atomicAdd(p.work_counter, 1ull));
+    for (;;) {
+        __syncthreads();                       // previous item fully consumed; barriers initialised; next_s written
         const int64_t lc = next_s;
         if (lc >= p.chunk_end) break;
+        long long g_ahead = 0;
+        if (tid == 0) g_ahead = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);
+        const int64_t chunk_row = row_s;
         const int sub = sub_s[0], nsub = sub_s[1];
         const int64_t lh0 = lc * CH;
         const int64_t h0 = local_to_global(p.st, lh0);
@@ -190,35 +223,35 @@ __global__ void __launch_bounds__(256, ReduceGeom<NF>::MINB) k_reduce(const __gr
             if (force) since_flush = 0;
         }
         const long long total = chunk_setup<NT, CH, uint32_t>(p, lh0, h0, ex_s, n_s, nullptr, base_s, scan_s);
-        const int64_t chunk_row = p.chunk_off[lc] - p.row0;
         int c0, cend;
         item_cubes(ex_s, CH, total, sub, nsub, c0, cend);
         since_flush += ex_s[cend] - ex_s[c0];
         // ---- tile list: a tile is a run of whole cubes staged together.  Cubes are binned by the row
-        // they start at (buckets of Q = CAP - CAP/4 rows); a cube of more than CAP/4 rows is a tile of its
-        // own (above CAP rows: a giant, streamed from HBM).  A tile then holds < Q + CAP/4 = CAP rows,
-        // and every thread can tell on its own whether its cube starts one (no serial walk).
+        // they start at (buckets of Q = 2/3 CAP rows, a power of two); a cube of more than CAP/3 rows is a
+        // tile of its own (above CAP rows: a giant, streamed from HBM).  A tile then holds < Q + CAP/3 =
+        // CAP rows, and every thread can tell on its own whether its cube starts one (no serial walk).
         {
             const int c = tid;
-            const int bigthr = CAP >> 2, Q = CAP - bigthr;
+            const int bigthr = CAP / 3, qshift = 31 - __clz(2 * bigthr);
             int flag = 0;
             if (c >= c0 && c < cend && n_s[c] > 0) {
                 const long long b0 = ex_s[c0];
-                const bool big = n_s[c] > bigthr;
-                if (c == c0 || big) flag = 1;
-                else {
-                    const bool pbig = n_s[c - 1] > bigthr;
-                    flag = (pbig || (ex_s[c] - b0) / Q != (ex_s[c - 1] - b0) / Q) ? 1 : 0;
-                }
+                if (c == c0 || n_s[c] > bigthr || n_s[c - 1] > bigthr) flag = 1;
+                else flag = (((ex_s[c] - b0) >> qshift) != ((ex_s[c - 1] - b0) >> qshift)) ? 1 : 0;
             }
-            long long ntl;
-            const long long rk = block_exscan<NT>((long long)flag, scan_s, &ntl);
+            // ranks of the flags: ballot + popc inside a warp, the warps' counts through shared memory
+            const unsigned bal = __ballot_sync(0xffffffffu, flag);
+            if (lane == 0) wcnt_s[warp] = __popc(bal);
+            __syncthreads();
+            int rk = __popc(bal & ((1u << lane) - 1u)), ntl = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { const int v = wcnt_s[w]; if (w < warp) rk += v; ntl += v; }
             if (flag) tl_s[rk] = c;
             if (tid == 0) {
                 int e = cend;                                      // one past the last cube with samples
                 while (e > c0 && n_s[e - 1] == 0) --e;
                 tl_s[ntl] = e;
-                ntile_s = (int)ntl;
+                ntile_s = ntl;
             }
         }
         __syncthreads();
@@ -319,7 +352,7 @@ __global__ void __launch_bounds__(256, ReduceGeom<NF>::MINB) k_reduce(const __gr
             // start bits of the tile's cubes (as in k_engine) while the copy lands
             const int nword = (Tt + 31) >> 5;
             if (tid <= nword) sb_s[tid] = 0u;
-            if (tid == 0) nlarge_s = 0;
+            if (tid == 0) { nlarge_s = 0; lclaim_s = 0; }
             __syncthreads();
             for (int c = ca + tid; c < cb; c += NT)
                 if (n_s[c] > 0) {
@@ -366,7 +399,7 @@ __global__ void __launch_bounds__(256, ReduceGeom<NF>::MINB) k_reduce(const __gr
             // ---- phase B: small cubes, one thread each, in the reference's order (pyx:2142-2186)
             for (int c = ca + tid; c < cb; c += NT) {
                 const int n = n_s[c];
-                if (n > 0 && n <= VB_WARP_CUBE) {
+                if (n > 0 && n <= VB_RWARP_CUBE) {
                     const double* wfp = fs + (size_t)(ex_s[c] - base) * NF;
                     double S[NF], m[NF], sd[NF], q[NV];
 #pragma unroll
@@ -386,14 +419,18 @@ __global__ void __launch_bounds__(256, ReduceGeom<NF>::MINB) k_reduce(const __gr
                     }
                     const double sigf2 = cube_finish<NF>(A, n, S, sd, q, correlate);
                     cube_epilogue<NF, uint32_t>(p, H, A, sigf2, lh0 + c, h0 + c, n, nullptr, chunk_row + ex_s[c] + n - 1);
-                } else if (n > VB_WARP_CUBE) {
+                } else if (n > VB_RWARP_CUBE) {
                     large_s[atomicAdd(&nlarge_s, 1)] = c;          // at most CAP / (VB_WARP_CUBE + 1) <= VB_LARGE_MAX per tile
                 }
             }
             __syncthreads();
             // ---- larger cubes: one warp each
-            const int nlarge = nlarge_s;
-            for (int j = warp; j < nlarge; j += NW) {
+            const int nlarge = nlarge_s;                           // (claimed from a counter: their sizes differ)
+            for (;;) {
+                int j = 0;
+                if (lane == 0) j = atomicAdd(&lclaim_s, 1);
+                j = __shfl_sync(0xffffffffu, j, 0);
+                if (j >= nlarge) break;
                 const int c = large_s[j], n = n_s[c];
                 const double* wfp = fs + (size_t)(ex_s[c] - base) * NF;
                 double S[NF], m[NF], sd[NF], q[NV];
@@ -423,6 +460,7 @@ __global__ void __launch_bounds__(256, ReduceGeom<NF>::MINB) k_reduce(const __gr
             }
             __syncthreads();                                       // the stage may be refilled now
         }
+        if (tid == 0) resolve(g_ahead);                            // (every thread read next_s / sub_s / row_s of this item long ago)
     }
 
     if (p.wtot > 0) hist_flush<NT>(p, H, nullptr);

@@ -55,19 +55,22 @@ static int launch_reduce_nf(const EngineP& p_in, LaunchCfg& cfg, cudaStream_t st
     const int rowb = 8 * NF + 8 + (train ? 2 * dim : 0);
     const long long fixed = sizeof(long long) * (G::CH + 1) + sizeof(int) * G::CH + sizeof(int) * (G::MAXT + 1) + 256;
     long long stage_budget = (per_cta - fixed) / 2;
-    if (!(p.flags & (VBF_TRAIN | VBF_TRAIN_ERRORS))) stage_budget = per_cta - fixed;
+    if (!(p.flags & (VBF_TRAIN | VBF_TRAIN_ERRORS))) stage_budget = per_cta - fixed - 2048;
+    if (stage_budget > 144 * 1024) stage_budget = 144 * 1024;
     int cap = (int)(stage_budget / 2 / rowb) - 16;
     cap = vb_env_int("VB200_RCAP", cap);
-    if (cap > 2048) cap = 2048;
-    cap &= ~31;
-    if (cap < 64) return -24;
+    // cap = 3 * 2^k (k_reduce bins the cubes by their first row in buckets of 2/3 cap rows, a power of two)
+    int k = 6;
+    while (3 * (2 << k) <= cap && k < 9) ++k;
+    if (3 * (1 << k) > cap) return -24;
+    cap = 3 * (1 << k);
     cfg.cap = p.cap = cap;
     vb_plan_windows(p, G::CH, 0, false);
-    const size_t smem0 = reduce_layout(p, NF, cap + 16, G::CH, dim, G::MAXT);
+    const size_t smem0 = reduce_layout(p, NF, cap + 16, G::CH, dim, G::MAXT, train);
     long long budget = (per_cta - (long long)smem0 - 256) / (long long)(sizeof(double) + sizeof(unsigned));
     vb_plan_windows(p, G::CH, budget, false);
     cfg.wtot = p.wtot;
-    cfg.smem = reduce_layout(p, NF, cap + 16, G::CH, dim, G::MAXT);
+    cfg.smem = reduce_layout(p, NF, cap + 16, G::CH, dim, G::MAXT, train);
     if ((long long)cfg.smem > dyn_max) return -24;
     cfg.blocks_per_sm = bps;
     int grid = bps * cfg.sm_count;

@@ -596,7 +596,10 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     cfg.light = light;
     cfg.very_light = c->very_light;
     for (int g = 0; g < 2; ++g) { cfg.item_off[g] = it.off[g]; cfg.item_begin[g] = it.begin[g]; cfg.item_end[g] = it.end[g]; }
-    const bool bulk = !fused && reduce_bulk_ok(p);
+    // k_reduce (TMA-staged rows) for up to 4 outputs; with more, the per-thread covariance accumulators make it a
+    // one-CTA-per-SM kernel and k_engine<BufferSrc> is the faster one (B200, 7 outputs: 3.8 against 4.1 ms per 8.4M rows)
+    const int bulk_mode = vb_env_int("VB200_REDUCE_BULK", 1);     // 0: never, 1: as measured, 2: whenever possible (developer switch)
+    const bool bulk = !fused && bulk_mode != 0 && (nf <= 4 || bulk_mode == 2) && reduce_bulk_ok(p);
     auto launch = [&](cudaStream_t s) { return fused ? do_launch_fused(c, p, cfg, s) : (bulk ? launch_reduce(p, nf, cfg, s) : launch_buffer(p, nf, cfg, s)); };
     int grid = launch(VB_DRYRUN);
     if (grid == -22) return fail(-4, "engine: no kernel compiled for dim=%d nf=%d integrand=%d", p.map.dim, nf, c->fid);
