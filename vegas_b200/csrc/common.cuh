@@ -99,10 +99,16 @@ __constant__ double vb_exp_c[6] = VB_EXP_POLY;
 __device__ const double vb_exp_tab_g[128] = VB_EXP_TABLE;
 static __shared__ double vb_exp_tab_s[128 * VB_EXP_COPIES];
 
-// called by all threads of a CTA before the first vb_exp*(); needs a barrier after
+// called by all threads of a CTA before the first vb_exp*(); needs a barrier after.
+// The shared copy holds T[j] with j << 13 subtracted from its high word: the reader adds n << 13 =
+// (128 k + j) << 13 to it and gets T[j] * 2^k in one integer multiply-add (no masking of n).
 __device__ __forceinline__ void vb_exp_init()
 {
-    for (int i = threadIdx.x; i < 128 * VB_EXP_COPIES; i += blockDim.x) vb_exp_tab_s[i] = vb_exp_tab_g[i / VB_EXP_COPIES];
+    for (int i = threadIdx.x; i < 128 * VB_EXP_COPIES; i += blockDim.x) {
+        const int j = i / VB_EXP_COPIES;
+        const double t = vb_exp_tab_g[j];
+        vb_exp_tab_s[i] = __hiloint2double(__double2hiint(t) - (j << 13), __double2loint(t));
+    }
 }
 
 template <int W>
@@ -129,21 +135,22 @@ __device__ __forceinline__ void vb_exp_n(const double (&x)[W], double (&e)[W])
 #pragma unroll
         for (int j = 0; j < W; ++j) p[j] = __fma_rn(p[j], r[j], vb_exp_c[i]);
     }
-    unsigned big = 0;
+    // |x| >= 708 shows in the high word of x: as an unsigned number for negative x, as a signed one for positive x
+    unsigned umax = 0u;
+    int smax = 0;
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        const unsigned n = (unsigned)__double2loint(t[j]);   // 128 k + j (two's complement in the low word)
-        // 2 integer instructions each for the table address and the exponent (mask, multiply-add)
-        unsigned sa, hi;
-        double T;
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"(n & 127u), "n"(1 << CSHIFT), "r"(tab));
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(sa));
-        p[j] = __dmul_rn(p[j], T);
-        asm("mad.lo.u32 %0, %1, 8192, %2;" : "=r"(hi) : "r"(n & ~127u), "r"((unsigned)__double2hiint(p[j])));
-        e[j] = __hiloint2double((int)hi, __double2loint(p[j]));
-        big = max(big, (unsigned)__double2hiint(x[j]) & 0x7fffffffu);
+        const int n = __double2loint(t[j]);                  // 128 k + j (two's complement in the low word)
+        // 3 integer instructions and one shared load per argument: table address (mask, multiply-add), scaled entry
+        unsigned sa, thi, tlo;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sa) : "r"((unsigned)n & 127u), "n"(1 << CSHIFT), "r"(tab));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tlo), "=r"(thi) : "r"(sa));
+        asm("mad.lo.u32 %0, %1, 8192, %2;" : "=r"(thi) : "r"((unsigned)n), "r"(thi));
+        e[j] = __dmul_rn(p[j], __hiloint2double((int)thi, (int)tlo));
+        umax = max(umax, (unsigned)__double2hiint(x[j]));
+        smax = max(smax, __double2hiint(x[j]));
     }
-    if (big >= 0x40862000u) {                              // some |x| >= 708: one branch for all W
+    if (umax >= 0xC0862000u || smax >= 0x40862000) {        // some |x| >= 708, inf or NaN: one branch for all W
 #pragma unroll
         for (int j = 0; j < W; ++j)
             if ((__double2hiint(x[j]) & 0x7fffffff) >= 0x40862000) e[j] = exp(x[j]);

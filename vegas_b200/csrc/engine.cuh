@@ -490,7 +490,9 @@ __device__ __forceinline__ void cube_epilogue(const EngineP& p, const HistW& H, 
                                               int64_t lh, int64_t h, int n, const dig_t* y0, int64_t row_last)
 {
     if (p.flags & VBF_UPDATE_SIGF) {
-        double sg = pow(sigf2, p.beta_half);
+        // sigf = sigf2^(beta/2) (pyx:2183) as exp(b log x): 2-3 times fewer instructions than pow(); relative error
+        // <= (2 + |b ln x|) ulp, far inside the 1e-12 the stratification is compared at
+        const double sg = sigf2 == 0.0 ? 0.0 : exp(p.beta_half * log(sigf2));
         p.sigf_out[lh] = sg;
         A.sum_sigf += sg;
     }
@@ -643,21 +645,22 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
     if (tid < VB_MAXD) wlo_s[tid] = -0x40000000;                   // no window yet: the first chunk installs them
     long long since_flush = 0;                                    // samples added since the last full flush
 
-    // work is claimed dynamically (one atomic per item) so that CTAs finish together
+    // Work is claimed dynamically (one atomic per item) so that CTAs finish together -- and one item AHEAD:
+    // thread 0 asks for item k+1 when item k starts and looks at the answer when item k is done, so the
+    // atomic's round trip to L2 and the chunk search hide behind the item's work.
+    auto resolve = [&](long long g) {
+        if (g >= p.item_end) { next_s = p.chunk_end; return; }
+        long long c; int sub, nsub;
+        locate_item(p, g, c, sub, nsub);
+        next_s = c; sub_s[0] = sub; sub_s[1] = nsub;
+    };
+    if (tid == 0) resolve(p.item_begin + (long long)atomicAdd(p.work_counter, 1ull));
     for (;;) {
-        __syncthreads();                       // previous item fully consumed
-        if (tid == 0) {
-            const long long g = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);
-            if (g >= p.item_end) next_s = p.chunk_end;
-            else {
-                long long c; int sub, nsub;
-                locate_item(p, g, c, sub, nsub);
-                next_s = c; sub_s[0] = sub; sub_s[1] = nsub;
-            }
-        }
-        __syncthreads();
+        __syncthreads();                       // previous item fully consumed, next_s written
         const int64_t lc = next_s;
         if (lc >= p.chunk_end) break;
+        long long g_ahead = 0;
+        if (tid == 0) g_ahead = p.item_begin + (long long)atomicAdd(p.work_counter, 1ull);
         const int sub = sub_s[0], nsub = sub_s[1];                 // this CTA does part `sub` of `nsub` of the chunk
         const int64_t lh0 = lc * CH;
         const int64_t h0 = local_to_global(p.st, lh0);
@@ -935,6 +938,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
             __syncthreads();
             c0 = c1;
         }
+        if (tid == 0) resolve(g_ahead);        // (every thread read next_s / sub_s of this item long ago)
     }
 
     if (p.wtot > 0) hist_flush<NT>(p, H, nullptr);               // the loop exits through a barrier
