@@ -140,6 +140,19 @@ int  vb200_dy_profile(vb200_ctx* ctx, uint32_t itn, int64_t chunk_begin, int64_t
                       const double* f_dev, int fstride, const double* wgt_dev, int ndy,
                       const double* yst_host, double* acc_dev, void* stream);
 
+/* PDFIntegrator's change of variables on device buffers (src/vegas/__init__.py:599-627, _f_lbatch):
+ * theta_dev[rows][dim] -> p_dev[rows][dim] = mean + chiv . vec_sig with chiv = scale * tan(theta), and
+ * w_dev[rows] = prod_i scale (tan^2 theta_i + 1) * dp_dchiv * pdf, pdf = the parameters' Gaussian
+ * prod_i exp(-chiv_i^2/2)/sqrt(2 pi) / dp_dchiv when `gaussian`, else 1 (the caller multiplies by its own
+ * pdf(p)).  mean_dev[dim], vec_sig_dev[dim][dim] (row i = principal axis i scaled by its sigma: gvar.PDF). */
+int  vb200_pdf_map(vb200_ctx* ctx, const double* theta_dev, int64_t rows, int dim, double scale, double dp_dchiv,
+                   int gaussian, const double* mean_dev, const double* vec_sig_dev, double* p_dev, double* w_dev,
+                   void* stream);
+/* rows of PDFIntegrator's integrand (__init__.py:617-640): out_dev[rows][nfp+1] = [w | fp * w] when
+ * pdf_first (adapt_to_pdf=True), else [fp * w | w]; fp_dev[rows][nfp] (NULL when nfp == 0) */
+int  vb200_pdf_weight(vb200_ctx* ctx, const double* fp_dev, int nfp, const double* w_dev, int64_t rows,
+                      int pdf_first, double* out_dev, void* stream);
+
 /* AdaptiveMap array methods on device buffers (pyx:310-360, 362-416, 265-295, 421-464) */
 int  vb200_map(vb200_ctx* ctx, const double* y_dev, double* x_dev, double* jac_dev, int64_t n, void* stream);
 int  vb200_invmap(vb200_ctx* ctx, const double* x_dev, double* y_dev, double* jac_dev, int64_t n, void* stream);

@@ -15,6 +15,7 @@ from ._integrand import (VegasIntegrand, LBatchIntegrand, RBatchIntegrand, Batch
 from ._results import RAvg, RAvgArray, RAvgDict, VegasResult, reporter, ravg
 from ._integrator import Integrator
 from ._restratify import restratify, restratifyIntegrator, stratification_profile
+from ._pdf import PDFIntegrator, PDFEV, PDFEVArray, PDFEVDict, PDFAnalyzer
 from . import integrands
 
 __version__ = '0.1.0'
@@ -23,5 +24,5 @@ ranseed = _gv.ranseed
 __all__ = ['Integrator', 'AdaptiveMap', 'RAvg', 'RAvgArray', 'RAvgDict', 'VegasResult', 'reporter',
            'VegasIntegrand', 'LBatchIntegrand', 'RBatchIntegrand', 'BatchIntegrand', 'DeviceIntegrand',
            'lbatchintegrand', 'rbatchintegrand', 'batchintegrand', 'devicebatchintegrand', 'integrands',
-           'restratify', 'restratifyIntegrator', 'ravg',
+           'restratify', 'restratifyIntegrator', 'ravg', 'PDFIntegrator', 'PDFEV', 'PDFEVArray', 'PDFEVDict',
            'ranseed']

@@ -877,11 +877,67 @@ class Integrator(object):
                                  % (tuple(fx.shape), rows, (rows, nf)))
             if self._timing is not None:
                 tev[2].record()
-            ctx.reduce(pitn, self.beta, flags, c0, c1, fx, nf, wgt, self._sigf_dev, acc, sum_f, n_f, hs, status, bins=bins)
+            if nf <= _lib.MAX_REDUCE_NF:
+                ctx.reduce(pitn, self.beta, flags, c0, c1, fx, nf, wgt, self._sigf_dev, acc, sum_f, n_f, hs, status, bins=bins)
+            else:
+                self._reduce_wide(ctx, torch, pitn, flags, c0, c1, fx, nf, wgt, acc, sum_f, n_f, hs, status, bins)
             if self._timing is not None:
                 tev[3].record()
                 self._unfused_events.append((tev, rows))
             self._launches += 3
+
+    def _wide_passes(self, nf, device, torch):
+        """plan of the reduce passes for an integrand with more components than the reduce kernel's
+        instantiations (``_lib.MAX_REDUCE_NF``): [(columns, source indices, destination indices in acc)].
+        Correlated integrands: components in groups of 4, one pass per pair of groups (every covariance
+        block is inside some pair); uncorrelated: groups of 8, one pass each.  Means, diagonal blocks and
+        sum_sigf are taken from the first pass that has them."""
+        key = (nf, bool(self.correlate_integrals), str(device))
+        if getattr(self, '_wide_plan', (None,))[0] == key:
+            return self._wide_plan[1]
+        tri = lambda s_, t_: s_ * (s_ + 1) // 2 + t_
+        nv = nf * (nf + 1) // 2
+        if self.correlate_integrals:
+            gs = 4
+            groups = [list(range(g0, min(g0 + gs, nf))) for g0 in range(0, nf, gs)]
+            sets = [groups[i] + groups[j] for i in range(len(groups)) for j in range(i + 1, len(groups))]
+        else:
+            sets = [list(range(g0, min(g0 + _lib.MAX_REDUCE_NF, nf))) for g0 in range(0, nf, _lib.MAX_REDUCE_NF)]
+        done_mean, done_var, passes = set(), set(), []
+        for k, cols in enumerate(sets):
+            m = len(cols)
+            src, dst = [], []
+            for a, s_ in enumerate(cols):
+                if s_ not in done_mean:
+                    done_mean.add(s_)
+                    src.append(a); dst.append(s_)
+                for b in range(a + 1):
+                    t_ = cols[b]
+                    if (s_, t_) not in done_var and (self.correlate_integrals or s_ == t_):
+                        done_var.add((s_, t_))
+                        src.append(m + tri(a, b)); dst.append(nf + tri(s_, t_))
+            if k == 0:
+                src.append(m + m * (m + 1) // 2); dst.append(nf + nv)        # sum_sigf
+            passes.append((torch.tensor(cols, dtype=torch.int64, device=device), m,
+                           torch.tensor(src, dtype=torch.int64, device=device),
+                           torch.tensor(dst, dtype=torch.int64, device=device)))
+        self._wide_plan = (key, passes)
+        return passes
+
+    def _reduce_wide(self, ctx, torch, pitn, flags, c0, c1, fx, nf, wgt, acc, sum_f, n_f, hs, status, bins):
+        """per-hypercube reduce of an integrand with more than ``_lib.MAX_REDUCE_NF`` components: the reduce
+        kernel runs on column subsets gathered in HBM (the reference handles any ``fcn.size`` in one loop,
+        pyx:2136-2197); training and the ``sigf`` update happen in the first pass only, which holds component 0"""
+        quiet = flags & ~(_lib.UPDATE_SIGF | _lib.TRAIN | _lib.TRAIN_ERRORS)
+        # the pass that updates sigf runs last: the others must still see the allocation the rows were sampled with
+        plan = list(enumerate(self._wide_passes(nf, ctx.device, torch)))
+        for k, (cols, m, src, dst) in plan[1:] + plan[:1]:
+            sub = fx.index_select(1, cols).contiguous()
+            acc_p = torch.zeros(m + m * (m + 1) // 2 + 1, dtype=torch.float64, device=ctx.device)
+            ctx.reduce(pitn, self.beta, flags if k == 0 else quiet, c0, c1, sub, m, wgt, self._sigf_dev, acc_p, sum_f, n_f,
+                       hs, status, bins=bins)
+            acc.index_add_(0, dst, acc_p.index_select(0, src))
+            self._launches += 1
 
     @property
     def gpu_launches(self):

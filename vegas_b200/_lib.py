@@ -17,6 +17,8 @@ UPDATE_SIGF, TRAIN, TRAIN_ERRORS, CORRELATE = 1, 2, 4, 8
 F_POLY, F_GAUSS_MIX, F_RIDGE, F_GENZ_OSC, F_GENZ_PRODPEAK, F_GENZ_CORNER, F_GENZ_GAUSS, F_GENZ_C0, \
     F_GENZ_DISC, F_PATHINT = range(10)
 
+MAX_REDUCE_NF = 8            # components vb200_reduce is instantiated for (wider integrands: Integrator._reduce_wide)
+
 # every symbol include/vegas_b200.h declares
 SYMBOLS = (
     'vb200_abi_version', 'vb200_last_error', 'vb200_create', 'vb200_destroy', 'vb200_set_seed',
@@ -24,7 +26,7 @@ SYMBOLS = (
     'vb200_iterate_fused', 'vb200_sample', 'vb200_reduce', 'vb200_map', 'vb200_invmap', 'vb200_jac1d',
     'vb200_add_training_data', 'vb200_map_adapt', 'vb200_uniforms', 'vb200_fp64_peak', 'vb200_launch_count',
     'vb200_last_launch', 'vb200_eval_integrand', 'vb200_dy_profile', 'vb200_sample_from_uniforms',
-    'vb200_plan_ahead', 'vb200_plan_commit',
+    'vb200_plan_ahead', 'vb200_plan_commit', 'vb200_pdf_map', 'vb200_pdf_weight',
 )
 
 
@@ -97,6 +99,8 @@ def load():
     L.vb200_uniforms.argtypes = [vp, u32, i64, i64, vp, vp]
     L.vb200_eval_integrand.argtypes = [vp, vp, i64, vp, vp]
     L.vb200_dy_profile.argtypes = [vp, u32, i64, i64, vp, i32, vp, i32, vp, vp, vp]
+    L.vb200_pdf_map.argtypes = [vp, vp, i64, i32, f64, f64, i32, vp, vp, vp, vp, vp]
+    L.vb200_pdf_weight.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp]
     L.vb200_fp64_peak.argtypes = [i32, i32, ctypes.POINTER(f64), ctypes.POINTER(f64)]
     L.vb200_launch_count.argtypes = [vp]
     L.vb200_launch_count.restype = i64
@@ -220,6 +224,17 @@ class Context(object):
     def eval_integrand(self, x, f):
         """f[rows, nf] = the context's built-in functor at x[rows, dim] (device tensors)"""
         check(self.L.vb200_eval_integrand(self.h, _ptr(x), x.shape[0], _ptr(f), _stream()))
+
+    def pdf_map(self, theta, scale, dp_dchiv, gaussian, mean, vec_sig, p, w):
+        """PDFIntegrator's change of variables: p[rows, dim], w[rows] from theta[rows, dim] (device tensors;
+        mean[dim], vec_sig[dim, dim] device tensors)"""
+        check(self.L.vb200_pdf_map(self.h, _ptr(theta), theta.shape[0], theta.shape[1], float(scale), float(dp_dchiv),
+                                   int(bool(gaussian)), _ptr(mean), _ptr(vec_sig), _ptr(p), _ptr(w), _stream()))
+
+    def pdf_weight(self, fp, w, out, pdf_first):
+        """out[rows, nfp + 1] = [w | fp * w] (pdf_first) or [fp * w | w]; fp[rows, nfp] or None"""
+        nfp = 0 if fp is None else fp.shape[1]
+        check(self.L.vb200_pdf_weight(self.h, _ptr(fp), nfp, _ptr(w), w.shape[0], int(bool(pdf_first)), _ptr(out), _stream()))
 
     def dy_profile(self, itn, c0, c1, f, fstride, wgt, yst, acc):
         yst = np.ascontiguousarray(yst, dtype=np.float64)

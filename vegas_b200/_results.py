@@ -498,6 +498,10 @@ def ravg(reslist, weighted=None, rescale=None):
     ``itn_results`` are then used.  ``weighted=False`` gives the unweighted (unbiased) average, e.g.
     ``vegas.ravg(r.itn_results[5:], weighted=False)`` to drop the iterations where the map was still
     adapting.  ``rescale`` as in :class:`RAvgArray`. """
+    from . import _pdf                     # (imported here: _pdf builds on this module)
+    for t in (_pdf.PDFEV, _pdf.PDFEVArray, _pdf.PDFEVDict):
+        if isinstance(reslist, t):         # average the underlying integrals, then form the ratios again
+            return t(ravg(reslist.itn_results, weighted=weighted, rescale=rescale))
     src = reslist
     if isinstance(reslist, (RAvg, RAvgArray, RAvgDict)):
         reslist = reslist.itn_results
