@@ -18,11 +18,14 @@ Only the behaviour the reference's hot path touches is provided:
 * ``SVD``                           -- eigen-decomposition with svdcut
                                        (``_vegas.pyx:2721``)
 * ``gammaQ``, ``GVarRef``, ``dumps`` / ``loads`` (pickle based)
+* ``PDF``, ``PDFStatistics``, ``gvar('1.0(5)')``  -- what ``vegas.PDFIntegrator`` needs
+                                       (``src/vegas/__init__.py:496-503, 599-606, 1009``)
 
 The real gvar algorithms are re-stated from their published behaviour; nothing
 here is used to produce shipped results.
 """
 import pickle as _pickle
+import re as _re
 
 import numpy as _np
 from scipy.special import gammaincc as _gammaincc
@@ -70,19 +73,6 @@ class GVar(object):
     @property
     def internaldata(self):
         return (self.mean, self._terms)
-
-    # comparisons act on the means (as in gvar; the reference's restratify sorts weights with them)
-    def __lt__(self, other):
-        return self.mean < getattr(other, 'mean', other)
-
-    def __gt__(self, other):
-        return self.mean > getattr(other, 'mean', other)
-
-    def __le__(self, other):
-        return self.mean <= getattr(other, 'mean', other)
-
-    def __ge__(self, other):
-        return self.mean >= getattr(other, 'mean', other)
 
     @property
     def var(self):
@@ -148,6 +138,22 @@ class GVar(object):
         return GVar(self.mean ** p,
                     [(b, i, k * p * self.mean ** (p - 1)) for b, i, k in self._terms])
 
+    # comparisons act on the means (as in gvar)
+    def __lt__(self, other):
+        return self.mean < getattr(other, 'mean', other)
+
+    def __gt__(self, other):
+        return self.mean > getattr(other, 'mean', other)
+
+    def __le__(self, other):
+        return self.mean <= getattr(other, 'mean', other)
+
+    def __ge__(self, other):
+        return self.mean >= getattr(other, 'mean', other)
+
+    def __abs__(self):
+        return self if self.mean >= 0 else -self
+
     def __call__(self):
         """A random sample from the distribution."""
         return self.mean + self.sdev * RNG.standard_normal()
@@ -201,16 +207,59 @@ def fmt_gvar(mean, sdev):
     return '%.*f(%d)' % (ndec, mean, int(s2))
 
 
+_GV_STR = _re.compile(r'^\s*([-+]?)(\d*)(?:\.(\d*))?\s*\(\s*(\d*)(?:\.(\d*))?\s*\)\s*(?:[eE]([-+]?\d+))?\s*$')
+_GV_PM = _re.compile(r'^\s*(\S+)\s*(?:\+-|\+/-|\u00b1)\s*(\S+)\s*$')
+
+
+def _parse(text):
+    """'1.35(86)', '13.5(8.6)', '1(1)e-3', '1.2 +- 0.3' -> (mean, sdev)"""
+    m = _GV_PM.match(text)
+    if m:
+        return float(m.group(1)), float(m.group(2))
+    m = _GV_STR.match(text)
+    if not m:
+        raise ValueError('cannot convert %r to a GVar' % (text,))
+    sign, ip, fp, eip, efp, ex = m.groups()
+    mean_ = float((ip or '0') + '.' + (fp or '0'))
+    if efp is not None:                       # error written with its own decimal point: literal
+        sdev_ = float((eip or '0') + '.' + (efp or '0'))
+    else:                                     # error in units of the last digit of the mean
+        sdev_ = float(eip or '0') * 10.0 ** (-len(fp or ''))
+    scale = 10.0 ** int(ex) if ex else 1.0
+    if sign == '-':
+        mean_ = -mean_
+    return mean_ * scale, sdev_ * scale
+
+
 def gvar(*args):
-    """gvar(mean, sdev) | gvar(mean_array, sdev_array | cov_matrix) | gvar(GVar)."""
+    """gvar(mean, sdev) | gvar(mean_array, sdev_array | cov_matrix) | gvar('1.0(5)') | gvar(array or dict of
+    those) | gvar(GVar)."""
     if len(args) == 1:
         a = args[0]
         if isinstance(a, GVar):
             return a
-        if isinstance(a, (tuple, list)) and len(a) == 2 and _np.ndim(a[0]) == 0:
+        if isinstance(a, str):
+            return gvar(*_parse(a))
+        if hasattr(a, 'keys'):
+            out = BufferDict()
+            for k in a:
+                out[k] = gvar(a[k])
+            return out
+        if isinstance(a, (tuple, list)) and len(a) == 2 and _np.ndim(a[0]) == 0 and not isinstance(a[0], (str, GVar)):
             return gvar(*a)
-        return _np.asarray(a, dtype=object)
+        arr = _np.asarray(a, dtype=object)
+        if arr.shape == ():
+            return gvar(arr.item()) if isinstance(arr.item(), str) else arr
+        out = _np.empty(arr.shape, dtype=object)
+        for idx in _np.ndindex(arr.shape):
+            v = arr[idx]
+            out[idx] = gvar(v) if isinstance(v, str) else v
+        return out
     m, s = args
+    if hasattr(m, 'keys'):
+        m = asbufferdict(m)
+        sb = asbufferdict(s).buf if hasattr(s, 'keys') else s
+        return BufferDict(m, buf=gvar(_np.array(m.buf, dtype=float), _np.array(sb, dtype=float)))
     if _np.ndim(m) == 0:
         m = float(m)
         s = float(s)
@@ -226,6 +275,21 @@ def gvar(*args):
     for i, mi in enumerate(m.reshape(-1)):
         out[i] = GVar(mi, [(blk, i, 1.0)])
     return out.reshape(m.shape)
+
+
+def fabs(g):
+    """elementwise absolute value (GVars keep their error)"""
+    if isinstance(g, GVar):
+        return abs(g)
+    if _is_bd(g):
+        return BufferDict(g, buf=fabs(g.buf))
+    a = _np.asarray(g)
+    if a.dtype != object:
+        return _np.fabs(a)
+    out = _np.empty(a.shape, dtype=object)
+    for idx in _np.ndindex(a.shape):
+        out[idx] = abs(a[idx])
+    return out if out.shape != () else out.item()
 
 
 def _is_bd(g):
@@ -310,6 +374,8 @@ class BufferDict(dict):
         lbatch_buf = kargs.pop('lbatch_buf', None)
         rbatch_buf = kargs.pop('rbatch_buf', None)
         src = args[0] if args else None
+        if src is None and kargs:               # BufferDict(a=..., b=...)
+            src, kargs = kargs, {}
         if src is None:
             self._buf = _np.zeros(0, float)
             return
@@ -419,6 +485,19 @@ class BufferDict(dict):
 
     __str__ = __repr__
 
+    def __truediv__(self, other):
+        return BufferDict(self, buf=self.buf / other)
+
+    def __mul__(self, other):
+        return BufferDict(self, buf=self.buf * other)
+
+    def slice(self, k):
+        sl = self._slices[k][0]
+        return sl if isinstance(sl, slice) else slice(sl, sl + 1)
+
+    def all_keys(self):
+        return list(self.keys())
+
     @property
     def buf(self):
         return self._buf
@@ -520,3 +599,158 @@ def gvar_factory():
 
 def tabulate(g, **kargs):
     return '\n'.join('%s  %s' % (k, g[k]) for k in g) if hasattr(g, 'keys') else str(g)
+
+
+class PDF(object):
+    r""" Gaussian probability density of a collection of GVars (the part of ``gvar.PDF`` that
+    ``PDFIntegrator`` uses, reference ``src/vegas/__init__.py:496-503, 599-606, 1163-1183``).
+
+    The parameters are written ``p = mean + chiv . vec_sig`` with ``chiv`` a vector of independent
+    unit normal variables along the principal axes of the correlation matrix (eigenvalues below
+    ``svdcut`` times the largest are raised to that floor).  ``dp_dchiv`` is the Jacobian of the map.
+    """
+
+    def __init__(self, g, svdcut=1e-12):
+        if isinstance(g, PDF):
+            self.__dict__.update(g.__dict__)
+            return
+        if hasattr(g, 'keys'):
+            self.g = asbufferdict(g)
+            self.shape = None
+            flat = _np.asarray(self.g.buf, dtype=object).reshape(-1)
+        else:
+            self.g = _np.asarray(g, dtype=object)
+            self.shape = self.g.shape
+            flat = self.g.reshape(-1)
+        self.size = int(flat.size)
+        self.svdcut = svdcut
+        self.meanflat = _np.asarray(mean(flat), dtype=float).reshape(-1)
+        cov = _np.asarray(evalcov(flat), dtype=float).reshape(self.size, self.size)
+        if _np.any(cov.diagonal() <= 0):
+            raise ValueError('PDF needs parameters with non-zero standard deviations')
+        svd = SVD(cov, svdcut=abs(svdcut) if svdcut else None, rescale=True)
+        self.vec_sig = svd.decomp(1)                 # rows w_i: cov = sum_i w_i w_i^T
+        self.vec_isig = svd.decomp(-1)               # rows v_i: cov^-1 = sum_i v_i v_i^T
+        self.dp_dchiv = float(_np.prod(svd.val ** 0.5) / _np.prod(svd.D))
+        self.log_gnorm = float(-0.5 * self.size * _np.log(2 * _np.pi) - _np.log(self.dp_dchiv))
+
+    # --- maps between the parameters and the unit-normal variables
+    def pflat(self, chiv, mode=None):
+        chiv = _np.asarray(chiv, dtype=float)
+        if mode == 'rbatch':
+            return self.meanflat[:, None] + self.vec_sig.T.dot(chiv)
+        return self.meanflat + chiv.dot(self.vec_sig)            # None: chiv[i]; 'lbatch': chiv[n, i]
+
+    def chiv(self, p, mode=None):
+        pf = self._flatten(p, mode)
+        if mode == 'rbatch':
+            return self.vec_isig.dot(pf - self.meanflat[:, None])
+        return (pf - self.meanflat).dot(self.vec_isig.T)
+
+    def _flatten(self, p, mode=None):
+        if hasattr(p, 'keys'):
+            p = asbufferdict(p)
+            b = _np.asarray(p.buf, dtype=float)
+            return b
+        p = _np.asarray(p, dtype=float)
+        if mode == 'lbatch':
+            return p.reshape(p.shape[0], -1)
+        if mode == 'rbatch':
+            return p.reshape(-1, p.shape[-1])
+        return p.reshape(-1)
+
+    def _unflatten(self, pflat, mode=None):
+        pflat = _np.asarray(pflat)
+        if self.shape is None:
+            if mode == 'lbatch':
+                return BufferDict(self.g, lbatch_buf=pflat)
+            if mode == 'rbatch':
+                return BufferDict(self.g, rbatch_buf=pflat)
+            return BufferDict(self.g, buf=pflat)
+        if mode == 'lbatch':
+            return pflat.reshape((pflat.shape[0],) + self.shape)
+        if mode == 'rbatch':
+            return pflat.reshape(self.shape + (pflat.shape[-1],))
+        return pflat.reshape(self.shape) if self.shape != () else pflat.reshape(-1)[0]
+
+    def sample(self, nbatch=None, mode=None):
+        """random parameter values drawn from the distribution, in the layout of ``g``"""
+        if nbatch is None or mode is None:
+            return self._unflatten(self.pflat(RNG.normal(size=self.size)))
+        if mode == 'lbatch':
+            return self._unflatten(self.pflat(RNG.normal(size=(nbatch, self.size)), mode='lbatch'), mode='lbatch')
+        return self._unflatten(self.pflat(RNG.normal(size=(self.size, nbatch)), mode='rbatch'), mode='rbatch')
+
+    def logpdf(self, p, mode=None):
+        c = self.chiv(p, mode)
+        return self.log_gnorm - 0.5 * _np.sum(c * c, axis=0 if mode == 'rbatch' else -1)
+
+    def pdf(self, p, mode=None):
+        return _np.exp(self.logpdf(p, mode))
+
+    def __call__(self, p, mode=None):
+        return self.pdf(p, mode)
+
+
+class _Loc(object):
+    """location with its lower and upper widths"""
+
+    def __init__(self, loc, minus, plus):
+        self.loc, self.minus, self.plus = loc, minus, plus
+
+    def __str__(self):
+        return '%s +/- %s/%s' % (self.loc, self.plus, self.minus)
+
+
+class PDFStatistics(object):
+    r""" Mean, standard deviation, skewness and excess kurtosis of a one-dimensional distribution from
+    its moments ``[<x>, <x^2>, <x^3>, <x^4>]`` (GVars; the last two optional), and its median with the
+    15.87 % / 84.13 % interval from a histogram ``(bins, count)`` (``count`` includes the underflow and
+    overflow bins).  The real ``gvar.PDFStatistics`` also fits split normal distributions to the
+    histogram; here ``splitnormal`` is the percentile-matched approximation (same object as ``median``).
+    """
+
+    def __init__(self, moments=None, histogram=None, prefix='   '):
+        self.prefix = prefix
+        self.mean = self.sdev = self.skew = self.ex_kurt = None
+        self.median = self.splitnormal = None
+        if moments is not None:
+            mom = list(moments)
+            self.mean = mom[0]
+            var_ = mom[1] - mom[0] * mom[0]
+            self.sdev = fabs(var_) ** 0.5
+            if len(mom) > 2:
+                self.skew = (mom[2] - 3. * self.mean * var_ - self.mean ** 3) / self.sdev ** 3
+            if len(mom) > 3:
+                m4 = mom[3] - 4. * mom[2] * self.mean + 6. * mom[1] * self.mean ** 2 - 3. * self.mean ** 4
+                self.ex_kurt = m4 / (var_ * var_) - 3.
+        if histogram is not None:
+            bins, count = histogram
+            self.bins = _np.asarray(bins, dtype=float)
+            prob = count / _np.sum(count)
+            self.prob = prob
+            cum = _np.cumsum(prob[:-1])                  # probability below bins[i], i = 0..nbin
+
+            def quantile(qv):
+                cm = mean(cum)
+                i = int(_np.searchsorted(cm, qv))
+                i = min(max(i, 1), len(cm) - 1)
+                x0, x1 = self.bins[i - 1], self.bins[i]
+                c0, c1 = cum[i - 1], cum[i]
+                return x0 + (x1 - x0) * ((qv - c0) / (c1 - c0))
+            med = quantile(0.5)
+            self.median = _Loc(med, med - quantile(0.158655253931457), quantile(0.841344746068543) - med)
+            self.splitnormal = self.median
+
+    def __str__(self):
+        out = []
+        if self.mean is not None:
+            line = self.prefix + 'mean = %s   sdev = %s' % (self.mean, self.sdev)
+            if self.skew is not None:
+                line += '   skew = %s' % (self.skew,)
+            if self.ex_kurt is not None:
+                line += '   ex_kurt = %s' % (self.ex_kurt,)
+            out.append(line)
+        if self.median is not None:
+            out.append(self.prefix + 'median: %s' % (self.median,))
+        return '\n'.join(out)

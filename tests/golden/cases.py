@@ -50,3 +50,18 @@ RESTRATIFY = {
     'damped': dict(limits=4 * [[0., 1.]], f='two_axes', kw=dict(neval=20000), nitn_adapt=3, nitn=1, ndy=4,
                    opt=dict(gamma=0.5, below_avg_nstrat=2), seed=32),
 }
+
+
+# ---- PDFIntegrator (tests/golden/make_golden_pdf.py -> ref_pdf.npz; replayed by tests/test_gpu_golden.py)
+PDF_CASES = {
+    'corr3': dict(mean=[1.0, 2.0, -0.5], cov=[[1.0, 0.3, -0.2], [0.3, 4.0, 0.5], [-0.2, 0.5, 0.25]], scale=1.0, limit=100.,
+                  adapt_to_pdf=True, seed=321, nitn=3, kw=dict(neval=3000)),
+    'corr3_fpdf': dict(mean=[1.0, 2.0, -0.5], cov=[[1.0, 0.3, -0.2], [0.3, 4.0, 0.5], [-0.2, 0.5, 0.25]], scale=1.5, limit=20.,
+                       adapt_to_pdf=False, seed=322, nitn=2, kw=dict(neval=2000, alpha=0.2)),
+}
+
+
+def pdf_f(p):
+    """dictionary-valued lbatch function of the parameters p[i, d]"""
+    import numpy as np
+    return dict(a=p[:, 0] + p[:, 1], b=np.stack([p[:, 1] * p[:, 2], p[:, 0] ** 2], axis=1))

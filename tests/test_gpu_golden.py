@@ -93,3 +93,57 @@ def test_ran_array_generator_feeds_random_batch():
     # u = 1/2 puts every sample at the centre of its stratum on the (still uniform) grid
     centres0 = (np.arange(ns[0]) + 0.5) / ns[0]
     assert np.allclose(np.unique(np.round(xs[:, 0], 12)), np.round(centres0, 12))
+
+
+# ---------------------------------------------------------------------------------------------
+# PDFIntegrator against the unmodified reference (tests/golden/make_golden_pdf.py -> ref_pdf.npz)
+# ---------------------------------------------------------------------------------------------
+from tests.golden.cases import PDF_CASES, pdf_f      # noqa: E402
+
+
+@pytest.mark.parametrize('name', sorted(PDF_CASES))
+def test_pdfintegrator_replays_reference_fixture(name):
+    """the reference's ``PDFIntegrator`` recorded: its tan-map grid (``_make_map`` from ``gvar.ranseed(1)``), its
+    integrand ``_f_lbatch`` on a fixed batch of theta, and three iterations on an injected uniform stream.
+    Ours: the same construction (map adapted by the CUDA map kernels), ``k_pdf_map`` / ``k_pdf_weight`` on
+    the same theta, and the same stream through sampler -> device wrapper -> reduce."""
+    import torch
+    from vegas_b200._gv import gv
+    from vegas_b200._pdf import _DevicePDFIntegrand
+    spec = PDF_CASES[name]
+    G = np.load(os.path.join(HERE, 'golden', 'ref_pdf.npz'))
+    gv.ranseed(1)
+    rng = np.random.default_rng(spec['seed'])
+    rec = Recorder()
+    sums = []
+    g = gv.gvar(spec['mean'], spec['cov'])
+    integ = vegas.PDFIntegrator(g, scale=spec['scale'], limit=spec['limit'], adapt_to_pdf=spec['adapt_to_pdf'],
+                                ran_array_generator=lambda shape: rng.random(shape), analyzer=rec, **spec['kw'])
+    integ._trace = sums.append
+    np.testing.assert_allclose(integ.param_pdf.vec_sig, G[name + '_vec_sig'], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(integ.param_pdf.dp_dchiv, float(G[name + '_dp_dchiv']), rtol=1e-13)
+    # ten adaptations of the 1-d map on 2000 points: CUDA map / add_training_data + host adapt vs the reference's
+    np.testing.assert_allclose(integ.map.grid, G[name + '_map0'], rtol=1e-10, atol=1e-12)
+    # the integrand on the recorded theta
+    f = vegas.lbatchintegrand(pdf_f)
+    fstd = integ._make_std_integrand(f, integ.param_sample)
+    dev = _DevicePDFIntegrand(integ, fstd, None)
+    rows = dev(torch.from_numpy(G[name + '_theta']).cuda()).cpu().numpy()
+    assert list(G[name + '_keys']) == (["pdf", "('f(p)*pdf', 'a')", "('f(p)*pdf', 'b')"] if spec['adapt_to_pdf']
+                                       else ["('f(p)*pdf', 'a')", "('f(p)*pdf', 'b')", "pdf"])
+    np.testing.assert_allclose(rows, G[name + '_rows'], rtol=1e-12, atol=1e-300)
+    # the iterations, from the reference's own initial map
+    integ.set(map=vegas.AdaptiveMap(G[name + '_map0']))
+    r = integ(f, nitn=spec['nitn'])
+    assert len(rec.rows) == spec['nitn']
+    for i, (row, raw) in enumerate(zip(rec.rows, sums)):
+        assert row['last_neval'] == int(G['%s_itn%d_last_neval' % (name, i)]), i
+        np.testing.assert_allclose(raw['mean'], G['%s_itn%d_mean' % (name, i)], rtol=1e-11, atol=1e-300)
+        cov = G['%s_itn%d_cov' % (name, i)]
+        np.testing.assert_allclose(raw['var'], cov, rtol=1e-9, atol=1e-16 * np.abs(cov).max())
+        np.testing.assert_allclose(row['sigf'], G['%s_itn%d_sigf' % (name, i)], rtol=1e-8, atol=1e-300)
+        np.testing.assert_allclose(row['grid'], G['%s_itn%d_grid' % (name, i)], rtol=1e-10, atol=1e-13)
+    flat = np.asarray(r.buf, dtype=object).reshape(-1)
+    np.testing.assert_allclose([x.mean for x in flat], G[name + '_result_mean'], rtol=1e-9)
+    np.testing.assert_allclose([x.sdev for x in flat], G[name + '_result_sdev'], rtol=1e-6)
+    np.testing.assert_allclose([r.pdfnorm.mean, r.pdfnorm.sdev], G[name + '_pdfnorm'], rtol=1e-6)
