@@ -127,8 +127,13 @@ def _ptr(t):
 
 
 def _stream():
+    """raw handle of torch's current CUDA stream (the private fast accessor when torch has it: the public
+    ``torch.cuda.current_stream()`` builds a Stream object, ~20 us a call -- more than a kernel launch)"""
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    try:
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    except AttributeError:
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 class Context(object):

@@ -535,12 +535,19 @@ class PDFAnalyzer(object):
         if self.save is None and self.saveall is None:
             return
         ans = PDFIntegrator._make_ans(results) if len(list(results.keys())) > 1 else results
+        rank, world = self.pdfinteg._rank_world()
+        # (pickling the integrator gathers sigf from every rank: all ranks pickle, rank 0 writes)
         for target, obj in ((self.save, ans), (self.saveall, (ans, self.pdfinteg))):
+            if target is None:
+                continue
+            payload = pickle.dumps(obj)
+            if world > 1 and rank != 0:
+                continue
             if isinstance(target, str):
                 with open(target, 'wb') as ofile:
-                    pickle.dump(obj, ofile)
-            elif target is not None:
-                pickle.dump(obj, target)
+                    ofile.write(payload)
+            else:
+                target.write(payload)
 
 
 def _eval_on_host(std, p):

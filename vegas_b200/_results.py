@@ -12,83 +12,149 @@ from ._gv import gv
 from ._map import TINY, EPSILON
 
 
-def _summary_table(itn_results, make_acc, first, weighted):
-    """iteration-by-iteration table shared by the three result classes"""
-    acc = make_acc()
-    linedata = []
-    for i, res in enumerate(itn_results):
-        acc.add(res)
-        itn = '%3d' % (i + 1)
-        integral = '%-15s' % first(res)
-        wgtavg = '%-15s' % first(acc)
-        chi2dof = '%8.2f' % (acc.chi2 / acc.dof if i != 0 else 0.0)
-        Q = '%8.2f' % (acc.Q if i != 0 else 1.0)
-        linedata.append((itn, integral, wgtavg, chi2dof, Q))
-    nchar = 5 * [0]
-    for data in linedata:
-        for i, d in enumerate(data):
-            nchar[i] = max(nchar[i], len(d))
-    fmt = '%%%ds   %%-%ds %%-%ds %%%ds %%%ds\n' % tuple(nchar)
-    ans = fmt % ('itn', 'integral', 'wgt average' if weighted else 'average', 'chi2/dof', 'Q')
-    ans += len(ans[:-1]) * '-' + '\n'
-    for data in linedata:
-        ans += fmt % data
-    return ans
+# --------------------------------------------------------------------------- the averaging core
+class _ScalarAverage(object):
+    """running average of scalar estimates (mean_i, var_i): inverse-variance weighted, or plain
+    (formulas of ``_vegas.pyx:2392-2410``).  O(1) per estimate: running sums, not lists re-summed."""
 
+    def __init__(self, weighted):
+        self.weighted = bool(weighted)
+        self.means, self.weights = [], []          # kept for chi2 (computed on demand)
+        self.sw = self.swm = 0.0                   # weighted: sum w, sum w m
+        self.msum = self.varsum = 0.0              # unweighted
+        self.n = 0
 
-class RAvg(gv.GVar):
-    r""" Running average of scalar-valued Monte Carlo estimates (``_vegas.pyx:2276-2451``).
-
-    Estimates are weighted by their inverse variances if ``weighted=True``; otherwise straight,
-    unweighted averages are used. """
-
-    def __init__(self, weighted=True, itn_results=None, sum_neval=0, _rescale=True):
-        self.rescale = None
-        if weighted:
-            self._wlist = []
-            self.weighted = True
-        else:
-            self._msum = 0.
-            self._varsum = 0.
-            self._n = 0
-            self.weighted = False
-        self._mlist = []
-        self.itn_results = []
-        if itn_results is None:
-            super(RAvg, self).__init__(*gv.gvar(0., 0.).internaldata)
-        else:
-            if isinstance(itn_results, bytes):
-                itn_results = gv.loads(itn_results)
-            for r in itn_results:
-                self.add(r)
-        self.sum_neval = sum_neval
-
-    def extend(self, ravg):
-        r""" Merge results from :class:`RAvg` object ``ravg`` after results currently in ``self``. """
-        for r in ravg.itn_results:
-            self.add(r)
-        self.sum_neval += ravg.sum_neval
-
-    def __reduce_ex__(self, protocol):
-        return (RAvg, (self.weighted, gv.dumps(self.itn_results, protocol=protocol), self.sum_neval))
-
-    @property
-    def chi2(self):
-        "*chi**2* of weighted average."
-        if len(self.itn_results) <= 1:
-            return 0.0
-        wavg = self.mean
+    def add(self, mean, var):
+        """returns (average, its variance) after taking in one estimate"""
+        self.n += 1
+        self.means.append(mean)
         if self.weighted:
-            ans = 0.0
-            for m, w in zip(self._mlist, self._wlist):
-                ans += (wavg - m) ** 2 * w
-            return ans
-        return np.sum([(m - wavg) ** 2 for m in self._mlist]) / (self._varsum / self._n)
+            w = 1. / (var if var > TINY else TINY)
+            self.weights.append(w)
+            self.sw += w
+            self.swm += w * mean
+            return self.swm / self.sw, 1. / self.sw
+        self.msum += mean
+        self.varsum += var
+        return self.msum / self.n, self.varsum / self.n ** 2
+
+    def chi2(self, avg):
+        if self.n <= 1:
+            return 0.0
+        if self.weighted:
+            return float(sum((avg - m) ** 2 * w for m, w in zip(self.means, self.weights)))
+        return float(sum((m - avg) ** 2 for m in self.means) / (self.varsum / self.n))
 
     @property
     def dof(self):
-        "Number of degrees of freedom in weighted average."
-        return len(self.itn_results) - 1
+        return self.n - 1
+
+
+class _VectorAverage(object):
+    """running average of vector estimates (mean_i[n], cov_i[n, n]) (formulas of ``_vegas.pyx:2801-2846``).
+
+    Weighted: every estimate contributes ``W_i = svd-protected decomposition of cov_i^-1`` (rows ``w`` with
+    ``cov_i^-1 = sum_w w w^T`` over the modes kept); the average is ``C sum_i W_i^T W_i m_i`` with
+    ``C = (sum_i W_i^T W_i)^-1``, again SVD-protected.  The two sums are kept running.  Estimates are divided
+    by ``scale`` first (``rescale``: fixed at the first estimate), which keeps the matrices well conditioned
+    when components differ by orders of magnitude."""
+
+    def __init__(self, weighted, rescale):
+        self.weighted = bool(weighted)
+        self.rescale = rescale                    # None | True | array of typical values
+        self.scale = None                         # set at the first estimate (weighted only)
+        self.means, self.ws = [], []
+        self.S = self.b = None                    # weighted: sum W^T W, sum W^T W m
+        self.msum = self.covsum = 0.0             # unweighted
+        self.n = 0
+        self._invw = None
+
+    @staticmethod
+    def decomp(matrix, rescale=False):
+        " rows w with matrix^-1 = sum w w^T, modes with tiny eigenvalues dropped "
+        return gv.SVD(matrix, svdcut=-EPSILON * len(matrix) * 1e4, rescale=rescale).decomp(-1)
+
+    def _set_scale(self, mean, sdev):
+        if self.rescale is None:
+            self.scale = 1.
+            return
+        sc = np.fabs(mean if self.rescale is True else np.asarray(gv.mean(self.rescale.flat[:]), float))
+        sc = np.array(sc, dtype=float)
+        big = sdev > sc
+        sc[big] = sdev[big]
+        sc[sc <= 0] = 1.
+        self.scale = sc
+
+    def add(self, mean, cov):
+        """returns (average[n], covariance[n, n]) after taking in one estimate"""
+        self.n += 1
+        if not self.weighted:
+            self.means.append(mean)
+            self.msum = self.msum + mean
+            self.covsum = self.covsum + cov
+            self._invw = None
+            return self.msum / self.n, self.covsum / self.n ** 2
+        if self.scale is None:
+            self._set_scale(mean, np.sqrt(np.fabs(np.diag(cov))))
+        mean = mean / self.scale
+        cov = cov / np.outer(self.scale, self.scale) if np.ndim(self.scale) else np.array(cov, float)
+        d = np.diag_indices(len(cov))
+        cov[d] = np.where(cov[d] <= 0, TINY, cov[d])
+        w = self.decomp(cov)
+        self.means.append(mean)
+        self.ws.append(w)
+        wtw = w.T.dot(w)
+        self.S = wtw if self.S is None else self.S + wtw
+        wm = wtw.dot(mean)
+        self.b = wm if self.b is None else self.b + wm
+        invw = self.decomp(self.S)
+        avg_cov = invw.T.dot(invw)
+        avg = avg_cov.dot(self.b)
+        sc = self.scale
+        return avg * sc, avg_cov * (np.outer(sc, sc) if np.ndim(sc) else 1.)
+
+    def chi2(self, avg):
+        if self.n <= 1:
+            return 0.0
+        ans = 0.0
+        if self.weighted:
+            avg = avg / self.scale
+            for w, m in zip(self.ws, self.means):
+                ans += float(np.sum(w.dot(m - avg) ** 2))
+            return ans
+        if self._invw is None:
+            self._invw = self.decomp(self.covsum / self.n)
+        for m in self.means:
+            ans += float(np.sum(self._invw.dot(avg - m) ** 2))
+        return ans
+
+    def dof(self, size):
+        if self.n <= 1:
+            return 0
+        if not self.weighted:
+            if self._invw is None:
+                self._invw = self.decomp(self.covsum / self.n)
+            return (self.n - 1) * len(self._invw)
+        return int(sum(len(w) for w in self.ws)) - size
+
+
+def _rescale_arg(rescale, weighted):
+    if rescale is False or rescale is None or not weighted:
+        return None
+    if rescale is True:
+        return True
+    return gv.asbufferdict(rescale) if hasattr(rescale, 'keys') else np.asarray(rescale)
+
+
+class _RunningAverage(object):
+    """what RAvg, RAvgArray and RAvgDict share: the list of per-iteration results, the neval count, and
+    the statistics of the average (chi2, dof, Q) from the core in ``self._avg``"""
+
+    def extend(self, ravg):
+        r""" Merge results from ``ravg`` after results currently in ``self``. """
+        for r in ravg.itn_results:
+            self.add(r)
+        self.sum_neval += ravg.sum_neval
 
     @property
     def nitn(self):
@@ -96,52 +162,88 @@ class RAvg(gv.GVar):
         return len(self.itn_results)
 
     @property
-    def Q(self):
-        "*Q* or *p-value* of weighted average's *chi**2*."
-        return gv.gammaQ(self.dof / 2., self.chi2 / 2.) if self.dof > 0 and self.chi2 >= 0 else float('nan')
-
-    @property
     def avg_neval(self):
         "Average number of integrand evaluations per iteration."
         return self.sum_neval / self.nitn if self.nitn > 0 else 0
 
-    def converged(self, rtol, atol):
-        return self.sdev < atol + rtol * abs(self.mean)
+    @property
+    def Q(self):
+        "*Q* or *p-value* of weighted average's *chi**2*."
+        dof, chi2 = self.dof, self.chi2
+        return gv.gammaQ(dof / 2., chi2 / 2.) if dof > 0 and chi2 >= 0 else float('nan')
+
+    def _table(self, fresh, first, weighted, extended):
+        """iteration-by-iteration table: each result next to the running average up to it"""
+        acc, rows = fresh(), []
+        for i, res in enumerate(self.itn_results):
+            acc.add(res)
+            rows.append(('%3d' % (i + 1), '%-15s' % first(res), '%-15s' % first(acc),
+                         '%8.2f' % (acc.chi2 / acc.dof if i != 0 else 0.0), '%8.2f' % (acc.Q if i != 0 else 1.0)))
+        width = [max(len(r[c]) for r in rows) if rows else 0 for c in range(5)]
+        fmt = '%%%ds   %%-%ds %%-%ds %%%ds %%%ds\n' % tuple(width)
+        out = fmt % ('itn', 'integral', 'wgt average' if weighted else 'average', 'chi2/dof', 'Q')
+        out += len(out[:-1]) * '-' + '\n'
+        for r in rows:
+            out += fmt % r
+        if extended and np.size(self.itn_results[0]) > 1:
+            out += '\n' + gv.tabulate(self) + '\n'
+        return out
+
+
+class RAvg(_RunningAverage, gv.GVar):
+    r""" Running average of scalar-valued Monte Carlo estimates (API of ``_vegas.pyx:2276-2451``).
+
+    Estimates are weighted by their inverse variances if ``weighted=True``; otherwise straight,
+    unweighted averages are used. """
+
+    def __init__(self, weighted=True, itn_results=None, sum_neval=0, _rescale=True):
+        self.rescale = None
+        self.weighted = bool(weighted)
+        self._avg = _ScalarAverage(weighted)
+        self.itn_results = []
+        gv.GVar.__init__(self, *gv.gvar(0., 0.).internaldata)
+        if itn_results is not None:
+            for r in (gv.loads(itn_results) if isinstance(itn_results, bytes) else itn_results):
+                self.add(r)
+        self.sum_neval = sum_neval
+
+    def __reduce_ex__(self, protocol):
+        return (RAvg, (self.weighted, gv.dumps(self.itn_results, protocol=protocol), self.sum_neval))
 
     def add(self, g):
         r""" Add estimate ``g`` to the running average. """
         self.itn_results.append(g)
         if isinstance(g, gv.GVarRef):
             return
-        self._mlist.append(g.mean)
-        if self.weighted:
-            self._wlist.append(1 / (g.var if g.var > TINY else TINY))
-            var = 1. / np.sum(self._wlist)
-            sdev = np.sqrt(var)
-            mean = np.sum([w * m for w, m in zip(self._wlist, self._mlist)]) * var
-            super(RAvg, self).__init__(*gv.gvar(mean, sdev).internaldata)
-        else:
-            self._msum += g.mean
-            self._varsum += g.var
-            self._n += 1
-            mean = self._msum / self._n
-            var = self._varsum / self._n ** 2
-            super(RAvg, self).__init__(*gv.gvar(mean, np.sqrt(var)).internaldata)
+        mean, var = self._avg.add(g.mean, g.var)
+        gv.GVar.__init__(self, *gv.gvar(mean, np.sqrt(var)).internaldata)
+
+    chi2 = property(lambda self: self._avg.chi2(self.mean), None, None, "*chi**2* of weighted average.")
+    dof = property(lambda self: len(self.itn_results) - 1, None, None, "Number of degrees of freedom in weighted average.")
+
+    def converged(self, rtol, atol):
+        return self.sdev < atol + rtol * abs(self.mean)
 
     def summary(self, extended=False, weighted=None):
         r""" Assemble summary of results, iteration-by-iteration, into a string. """
-        if weighted is None:
-            weighted = self.weighted
-        return _summary_table(self.itn_results, lambda: RAvg(weighted=weighted), lambda r: r, weighted)
+        weighted = self.weighted if weighted is None else weighted
+        return self._table(lambda: RAvg(weighted=weighted), lambda r: r, weighted, False)
 
 
-class RAvgArray(np.ndarray):
-    r""" Running average of array-valued Monte Carlo estimates (``_vegas.pyx:2579-2879``): an
-    ``ndarray`` of Gaussian variables; estimates are combined with their inverse covariance
-    matrices (SVD-protected) if ``weighted=True``. """
+def _rebuild_array(shape, weighted, itn_results, sum_neval, rescale):
+    return RAvgArray(shape, weighted=weighted, itn_results=itn_results, sum_neval=sum_neval, rescale=rescale)
+
+
+class RAvgArray(_RunningAverage, np.ndarray):
+    r""" Running average of array-valued Monte Carlo estimates (API of ``_vegas.pyx:2579-2879``): an
+    ``ndarray`` of Gaussian variables; estimates are combined with their inverse covariance matrices
+    (SVD-protected) if ``weighted=True``.  ``rescale``: integrals are divided by ``rescale`` (``True``: by
+    the first estimate) before weighted averages are taken. """
 
     def __new__(subtype, shape=None, dtype=object, buffer=None, offset=0, strides=None, order=None,
                 weighted=True, itn_results=None, sum_neval=0, rescale=True):
+        if isinstance(itn_results, bytes):
+            itn_results = gv.loads(itn_results)
         if shape is None and (itn_results is None or len(itn_results) < 1):
             raise ValueError('must specificy shape or itn_results')
         obj = np.ndarray.__new__(
@@ -149,146 +251,32 @@ class RAvgArray(np.ndarray):
             dtype=object, buffer=buffer, offset=offset, strides=strides, order=order)
         if buffer is None:
             obj.flat = np.array(obj.size * [gv.gvar(0, 0)])
+        obj.weighted = bool(weighted)
+        obj.rescale = _rescale_arg(rescale, weighted)
+        obj._avg = _VectorAverage(weighted, obj.rescale)
         obj.itn_results = []
-        obj._mlist = []
-        if rescale is False or rescale is None or not weighted:
-            obj.rescale = None
-        elif rescale is True:
-            obj.rescale = True
-        elif hasattr(rescale, 'keys'):
-            obj.rescale = gv.asbufferdict(rescale)
-        else:
-            obj.rescale = np.asarray(rescale)
-        if weighted:
-            obj.weighted = True
-            obj._wlist = []
-        else:
-            obj._msum = 0.
-            obj._covsum = 0.
-            obj._n = 0
-            obj.weighted = False
         obj.sum_neval = sum_neval
         return obj
 
-    def __reduce_ex__(self, protocol):
-        save = np.array(self.flat[:])
-        self.flat[:] = 0
-        superpickled = super(RAvgArray, self).__reduce__()
-        self.flat[:] = save
-        state = superpickled[2] + (
-            self.weighted, gv.dumps(self.itn_results, protocol=protocol), (self.sum_neval, self.rescale))
-        return (superpickled[0], superpickled[1], state)
-
-    def __setstate__(self, state):
-        super(RAvgArray, self).__setstate__(state[:-3])
-        if isinstance(state[-1], tuple):
-            self.sum_neval, self.rescale = state[-1]
-        else:
-            self.sum_neval, self.rescale = state[-1], True
-        itn_results = gv.loads(state[-2])
-        self.weighted = state[-3]
-        if self.weighted:
-            self._wlist = []
-            self._mlist = []
-        else:
-            self._msum = 0.
-            self._covsum = 0.
-            self._n = 0
-            self._mlist = []
-        self.__dict__.pop('_rescale', None)
-        self.itn_results = []
-        for r in itn_results:
-            self.add(r)
+    def __init__(self, shape=None, dtype=object, buffer=None, offset=0, strides=None, order=None,
+                 weighted=True, itn_results=None, sum_neval=0, rescale=True):
+        if itn_results is not None:
+            for r in (gv.loads(itn_results) if isinstance(itn_results, bytes) else itn_results):
+                self.add(r)
 
     def __array_finalize__(self, obj):
         if obj is None:
             return
-        if getattr(obj, 'weighted', True):
-            self.weighted = True
-            self._wlist = getattr(obj, '_wlist', [])
-        else:
-            self._msum = getattr(obj, '_msum', 0.)
-            self._covsum = getattr(obj, '_covsum', 0.)
-            self._n = getattr(obj, '_n', 0.)
-            self.weighted = False
-        self._mlist = getattr(obj, '_mlist', [])
+        # views and copies share the bookkeeping of the array they come from
+        self.weighted = getattr(obj, 'weighted', True)
+        self.rescale = getattr(obj, 'rescale', True)
+        self._avg = getattr(obj, '_avg', None)
         self.itn_results = getattr(obj, 'itn_results', [])
         self.sum_neval = getattr(obj, 'sum_neval', 0)
-        self.rescale = getattr(obj, 'rescale', True)
 
-    def __init__(self, shape=None, dtype=object, buffer=None, offset=0, strides=None, order=None,
-                 weighted=True, itn_results=None, sum_neval=0, rescale=True):
-        self[:] *= 0
-        if itn_results is not None:
-            if isinstance(itn_results, bytes):
-                itn_results = gv.loads(itn_results)
-            self.itn_results = []
-            for r in itn_results:
-                self.add(r)
-
-    def extend(self, ravg):
-        r""" Merge results from :class:`RAvgArray` object ``ravg`` after results currently in ``self``. """
-        for r in ravg.itn_results:
-            self.add(r)
-        self.sum_neval += ravg.sum_neval
-
-    def _w(self, matrix, rescale=False):
-        " Decompose inverse matrix, with protection against singular matrices. "
-        s = gv.SVD(matrix, svdcut=-EPSILON * len(matrix) * 1e4, rescale=rescale)
-        return s.decomp(-1)
-
-    def converged(self, rtol, atol):
-        return np.all(gv.sdev(self) < atol + rtol * np.abs(gv.mean(self)))
-
-    @property
-    def chi2(self):
-        "*chi**2* of weighted average."
-        if len(self.itn_results) <= 1:
-            return 0.0
-        wavg = np.array(gv.mean(self), dtype=float).reshape((-1,))
-        ans = 0.0
-        if self.weighted:
-            if self.rescale is not None:
-                wavg = wavg / self._rescale
-            for w, m in zip(self._wlist, self._mlist):
-                for wi in w:
-                    ans += wi.dot(m - wavg) ** 2
-            return ans
-        if self._invw is None:
-            self._invw = self._w(self._covsum / self._n)
-        for m in self._mlist:
-            delta = wavg - m
-            for invwi in self._invw:
-                ans += invwi.dot(delta) ** 2
-        return ans
-
-    @property
-    def dof(self):
-        "Number of degrees of freedom in weighted average."
-        if len(self.itn_results) <= 1:
-            return 0
-        if not self.weighted:
-            if self._invw is None:
-                self._invw = self._w(self._covsum / self._n)
-            return (len(self.itn_results) - 1) * len(self._invw)
-        return np.sum([len(w) for w in self._wlist]) - self.size
-
-    @property
-    def nitn(self):
-        "Number of iterations."
-        return len(self.itn_results)
-
-    @property
-    def Q(self):
-        "*Q* or *p-value* of weighted average's *chi**2*."
-        if self.dof <= 0 or self.chi2 < 0:
-            return float('nan')
-        return gv.gammaQ(self.dof / 2., self.chi2 / 2.)
-
-    @property
-    def avg_neval(self):
-        "Average number of integrand evaluations per iteration."
-        return self.sum_neval / self.nitn if self.nitn > 0 else 0
+    def __reduce_ex__(self, protocol):
+        return (_rebuild_array, (self.shape, self.weighted, gv.dumps(self.itn_results, protocol=protocol),
+                                 self.sum_neval, self.rescale))
 
     def add(self, g):
         r""" Add estimate ``g`` to the running average. """
@@ -296,94 +284,57 @@ class RAvgArray(np.ndarray):
         self.itn_results.append(g)
         if g.size > 1 and isinstance(g.flat[0], gv.GVarRef):
             return
-        g = g.reshape((-1,))
-        if self.weighted:
-            if '_rescale' not in self.__dict__:
-                if self.rescale is not None:
-                    self._rescale = np.fabs(gv.mean(g if self.rescale is True else self.rescale.flat[:]))
-                    gsdev = gv.sdev(g)
-                    idx = gsdev > self._rescale
-                    self._rescale[idx] = gsdev[idx]
-                    self._rescale[self._rescale <= 0] = 1.
-                else:
-                    self._rescale = 1.
-            g = g / self._rescale
-            gmean = gv.mean(g)
-            gcov = gv.evalcov(g)
-            for i in range(len(gcov)):
-                if gcov[i, i] <= 0:
-                    gcov[i, i] = TINY
-            self._mlist.append(gmean)
-            self._wlist.append(self._w(gcov))
-            invcov = np.sum([(w.T).dot(w) for w in self._wlist], axis=0)
-            invw = self._w(invcov)
-            cov = (invw.T).dot(invw)
-            mean = 0.0
-            for m, w in zip(self._mlist, self._wlist):
-                for wj in w:
-                    wj_m = wj.dot(m)
-                    for invwi in invw:
-                        mean += invwi * invwi.dot(wj) * wj_m
-            self[:] = (gv.gvar(mean, cov) * self._rescale).reshape(self.shape)
-        else:
-            gmean = gv.mean(g)
-            gcov = gv.evalcov(g)
-            self._mlist.append(gmean)
-            self._msum += gmean
-            self._covsum += gcov
-            self._invw = None
-            self._n += 1
-            mean = self._msum / self._n
-            cov = self._covsum / (self._n ** 2)
-            self[:] = gv.gvar(mean, cov).reshape(self.shape)
+        g = g.reshape(-1)
+        if self._avg is None:
+            self._avg = _VectorAverage(self.weighted, self.rescale)
+        mean, cov = self._avg.add(np.asarray(gv.mean(g), float), np.array(gv.evalcov(g), float))
+        self[...] = gv.gvar(mean, cov).reshape(self.shape)
+
+    @property
+    def chi2(self):
+        "*chi**2* of weighted average."
+        return self._avg.chi2(np.array(gv.mean(self), dtype=float).reshape(-1)) if len(self.itn_results) > 1 else 0.0
+
+    @property
+    def dof(self):
+        "Number of degrees of freedom in weighted average."
+        return self._avg.dof(self.size) if len(self.itn_results) > 1 else 0
+
+    def converged(self, rtol, atol):
+        return np.all(gv.sdev(self) < atol + rtol * np.abs(gv.mean(self)))
 
     def summary(self, extended=False, weighted=None, rescale=None):
         r""" Assemble summary of results, iteration-by-iteration, into a string. """
-        if weighted is None:
-            weighted = self.weighted
-        if rescale is None:
-            rescale = self.rescale
-        ans = _summary_table(self.itn_results,
-                             lambda: RAvgArray(self.shape, weighted=weighted, rescale=rescale),
-                             lambda r: r.flat[0], weighted)
-        if extended and self.itn_results[0].size > 1:
-            ans += '\n' + gv.tabulate(self) + '\n'
-        return ans
+        weighted = self.weighted if weighted is None else weighted
+        rescale = self.rescale if rescale is None else rescale
+        return self._table(lambda: RAvgArray(self.shape, weighted=weighted, rescale=rescale),
+                           lambda r: r.flat[0], weighted, extended)
 
 
-class RAvgDict(gv.BufferDict):
-    r""" Running average of dictionary-valued Monte Carlo estimates (``_vegas.pyx:2453-2577``); the
-    values share one flat :class:`RAvgArray`. """
+class RAvgDict(_RunningAverage, gv.BufferDict):
+    r""" Running average of dictionary-valued Monte Carlo estimates (API of ``_vegas.pyx:2453-2577``); the
+    values share one flat :class:`RAvgArray` (``rarray``). """
 
     def __init__(self, dictionary=None, weighted=True, itn_results=None, sum_neval=0, rescale=True):
         if isinstance(itn_results, bytes):
             itn_results = gv.loads(itn_results)
         if dictionary is None and (itn_results is None or len(itn_results) < 1):
             raise ValueError('must specificy dictionary or itn_results')
-        super(RAvgDict, self).__init__(dictionary if dictionary is not None else itn_results[0])
+        gv.BufferDict.__init__(self, dictionary if dictionary is not None else itn_results[0])
         self.rarray = RAvgArray(shape=(self.size,), weighted=weighted, rescale=rescale)
         self.buf = np.asarray(self.rarray)
         self.itn_results = []
         self.weighted = weighted
-        if itn_results is not None:
-            for r in itn_results:
-                self.add(r)
-        self.sum_neval = sum_neval
-
-    def extend(self, ravg):
-        r""" Merge results from :class:`RAvgDict` object ``ravg`` after results currently in ``self``. """
-        for r in ravg.itn_results:
+        for r in (itn_results or []):
             self.add(r)
-        self.sum_neval += ravg.sum_neval
+        self.sum_neval = sum_neval
 
     def __reduce_ex__(self, protocol):
         return (RAvgDict, (None, self.weighted, gv.dumps(self.itn_results, protocol=protocol),
                            self.sum_neval, self.rescale))
 
-    def converged(self, rtol, atol):
-        return np.all(gv.sdev(self.buf) < atol + rtol * np.abs(gv.mean(self.buf)))
-
     def add(self, g):
+        r""" Add estimate ``g`` (a dictionary with this dictionary's keys) to the running average. """
         if isinstance(g, gv.BufferDict):
             newg = gv.BufferDict(g)
         else:
@@ -396,25 +347,30 @@ class RAvgDict(gv.BufferDict):
         self.itn_results.append(newg)
         self.rarray.add(newg.buf)
 
+    chi2 = property(lambda self: self.rarray.chi2, None, None, "*chi**2* of weighted average.")
+    dof = property(lambda self: self.rarray.dof, None, None, "Number of degrees of freedom in weighted average.")
+    rescale = property(lambda self: self.rarray.rescale, None, None,
+                       "Integrals divided by ``rescale`` before doing weighted averages.")
+
+    def converged(self, rtol, atol):
+        return np.all(gv.sdev(self.buf) < atol + rtol * np.abs(gv.mean(self.buf)))
+
     def summary(self, extended=False, weighted=None, rescale=None):
         r""" Assemble summary of results, iteration-by-iteration, into a string. """
-        if weighted is None:
-            weighted = self.weighted
-        if rescale is None:
-            rescale = self.rarray.rescale
+        weighted = self.weighted if weighted is None else weighted
+        rescale = self.rarray.rescale if rescale is None else rescale
         ans = self.rarray.summary(weighted=weighted, extended=False, rescale=rescale)
         if extended and self.itn_results[0].size > 1:
             ans += '\n' + gv.tabulate(self) + '\n'
         return ans
 
-    chi2 = property(lambda self: self.rarray.chi2, None, None, "*chi**2* of weighted average.")
-    dof = property(lambda self: self.rarray.dof, None, None, "Number of degrees of freedom in weighted average.")
-    nitn = property(lambda self: len(self.itn_results), None, None, "Number of iterations.")
-    Q = property(lambda self: self.rarray.Q, None, None, "*Q* or *p-value* of weighted average's *chi**2*.")
-    avg_neval = property(lambda self: self.sum_neval / self.nitn if self.nitn > 0 else 0, None, None,
-                         "Average number of integrand evaluations per iteration.")
-    rescale = property(lambda self: self.rarray.rescale, None, None,
-                       "Integrals divided by ``rescale`` before doing weighted averages.")
+
+def _dump(payload, outfile):
+    if isinstance(outfile, str):
+        with open(outfile, 'wb') as ofile:
+            ofile.write(payload)
+    else:
+        outfile.write(payload)
 
 
 class VegasResult(object):
@@ -432,21 +388,21 @@ class VegasResult(object):
         else:
             self.result = RAvgArray(self.shape, weighted=weighted)
 
+    # With the hypercube range sharded over ranks every rank holds the same results; only the writer
+    # (rank 0, as in the reference: pyx:2923-2941 with mpi_rank) touches the file.  Pickling the integrator
+    # gathers sigf from all ranks -- a collective -- so it happens on every rank before the writer writes.
+    is_writer = True
+
     def save(self, outfile):
         " pickle current results in ``outfile`` for later use. "
-        if isinstance(outfile, str):
-            with open(outfile, 'wb') as ofile:
-                pickle.dump(self.result, ofile)
-        else:
-            pickle.dump(self.result, outfile)
+        if self.is_writer:
+            _dump(pickle.dumps(self.result), outfile)
 
     def saveall(self, integrator, outfile):
         " pickle current (results,integrator) in ``outfile`` for later use. "
-        if isinstance(outfile, str):
-            with open(outfile, 'wb') as ofile:
-                pickle.dump((self.result, integrator), ofile)
-        else:
-            pickle.dump((self.result, integrator), outfile)
+        payload = pickle.dumps((self.result, integrator))
+        if self.is_writer:
+            _dump(payload, outfile)
 
     def update(self, mean, var, last_neval=None):
         self.result.add(self.integrand.format_result(mean, var))

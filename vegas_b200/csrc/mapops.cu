@@ -157,7 +157,12 @@ void smooth_and_damp(std::vector<double>& w, std::vector<double>& tmp, int64_t n
     }
     for (int64_t i = 0; i < n; ++i) {
         double a = total > 0 ? tmp[i] / total + kTiny : kTiny;
-        if (a > 0 && a <= 0.99999999) a = pow(-(1 - a) / log(a), alpha);
+        if (a > 0 && a <= 0.99999999) {
+            const double x = -(1 - a) / log(a);
+            // pyx:575 raises to the power alpha; the default alpha = 0.5 is a square root (correctly rounded, and
+            // several times cheaper than pow -- this loop is most of an iteration's host time at small neval)
+            a = alpha == 0.5 ? sqrt(x) : (alpha == 1.0 ? x : pow(x, alpha));
+        }
         w[i] = a;
     }
 }
