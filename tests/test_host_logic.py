@@ -503,3 +503,12 @@ def test_rescaling():
         d.add(dict(a=xx, b=1e50 * xx))
     assert str(d['a'] * 1e50) == str(d['b'])
     assert str(gv.evalcorr(d.buf).flat[:]) == str(np.ones(4, float))
+
+
+def test_dimension_limit_is_a_clear_error():
+    """the kernels carry per-axis parameters in fixed-size blocks (VB_MAXD = 32); the reference has no limit, so
+    the difference must surface as a plain message at construction, not as a launch failure"""
+    import pytest
+    with pytest.raises(ValueError, match='up to 32 dimensions'):
+        vegas.Integrator(33 * [[0., 1.]])
+    assert vegas.Integrator(32 * [[0., 1.]]).dim == 32

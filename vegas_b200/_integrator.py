@@ -98,6 +98,7 @@ class Integrator(object):
         self._ctx_map_version = None
         self._ctx_strata = None
         self._sigf_dev = None
+        self._sigf_layout = None     # (nhcube, slab, rank, world) of the device copy of sigf
         self._sigf_host = None
         self._sigf_len = 0
         self._itn_counter = 0
@@ -169,20 +170,20 @@ class Integrator(object):
     def _get_sigf(self):
         if self._sigf_dev is not None:
             local = self._sigf_dev.cpu().numpy()
-            rank, world = self._rank_world()
+            # the layout the device copy was created with (set() may have changed slab / mpi since)
+            nh, slab, rank, world = self._sigf_layout
             if world == 1:
                 return local
-            return self._gather_sigf(local, rank, world)
+            return self._gather_sigf(local, nh, slab, rank, world)
         if self._sigf_host is not None:
             return self._sigf_host
         return np.ones(self._sigf_len, float)
 
     sigf = property(_get_sigf, doc="sigf[h] = |variance of hypercube h|**(beta/2) (host copy)")
 
-    def _gather_sigf(self, local, rank, world):
+    def _gather_sigf(self, local, nh, slab, rank, world):
         import torch
         dist = _dist()
-        nh, slab = int(self.nhcube), self._slab(world)
         counts = [len(_local_cubes(nh, slab, r, world)) for r in range(world)]
         bufs = [torch.empty(c, dtype=torch.float64, device=self._sigf_dev.device) for c in counts]
         dist.all_gather(bufs, self._sigf_dev)
@@ -193,6 +194,12 @@ class Integrator(object):
 
     def _set_map(self, map):
         r""" install new map, create xsample (pyx:1209-1253) """
+        self._set_map_checked(map)
+        if self.map.dim > _lib.MAXDIM:
+            raise ValueError('vegas_b200 integrates up to %d dimensions (the kernels carry per-axis parameters in '
+                             'fixed-size blocks, VB_MAXD); this map has %d' % (_lib.MAXDIM, self.map.dim))
+
+    def _set_map_checked(self, map):
         if isinstance(map, AdaptiveMap):
             self.map = AdaptiveMap(map)
             self.xsample = np.empty(self.map.dim, dtype=float)
@@ -538,6 +545,7 @@ class Integrator(object):
             else:
                 self._sigf_dev = torch.ones(self._nlocal, dtype=torch.float64, device=ctx.device)
             self._sigf_host = None
+            self._sigf_layout = (int(self.nhcube), key[3], rank, world)
         return ctx, torch
 
     def _sigf_dev_stale(self):
