@@ -512,3 +512,29 @@ def test_dimension_limit_is_a_clear_error():
     with pytest.raises(ValueError, match='up to 32 dimensions'):
         vegas.Integrator(33 * [[0., 1.]])
     assert vegas.Integrator(32 * [[0., 1.]]).dim == 32
+
+
+def test_wide_reduce_plan_covers_every_accumulator_once():
+    """integrands with more components than the reduce kernel's instantiations are reduced in column subsets
+    (Integrator._wide_passes): every mean, every (lower-triangle or diagonal) covariance entry and sum_sigf is
+    taken from exactly one pass; a pass has at most 8 columns; the first pass starts with component 0 (it is
+    the one that trains the map and updates sigf)"""
+    import torch
+    for correlate in (True, False):
+        for nf in (9, 13, 30):
+            integ = vegas.Integrator(2 * [[0., 1.]], correlate_integrals=correlate)
+            passes = integ._wide_passes(nf, 'cpu', torch)
+            nv = nf * (nf + 1) // 2
+            seen = np.zeros(nf + nv + 1, int)
+            for k, (cols, m, src, dst) in enumerate(passes):
+                cols = cols.tolist()
+                assert m == len(cols) <= 8 and cols == sorted(cols)
+                assert len(src) == len(dst) and int(src.max()) < m + m * (m + 1) // 2 + 1
+                np.add.at(seen, dst.numpy(), 1)
+                if k == 0:
+                    assert cols[0] == 0 and int(dst[-1]) == nf + nv
+            want = np.ones(nf + nv + 1, int)
+            if not correlate:
+                want[nf:nf + nv] = 0
+                want[[nf + s * (s + 1) // 2 + s for s in range(nf)]] = 1
+            assert np.array_equal(seen, want), (correlate, nf)

@@ -44,6 +44,19 @@ elif what == 'pathint_unfused':
     integ = vegas.Integrator(f.region, neval=neval, seed=3, alpha=0.1)
     integ(fdev, nitn=3)
     fused_f, f = f, fdev
+elif what == 'pdf':
+    from vegas_b200._gv import gv
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=(6, 6))
+    g = gv.gvar(rng.normal(size=6), a @ a.T + 0.5 * np.eye(6))
+    integ = vegas.PDFIntegrator(g, neval=neval, seed=3)
+    integ(nitn=3)
+    f = vegas.devicebatchintegrand(lambda p: torch.stack([p[:, 0], p[:, 0] * p[:, 1], p[:, 2] ** 2], dim=1))
+elif what == 'restratify':
+    f = F.GaussMix([[0.5, 0.5, 0.5, 0.5]], 100., 1013.2118364296088)
+    integ = vegas.Integrator(4 * [[0., 1.]], neval=neval, seed=3)
+    integ(f, nitn=4)
+    vegas.restratify(integ, f, nitn=2, ndy=8)
 torch.cuda.synchronize()
 r = integ(f, nitn=2)
 torch.cuda.synchronize()
