@@ -374,10 +374,41 @@ def other_configs(env, vegas, _lib, fp64_peak):
         except Exception as e:        # noqa: BLE001
             out['cfg4_pathint10_callback_path'] = dict(error='%s: %s' % (type(e).__name__, str(e)[:300]))
         try:
+            out['pdf6_expectation_values'] = pdf_path(env, vegas)
+        except Exception as e:        # noqa: BLE001
+            out['pdf6_expectation_values'] = dict(error='%s: %s' % (type(e).__name__, str(e)[:300]))
+        try:
             out['cfg1_reference_cpu'] = cfg1_reference()
         except Exception as e:        # noqa: BLE001
             out['cfg1_reference_cpu'] = dict(error='%s: %s' % (type(e).__name__, str(e)[:300]))
     return out
+
+
+def pdf_path(env, vegas):
+    """PDFIntegrator (reference src/vegas/__init__.py:373-1188) end to end: expectation values of three functions of
+    six correlated Gaussian parameters, f(p) a @devicebatchintegrand, neval=1e7: sampler -> k_pdf_map -> f(p) in HBM ->
+    k_pdf_weight -> reduce (4 components with covariances), through PDFIntegrator.__call__"""
+    torch = env.torch
+    from vegas_b200._gv import gv
+    rng = np.random.default_rng(11)
+    a = rng.normal(size=(6, 6))
+    cov = a @ a.T + 0.5 * np.eye(6)
+    mean = rng.normal(size=6)
+    integ = vegas.PDFIntegrator(gv.gvar(mean, cov), neval=1e7, seed=12)
+    integ(nitn=5)
+    f = vegas.devicebatchintegrand(lambda p: torch.stack([p[:, 0], p[:, 0] * p[:, 1], p[:, 2] ** 2], dim=1))
+    integ(f, nitn=1, adapt=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = integ(f, nitn=5, adapt=False)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    exact = [mean[0], cov[0, 1] + mean[0] * mean[1], cov[2, 2] + mean[2] ** 2]
+    pulls = [float((r[i].mean - exact[i]) / r[i].sdev) for i in range(3)]
+    return dict(value=float(r.sum_neval) / sec, unit='samples/s', ms_per_step=sec / 5 * 1e3, neval=1e7, dim=6, components=4,
+                result=str(np.asarray(r)), pdfnorm=str(r.pdfnorm), pulls_vs_exact=pulls, Q=float(r.Q))
 
 
 def cfg1_reference():
