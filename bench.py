@@ -297,7 +297,7 @@ def variants(env, vegas, _lib, fp64_peak):
     ranks; roofline_frac = this rank's algorithmic flops / its kernel time / measured FP64 peak."""
     world = env.world
     out = {}
-    for n, shifted in ((1, False), (30, False), (RIDGE_N, True)):
+    for n, shifted in ((1, False), (30, False), (72, False), (RIDGE_N, True)):
         f = vegas.integrands.Ridge(DIM, N=n, lo=0.5 if n == 1 else 0.4, hi=0.5 if n == 1 else 0.6, shifted=shifted)
         integ = vegas.Integrator(DIM * [[0., 1.]], neval=NEVAL_PER_GPU * world, seed=77, mpi=world > 1, max_mem=1e11)
         integ(f, nitn=5)
@@ -365,6 +365,13 @@ def other_configs(env, vegas, _lib, fp64_peak):
                          n_gpus=world, neval=kw['neval'], ms_per_step=ms / steps, kernel_ms=kms / steps,
                          nhcube=int(integ.nhcube), neval_hcube_range=[int(v) for v in integ.neval_hcube_range],
                          result='%s Q=%.2f' % (r0, r.Q), launch=integ._ctx.last_launch())
+        if name.startswith('cfg1'):
+            # the everyday size: wall time of the public call, host epilogue (D2H, adapt, result update) included
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            integ(f, nitn=20)
+            torch.cuda.synchronize()
+            out[name]['e2e_ms_per_step'] = (time.perf_counter() - t0) / 20 * 1e3
         if name.startswith('cfg4'):
             integ4, f4 = integ, f
             integ = None

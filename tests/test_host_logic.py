@@ -538,3 +538,36 @@ def test_wide_reduce_plan_covers_every_accumulator_once():
                 want[nf:nf + nv] = 0
                 want[[nf + s * (s + 1) // 2 + s for s in range(nf)]] = 1
             assert np.array_equal(seen, want), (correlate, nf)
+
+
+def test_save_only_on_the_writer_rank(tmp_path):
+    """with the hypercube range sharded over ranks every rank holds the same results; only rank 0 writes the
+    pickle (pyx:2923-2941), the others still serialise (pickling the integrator gathers sigf: a collective)"""
+    import pickle
+    from vegas_b200._results import VegasResult
+
+    class Std(object):
+        shape = ()
+
+        def format_result(self, mean, var):
+            from vegas_b200._gv import gv
+            return gv.gvar(mean[0], var[0, 0] ** 0.5)
+
+    res = VegasResult(Std(), weighted=True)
+    res.update(np.array([1.0]), np.array([[0.01]]), 100)
+    calls = []
+
+    class Integ(object):
+        def __reduce__(self):
+            calls.append(1)
+            return (dict, ())
+
+    for writer in (False, True):
+        res.is_writer = writer
+        p1, p2 = tmp_path / ('r%d.pkl' % writer), tmp_path / ('a%d.pkl' % writer)
+        res.save(str(p1))
+        res.saveall(Integ(), str(p2))
+        assert p1.exists() == writer and p2.exists() == writer
+    assert len(calls) == 2                       # the integrator was pickled on the non-writer too
+    r, i = pickle.load(open(str(tmp_path / 'a1.pkl'), 'rb'))
+    assert abs(r.mean - 1.0) < 1e-12 and i == {}

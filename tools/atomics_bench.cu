@@ -109,6 +109,21 @@ __global__ void __launch_bounds__(256) k_hist(double* out, int W, int iters)
         } else if (MODE == 6) {
 #pragma unroll
             for (int d = 0; d < D; ++d) { sm[b[d]] += v; scnt[b[d]] += 1u; }
+        } else if (MODE == 10 || MODE == 11) {
+            // staggered axes: at step s lane group g works on axis (s + g) & 7, so only 4 (MODE 10: 8 groups of 4 lanes)
+            // or 16 (MODE 11: even / odd lanes in opposite order) lanes of a warp update the same axis' window at once
+            // -- fewer same-bin collisions, fewer CAS retries; costs a select tree on the register-held bins
+            const int g = MODE == 10 ? ((threadIdx.x >> 2) & 7) : ((threadIdx.x & 1) * 7);
+#pragma unroll
+            for (int st = 0; st < D; ++st) {
+                const int a = MODE == 10 ? ((st + g) & 7) : (st ^ g);
+                const int t0 = (a & 1) ? b[1] : b[0], t1 = (a & 1) ? b[3] : b[2], t2 = (a & 1) ? b[5] : b[4], t3 = (a & 1) ? b[7] : b[6];
+                const int u0 = (a & 2) ? t1 : t0, u1 = (a & 2) ? t3 : t2;
+                const int ba = (a & 4) ? u1 : u0;
+                atomicAdd(scnt + ba, 1u);
+                atomicAdd(sm + ba, v);
+            }
+            __syncwarp();
         } else if (MODE == 7) {
 #pragma unroll
             for (int d = 0; d < D; ++d) {
@@ -282,6 +297,8 @@ int main(int argc, char** argv)
             if (run<5>("CAS.128 {sum,count}", sms, W, nt, bps, mhz, out)) return 1;
             if (run<6>("plain RMW (not atomic)", sms, W, nt, bps, mhz, out)) return 1;
             if (run<7>("match_any leader + atomics", sms, W, nt, bps, mhz, out)) return 1;
+            if (run<10>("staggered axes, 8 x 4 lanes", sms, W, nt, bps, mhz, out)) return 1;
+            if (run<11>("staggered axes, 2 x 16 lanes", sms, W, nt, bps, mhz, out)) return 1;
         }
     }
     CK(cudaDeviceSynchronize());

@@ -105,7 +105,6 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     if (cap > lim) cap = lim;
     if (cap < 256) cap = 256;
     if (cap > 32 * NT) cap = 32 * NT;                               // k_engine's start-bit words: one per thread
-    cfg.cap = p.cap = cap;
     if (CH != VB_CH) {
         // super-chunks: only whole-range launches (the fused path); slabs must be whole chunks
         if (p.chunk_begin != 0 || p.chunk_off != nullptr) return -23;
@@ -118,9 +117,6 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
     if (p.item_off == nullptr) { p.item_begin = p.chunk_begin; p.item_end = p.chunk_end; }
     const int64_t nwork = p.item_end - p.item_begin;                // claimable work items
     const int max_grid = (int)(nwork < 0x7fffffff ? nwork : 0x7fffffff);
-    // pass 1: residency without the windows (registers / staging buffer decide)
-    vb_plan_windows(p, CH, 0, false);
-    size_t smem0 = engine_layout(p, NF, cap, CH, dim, Src::GRIDW, DIGB);
     // The kernel's attributes and its residency per shared-memory size are asked of the driver once
     // per (device, instantiation): these queries run twice per iteration otherwise, a visible share
     // of the ~0.5 ms an iteration costs at the reference's everyday sizes (neval = 1e4).
@@ -148,20 +144,37 @@ static int launch_engine(const EngineP& p_in, const Src& src, LaunchCfg& cfg, cu
         return err;
     };
     int bps = 0;
-    e = residency(smem0, bps);
-    if (e != cudaSuccess) return -(int)e - 1000;
-    if (bps < 1) return -24;                                        // does not fit at all
-    // pass 2: give the windows the shared memory that this residency leaves unused
-    long long per_cta = (long long)cfg.smem_per_sm / bps - 1024;    // 1 KB reserved per CTA
-    per_cta -= (long long)fa.sharedSizeBytes;
-    if (per_cta > dyn_max) per_cta = dyn_max;
-    const long long per_bin = sizeof(double) + sizeof(unsigned) + (Src::GRIDW ? sizeof(double) : 0);
-    long long budget = (per_cta - (long long)smem0 - 256) / per_bin;
     const int cap_bins = vb_env_int("VB200_HIST_BINS", 1 << 30);
-    if (budget > cap_bins) budget = cap_bins;
-    vb_plan_windows(p, CH, budget, Src::GRIDW);
-    cfg.wtot = p.wtot;
-    cfg.smem = engine_layout(p, NF, cap, CH, dim, Src::GRIDW, DIGB);
+    const int cap_first = cap;
+    bool giving_up = false;
+    for (;;) {
+        cfg.cap = p.cap = cap;
+        // pass 1: residency without the windows (registers / staging buffer decide)
+        vb_plan_windows(p, CH, 0, false);
+        size_t smem0 = engine_layout(p, NF, cap, CH, dim, Src::GRIDW, DIGB);
+        e = residency(smem0, bps);
+        if (e != cudaSuccess) return -(int)e - 1000;
+        if (bps < 1) return -24;                                    // does not fit at all
+        // pass 2: give the windows the shared memory that this residency leaves unused
+        long long per_cta = (long long)cfg.smem_per_sm / bps - 1024;    // 1 KB reserved per CTA
+        per_cta -= (long long)fa.sharedSizeBytes;
+        if (per_cta > dyn_max) per_cta = dyn_max;
+        const long long per_bin = sizeof(double) + sizeof(unsigned) + (Src::GRIDW ? sizeof(double) : 0);
+        long long budget = (per_cta - (long long)smem0 - 256) / per_bin;
+        if (budget > cap_bins) budget = cap_bins;
+        vb_plan_windows(p, CH, budget, Src::GRIDW);
+        cfg.wtot = p.wtot;
+        cfg.smem = engine_layout(p, NF, cap, CH, dim, Src::GRIDW, DIGB);
+        // Sources that read the map's grid from the windows fall back to global memory for EVERY sample as soon
+        // as one axis has no window (FusedSrc::sample) -- a cliff: the N = 1 ridge took 8.4 ms instead of 6.0 at
+        // the strata of neval = 4e8, where the windows missed the budget by 3 %.  Trade staging capacity for
+        // window bins until every axis fits (down to 4 samples per thread).
+        // (only for the cheapest functors: with a term loop around, larger tiles matter more -- N = 30: 10.8 ms with
+        //  20 samples per thread and the fallback, 12.0 ms with windows on every axis and 8 per thread)
+        if (!Src::GRIDW || !cfg.very_light || p.win_all || giving_up) break;
+        if (cap <= 4 * NT) { cap = cap_first; giving_up = true; continue; }     // no capacity makes them fit: keep the first choice
+        cap -= NT;
+    }
     e = residency(cfg.smem, bps);
     if (e != cudaSuccess) return -(int)e - 1000;
     if (bps < 1) return -24;
