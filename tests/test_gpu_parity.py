@@ -197,6 +197,30 @@ def test_unfused_iterations_vs_oracle(name):
     compare_iterations(eng, ora, rtol=RTOL, var_rtol=1e-10)
 
 
+@pytest.mark.parametrize('name', ['gauss4', 'pathint10', 'torch_gauss4'])
+def test_device_callback_route_vs_oracle(name):
+    """the on-device callback route (sampler -> @devicebatchintegrand on the HBM buffers -> reduce; samples and
+    integrand values never leave the GPU) vs the oracle on the same uniforms: a library functor run on the buffers
+    (``DeviceIntegrand.device_twin`` = vb200_eval_integrand), and a callback written in torch"""
+    import torch
+    vegas = _vegas()
+    if name == 'torch_gauss4':
+        limits, f, kw = _cases()['gauss4']
+
+        @vegas.devicebatchintegrand
+        def fdev(x):
+            assert x.is_cuda and x.dtype == torch.float64
+            return torch.exp(-100. * ((x - 0.5) ** 2).sum(dim=1)) * 1013.2118364296088
+
+        fnp = vegas.lbatchintegrand(lambda x: np.exp(-100. * np.sum((x - 0.5) ** 2, axis=1)) * 1013.2118364296088)
+    else:
+        limits, fnp, kw = _cases()[name]
+        fdev = fnp.device_twin(len(limits))
+    eng = run_engine_iterations(limits, fdev, nitn=3, seed=78, fused=False, **kw)
+    ora = run_oracle_iterations(limits, fnp, nitn=3, seed=78, engine=eng, **kw)
+    compare_iterations(eng, ora, rtol=1e-11 if name.startswith('pathint') else RTOL, var_rtol=1e-10)
+
+
 def test_unfused_philox_replay_equals_bins():
     """reduce kernel: training bins re-derived from the Philox counter (train_bins=False) == bins
     handed over by the sampler"""

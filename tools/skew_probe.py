@@ -18,6 +18,8 @@ if what == 'ridge':
     f, limits, kw = F.Ridge(8, N=1000), 8 * [[0., 1.]], {}
 else:
     f, limits, kw = F.PathIntegral(T=4., ndT=10, x0list=np.linspace(0, 2., 6)), 10 * [[-np.pi / 2, np.pi / 2]], dict(alpha=0.1)
+if os.environ.get('SLAB'):
+    kw['slab'] = int(os.environ['SLAB'])
 integ = vegas.Integrator(limits, neval=neval, seed=5, mpi=True, **kw)
 integ(f, nitn=5)
 integ._timing = []
@@ -44,6 +46,7 @@ for _ in range(20):
 e1.record(); torch.cuda.synchronize()
 if rank == 0:
     a = torch.stack(allr).cpu().numpy()          # [rank][itn][plan, kernel, reduce+plan_next, samples]
+    print('slab', integ._slab(world), end='  ')
     print('%s neval=%.0e world=%d: wall %.3f ms/iteration, all-reduce of the packed buffer alone %.3f ms' % (what, neval, world, wall, e0.elapsed_time(e1) / 20))
     print('kernel ms by rank (mean over iterations):', np.round(a[:, :, 1].mean(axis=1), 3))
     print('samples  by rank (last iteration, 1e6):  ', np.round(a[:, -1, 3] / 1e6, 3))
