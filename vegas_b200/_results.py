@@ -335,17 +335,14 @@ class RAvgDict(_RunningAverage, gv.BufferDict):
 
     def add(self, g):
         r""" Add estimate ``g`` (a dictionary with this dictionary's keys) to the running average. """
-        if isinstance(g, gv.BufferDict):
-            newg = gv.BufferDict(g)
-        else:
-            newg = gv.BufferDict()
-            for k in self:
-                try:
-                    newg[k] = g[k]
-                except (AttributeError, KeyError):
-                    raise ValueError("Dictionary g doesn't contain key " + str(k) + '.')
-        self.itn_results.append(newg)
-        self.rarray.add(newg.buf)
+        if not isinstance(g, gv.BufferDict):
+            missing = [k for k in self if k not in g]
+            if missing or not hasattr(g, 'keys'):
+                raise ValueError("Dictionary g doesn't contain key " + str(missing[0] if missing else None) + '.')
+            g = {k: g[k] for k in self}                 # this dictionary's key order
+        entry = gv.BufferDict(g)
+        self.itn_results.append(entry)
+        self.rarray.add(entry.buf)
 
     chi2 = property(lambda self: self.rarray.chi2, None, None, "*chi**2* of weighted average.")
     dof = property(lambda self: self.rarray.dof, None, None, "Number of degrees of freedom in weighted average.")
@@ -374,19 +371,14 @@ def _dump(payload, outfile):
 
 
 class VegasResult(object):
-    """ Accumulated result object --- standard interface for integration results
-    (``_vegas.pyx:2892-2957``): picks RAvg / RAvgArray / RAvgDict from the integrand's shape. """
+    """ Accumulated result of an integration (API of ``_vegas.pyx:2892-2957``): the running average that matches
+    the integrand's output -- ``RAvgDict`` for dictionaries (``shape is None``), ``RAvg`` for scalars, ``RAvgArray``
+    otherwise -- plus the running count of integrand evaluations. """
 
     def __init__(self, integrand=None, weighted=None):
-        self.integrand = integrand
-        self.shape = integrand.shape
-        self.sum_neval = 0
-        if self.shape is None:
-            self.result = RAvgDict(integrand.bdict, weighted=weighted)
-        elif self.shape == ():
-            self.result = RAvg(weighted=weighted)
-        else:
-            self.result = RAvgArray(self.shape, weighted=weighted)
+        self.integrand, self.shape, self.sum_neval = integrand, integrand.shape, 0
+        make = {None: lambda: RAvgDict(integrand.bdict, weighted=weighted), (): lambda: RAvg(weighted=weighted)}
+        self.result = make.get(self.shape, lambda: RAvgArray(self.shape, weighted=weighted))()
 
     # With the hypercube range sharded over ranks every rank holds the same results; only the writer
     # (rank 0, as in the reference: pyx:2923-2941 with mpi_rank) touches the file.  Pickling the integrator
@@ -405,17 +397,18 @@ class VegasResult(object):
             _dump(payload, outfile)
 
     def update(self, mean, var, last_neval=None):
+        """fold one iteration's estimate (flat ``mean``, covariance or variances ``var``) into the average"""
         self.result.add(self.integrand.format_result(mean, var))
         if last_neval is not None:
             self.sum_neval += last_neval
             self.result.sum_neval = self.sum_neval
 
     def update_analyzer(self, analyzer):
-        r""" Update analyzer at end of an iteration. """
+        r""" Hand the latest iteration and the running average to ``analyzer.end``. """
         analyzer.end(self.result.itn_results[-1], self.result)
 
     def converged(self, rtol, atol):
-        " Convergence test. "
+        " Has the average reached the requested tolerances? "
         return self.result.converged(rtol, atol)
 
 
@@ -436,14 +429,13 @@ class reporter(object):
         sys.stdout.flush()
 
     def end(self, itn_ans, ans):
+        I = self.integrator
+        have_dof = ans.dof > 0
         print("    itn %2d: %s\n all itn's: %s" % (self.itn + 1, itn_ans, ans))
         print('    neval = %s  neval/h-cube = %s\n    chi2/dof = %.2f  Q = %.2f  time = %.2f' % (
-            format(self.integrator.last_neval, '.6g'),
-            tuple(self.integrator.neval_hcube_range),
-            ans.chi2 / ans.dof if ans.dof > 0 else 0,
-            ans.Q if ans.dof > 0 else 1.,
-            self.clock() - self.t0))
-        print(self.integrator.map.settings(ngrid=self.ngrid))
+            format(I.last_neval, '.6g'), tuple(I.neval_hcube_range), ans.chi2 / ans.dof if have_dof else 0,
+            ans.Q if have_dof else 1., self.clock() - self.t0))
+        print(I.map.settings(ngrid=self.ngrid))
         print('')
         sys.stdout.flush()
 
@@ -458,24 +450,24 @@ def ravg(reslist, weighted=None, rescale=None):
     for t in (_pdf.PDFEV, _pdf.PDFEVArray, _pdf.PDFEVDict):
         if isinstance(reslist, t):         # average the underlying integrals, then form the ratios again
             return t(ravg(reslist.itn_results, weighted=weighted, rescale=rescale))
-    src = reslist
+    src, items = reslist, reslist
     if isinstance(reslist, (RAvg, RAvgArray, RAvgDict)):
-        reslist = reslist.itn_results
+        items = reslist.itn_results
     try:
-        if len(reslist) < 1:
-            raise ValueError('reslist empty')
+        n = len(items)
     except TypeError:
         raise ValueError('improper type for reslist')
-    if weighted is None:
-        weighted = getattr(src, 'weighted', True)
-    if rescale is None:
-        rescale = getattr(src, 'rescale', reslist[-1])
-    if hasattr(reslist[0], 'keys'):
-        return RAvgDict(itn_results=reslist, weighted=weighted, rescale=rescale)
+    if n < 1:
+        raise ValueError('reslist empty')
+    weighted = getattr(src, 'weighted', True) if weighted is None else weighted
+    rescale = getattr(src, 'rescale', items[-1]) if rescale is None else rescale
+    first = items[0]
+    if hasattr(first, 'keys'):
+        return RAvgDict(itn_results=items, weighted=weighted, rescale=rescale)
     try:
-        shape = np.shape(reslist[0])
+        scalar = np.shape(first) == ()
     except Exception:
         raise ValueError('reslist[i] not GVar, array, or dictionary')
-    if shape == ():
-        return RAvg(itn_results=reslist, weighted=weighted)
-    return RAvgArray(itn_results=reslist, weighted=weighted, rescale=rescale)
+    if scalar:
+        return RAvg(itn_results=items, weighted=weighted)
+    return RAvgArray(itn_results=items, weighted=weighted, rescale=rescale)
