@@ -167,6 +167,15 @@ int  vb200_map_adapt(const double* grid_host, const int64_t* ninc, int dim, int6
                      const double* sum_f_host, const double* n_f_host, int64_t hstride, double alpha,
                      const int64_t* new_ninc, double* new_grid_host, int64_t ngstride);
 
+/* AdaptiveMap.adapt on the device (pyx:467-594 for alpha > 0, training data on every axis, ninc unchanged): the
+ * context's grid is adapted in place from the iteration's histogram (sum_f_dev[dim][hstride]; counts as u64 or,
+ * after a sharded run's all-reduce, as fp64 -- exactly one of the two pointers non-NULL); skipped when
+ * status_dev[0] != 0 (NaN seen).  vb200_get_map copies the context's grid back (host_grid[dim][gstride]). */
+int  vb200_map_adapt_device(vb200_ctx* ctx, const double* sum_f_dev, const uint64_t* n_f_u64_dev,
+                            const double* n_f_f64_dev, int64_t hstride, double alpha, const int32_t* status_dev,
+                            void* stream);
+int  vb200_get_map(vb200_ctx* ctx, double* grid_host, int64_t gstride, void* stream);
+
 /* engine uniforms for testing: u_dev[rows][dim] of local chunks [chunk_begin, chunk_end) */
 int  vb200_uniforms(vb200_ctx* ctx, uint32_t itn, int64_t chunk_begin, int64_t chunk_end, double* u_dev, void* stream);
 

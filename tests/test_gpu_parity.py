@@ -611,3 +611,48 @@ def test_large_config5_three_peaks():
     exact = np.mean([one(c) ** 5 * one(0.45) ** 15 for c in (.23, .39, .74)]) * 356047712484621.56 * 3 / (100 / np.pi) ** 10
     assert abs(exact - 0.9991466) < 1e-7
     _check_full_size(integ, f, exact, 5, 3, neval_lo=0.1)
+
+
+def test_device_adapt_equals_host_adapt(monkeypatch):
+    """AdaptiveMap.adapt on the device (the Integrator's fast path: no analyzer / trace hook) against the host step:
+    five adapting iterations from the same seed give the same grid (log / sqrt are the device's instead of glibc's:
+    1e-12 on the nodes), the same results, and integ.map.grid / inc are refreshed from the device on first access;
+    a NaN leaves the map untouched"""
+    vegas = _vegas()
+    f = vegas.integrands.Ridge(4, N=7)
+
+    def run(host, alpha=0.5, **kw):
+        if host:
+            monkeypatch.setenv('VB200_HOST_ADAPT', '1')
+        else:
+            monkeypatch.delenv('VB200_HOST_ADAPT', raising=False)
+        integ = vegas.Integrator(4 * [[0., 1.]], neval=20000, seed=99, alpha=alpha, **kw)
+        r = integ(f, nitn=5)
+        return integ, r
+
+    for alpha, kw in ((0.5, {}), (0.8, dict(maxinc_axis=50)), (1.0, {})):
+        ih, rh = run(True, alpha, **kw)
+        idv, rd = run(False, alpha, **kw)
+        assert idv.map._device_owner is not None and ih.map._device_owner is None
+        g = idv.map.grid
+        assert idv.map._device_owner is None
+        np.testing.assert_allclose(g, ih.map.grid, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(idv.map.inc, ih.map.inc, rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose(np.diff(g, axis=1)[:, :idv.map.ninc[0]], idv.map.inc[:, :idv.map.ninc[0]], rtol=0, atol=0)
+        assert abs(rd.mean - rh.mean) < 1e-10 and abs(rd.sdev - rh.sdev) < 1e-8 * rh.sdev + 1e-14
+        assert rd.sum_neval == rh.sum_neval
+        # pickling and copies see the adapted grid (an unpickled integrator regrids through its defaults, as the
+        # reference's does: compare the two routes with each other)
+        import pickle
+        i2, ih2 = pickle.loads(pickle.dumps(idv)), pickle.loads(pickle.dumps(ih))
+        np.testing.assert_allclose(i2.map.grid, ih2.map.grid, rtol=1e-9, atol=1e-12)
+        r2 = vegas.Integrator(idv)(f, nitn=1)
+        assert abs(r2.mean - 1) < 5 * r2.sdev
+    # NaN: the reference raises before adapting (pyx:2133-2134)
+    monkeypatch.delenv('VB200_HOST_ADAPT', raising=False)
+    integ = vegas.Integrator(4 * [[0., 1.]], neval=5000, seed=3)
+    integ(f, nitn=2)
+    before = integ.map.grid.copy()
+    with pytest.raises(ValueError, match='nan'):
+        integ(vegas.integrands.Poly(float('nan'), [1.], [1]), nitn=1)
+    np.testing.assert_array_equal(integ.map.grid, before)

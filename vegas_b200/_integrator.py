@@ -790,6 +790,21 @@ class Integrator(object):
             if world > 1:
                 pack_iteration(buf_f, nacc, nh, n_f, status, total, nmax, rank)
                 exchange_iteration(buf_f)
+            # AdaptiveMap.adapt on the device, behind the kernels (the grid stays in HBM; the host copy is refreshed
+            # when somebody looks at integ.map.grid).  The host route remains for everything the kernel does not
+            # cover: analyzers / trace hooks that want the histogram, adapt_to_errors, alpha <= 0, single-increment
+            # axes, training data added by hand.
+            dev_adapt = (bool(flags & _lib.TRAIN) and self.alpha > 0 and self.adapt and self.analyzer is None
+                         and self._trace is None and self.map.sum_f is None and int(np.min(self.map.ninc)) > 1
+                         and not os.environ.get('VB200_HOST_ADAPT'))
+            if dev_adapt:
+                if world > 1:       # all-reduced counts (fp64) and NaN count of all ranks: every rank decides alike
+                    counts = buf_f[nacc + nh:nacc + 2 * nh].view(self.dim, hs)
+                    nan_any = (buf_f[nacc + 2 * nh + 1:nacc + 2 * nh + 2] != 0).to(torch.int32)
+                else:
+                    counts, nan_any = n_f, status
+                ctx.map_adapt_device(sum_f, counts, hs, self.alpha, nan_any)
+                self._launches += 1
             # the next iteration's allocation pre-pass rides behind this one (sum_sigf is final on the device)
             plan_next = ((flags & _lib.UPDATE_SIGF) and itn + 1 < self.nitn and self._sigf_dev is not None
                          and not os.environ.get('VB200_NO_PLAN_AHEAD'))     # (developer switch)
@@ -840,10 +855,14 @@ class Integrator(object):
                     if self._sigf_dev is not None:
                         self._sigf_dev.fill_(1.)
                     self.sum_sigf = self._sigf_len
-            if flags & (_lib.TRAIN | _lib.TRAIN_ERRORS):
-                self.map._accumulate_training(sum_f_h, n_f_h)
-            if self.alpha > 0 and self.adapt:
-                self.map.adapt(alpha=self.alpha)
+            if dev_adapt:
+                self.map._adapted_on_device(ctx)
+                self._ctx_map_version = (id(self.map), self.map._version)     # the context already holds this grid
+            else:
+                if flags & (_lib.TRAIN | _lib.TRAIN_ERRORS):
+                    self.map._accumulate_training(sum_f_h, n_f_h)
+                if self.alpha > 0 and self.adapt:
+                    self.map.adapt(alpha=self.alpha)
             if self.analyzer is not None:
                 result.update_analyzer(self.analyzer)
             if save is not None:

@@ -27,6 +27,7 @@ SYMBOLS = (
     'vb200_add_training_data', 'vb200_map_adapt', 'vb200_uniforms', 'vb200_fp64_peak', 'vb200_launch_count',
     'vb200_last_launch', 'vb200_eval_integrand', 'vb200_dy_profile', 'vb200_sample_from_uniforms',
     'vb200_plan_ahead', 'vb200_plan_commit', 'vb200_pdf_map', 'vb200_pdf_weight',
+    'vb200_map_adapt_device', 'vb200_get_map',
 )
 
 
@@ -101,6 +102,8 @@ def load():
     L.vb200_dy_profile.argtypes = [vp, u32, i64, i64, vp, i32, vp, i32, vp, vp, vp]
     L.vb200_pdf_map.argtypes = [vp, vp, i64, i32, f64, f64, i32, vp, vp, vp, vp, vp]
     L.vb200_pdf_weight.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp]
+    L.vb200_map_adapt_device.argtypes = [vp, vp, vp, vp, i64, f64, vp, vp]
+    L.vb200_get_map.argtypes = [vp, vp, i64, vp]
     L.vb200_fp64_peak.argtypes = [i32, i32, ctypes.POINTER(f64), ctypes.POINTER(f64)]
     L.vb200_launch_count.argtypes = [vp]
     L.vb200_launch_count.restype = i64
@@ -169,6 +172,20 @@ class Context(object):
         grid = np.ascontiguousarray(grid, dtype=np.float64)
         ninc = np.ascontiguousarray(ninc, dtype=np.int64)
         check(self.L.vb200_set_map(self.h, grid.ctypes.data, ninc.ctypes.data, grid.shape[0], grid.shape[1]))
+
+    def map_adapt_device(self, sum_f, n_f, hstride, alpha, status):
+        """AdaptiveMap.adapt of the context's grid on the device from the iteration's histogram (device tensors;
+        ``n_f`` int64 counts or -- after an all-reduce -- float64)"""
+        import torch
+        as_int = n_f.dtype == torch.int64
+        check(self.L.vb200_map_adapt_device(self.h, _ptr(sum_f), _ptr(n_f) if as_int else None, None if as_int else _ptr(n_f),
+                                            int(hstride), float(alpha), _ptr(status), _stream()))
+
+    def get_map(self, shape):
+        """the context's grid as a host array [dim, gstride]"""
+        out = np.empty(shape, dtype=np.float64)
+        check(self.L.vb200_get_map(self.h, out.ctypes.data, int(shape[1]), _stream()))
+        return out
 
     def set_strata(self, nstrat, slab, rank=0, world=1):
         nstrat = np.ascontiguousarray(nstrat, dtype=np.int64)

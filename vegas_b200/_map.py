@@ -24,6 +24,48 @@ class AdaptiveMap(object):
     ``_vegas.pyx:39-110``).  ``grid[d][i]`` is the ``i``-th node in direction ``d``; ``ninc`` optionally
     regrids to a different number of increments with the same Jacobian."""
 
+    # ``grid`` and ``inc`` are host arrays.  After a device-side adapt (``Integrator`` fast path:
+    # ``vb200_map_adapt_device``) the current grid lives in the integrator's context only; it is copied back
+    # the first time somebody looks (``_device_owner`` = that context until then).
+    _device_owner = None
+
+    def _pull(self):
+        ctx, self._device_owner = self._device_owner, None
+        if ctx is not None:
+            g = ctx.get_map(self._grid.shape)
+            inc = np.zeros_like(self._inc)
+            for d in range(g.shape[0]):
+                n = int(self.ninc[d])
+                inc[d, :n] = g[d, 1:n + 1] - g[d, :n]
+            self._grid, self._inc = g, inc
+
+    @property
+    def grid(self):
+        if self._device_owner is not None:
+            self._pull()
+        return self._grid
+
+    @grid.setter
+    def grid(self, value):
+        self._device_owner = None
+        self._grid = value
+
+    @property
+    def inc(self):
+        if self._device_owner is not None:
+            self._pull()
+        return self._inc
+
+    @inc.setter
+    def inc(self, value):
+        self._inc = value
+
+    def _adapted_on_device(self, ctx):
+        """the integrator's context holds a newer grid than the host arrays (same shape, same ninc)"""
+        self._device_owner = ctx
+        self.clear()
+        self._changed()
+
     def __init__(self, grid, ninc=None):
         self._ctx = None
         self._ctx_version = -1

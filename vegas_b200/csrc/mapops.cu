@@ -216,3 +216,133 @@ extern "C" int vb200_map_adapt(const double* grid_host, const int64_t* ninc, int
     return 0;
 }
 
+
+
+// ---------------------------------------------------------------------------------------------
+// AdaptiveMap.adapt on the device (pyx:467-594 for the common case: alpha > 0, training data on every
+// axis, the same number of increments before and after).  One CTA per axis; the grid never leaves HBM,
+// so an iteration's host epilogue shrinks to reading [mean, cov, sum_sigf] -- at the reference's
+// everyday sizes (neval = 1e4) the host adapt, the histogram D2H and the grid H2D were most of an
+// iteration.  Element-wise steps (averages, smoothing, damping) are the host's operations.  The sums
+// are block reductions and the regrid is a prefix sum + one binary search per new node instead of the
+// host's sequential walk (a chain of n dependent fp64 adds is ~40 us on one GPU thread): new node i
+// sits where the running sum of the weights passes i * share.  The nodes agree with the host's to
+// ~1e-13 of an increment (summation order; log / pow / sqrt are the device's instead of glibc's).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double adapt_block_sum(double v, double* red)       // all threads get the total
+{
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_map_adapt(MapP m, double* grid, const double* __restrict__ sum_f,
+                                                   const unsigned long long* __restrict__ n_u64,
+                                                   const double* __restrict__ n_f64, int hstride, double alpha,
+                                                   const int* __restrict__ status)
+{
+    extern __shared__ double ad_s[];           // w [n] | tmp -> prefix sums [n] | old nodes [n + 1]
+    __shared__ double red[8], seg_s[256];
+    const int d = blockIdx.x, n = m.ninc[d], tid = threadIdx.x, NT = blockDim.x;
+    if (status != nullptr && status[0] != 0) return;          // the integrand returned NaN: the caller raises, the map stays
+    double* w = ad_s;
+    double* tmp = ad_s + n;
+    double* g = ad_s + 2 * n;
+    double* row = grid + (size_t)d * m.gstride;
+    for (int i = tid; i <= n; i += NT) g[i] = row[i];
+    for (int i = tid; i < n; i += NT) {
+        const double cnt = n_u64 ? (double)n_u64[(size_t)d * hstride + i] : n_f64[(size_t)d * hstride + i];
+        w[i] = cnt > 0 ? sum_f[(size_t)d * hstride + i] / cnt : 0.;
+    }
+    __syncthreads();
+    double part = 0.;
+    for (int i = tid; i < n; i += NT) {
+        double t;
+        if (i == 0) t = fabs(7. * w[0] + w[1]) / 8.;
+        else if (i == n - 1) t = fabs(7. * w[n - 1] + w[n - 2]) / 8.;
+        else t = fabs(6. * w[i] + w[i - 1] + w[i + 1]) / 8.;
+        tmp[i] = t;
+        part += t;
+    }
+    const double total = adapt_block_sum(part, red);           // (contains the barriers that order tmp / w)
+    const double tiny = 1e-257;
+    __syncthreads();
+    part = 0.;
+    for (int i = tid; i < n; i += NT) {
+        double a = total > 0 ? tmp[i] / total + tiny : tiny;
+        if (a > 0 && a <= 0.99999999) {
+            const double x = -(1 - a) / log(a);
+            a = alpha == 0.5 ? sqrt(x) : (alpha == 1.0 ? x : pow(x, alpha));
+        }
+        w[i] = a;
+        part += a;
+    }
+    const double share = adapt_block_sum(part, red) / (double)n;
+    // inclusive prefix sums of w into tmp: contiguous segments per thread, then the segments' offsets
+    const int per = (n + NT - 1) / NT, lo = min(tid * per, n), hi = min(lo + per, n);
+    double run = 0.;
+    for (int i = lo; i < hi; ++i) { run += w[i]; tmp[i] = run; }
+    seg_s[tid] = run;
+    __syncthreads();
+    double off = 0.;
+    for (int t = 0; t < tid; ++t) off += seg_s[t];             // (256 broadcast reads; n is a few thousand at most)
+    for (int i = lo; i < hi; ++i) tmp[i] += off;
+    __syncthreads();
+    for (int i = 1 + tid; i < n; i += NT) {
+        const double target = (double)i * share;
+        int a = -1, b = n - 1;                                  // first j with tmp[j] >= target (clamped to the last increment)
+        while (b - a > 1) {
+            const int mid = (a + b) >> 1;
+            if (tmp[mid] >= target) b = mid; else a = mid;
+        }
+        const int j = b;
+        const double acc = tmp[j] - target;
+        row[i] = g[j + 1] - (acc / w[j]) * (g[j + 1] - g[j]);
+    }
+    // (row[0] and row[n] keep the old end points; the padding beyond n repeats the last node)
+}
+
+extern "C" int vb200_map_adapt_device(vb200_ctx* c, const double* sum_f_dev, const uint64_t* n_f_u64_dev,
+                                      const double* n_f_f64_dev, int64_t hstride, double alpha, const int32_t* status_dev,
+                                      void* stream)
+{
+    if (!c || !sum_f_dev || (!n_f_u64_dev && !n_f_f64_dev)) return fail(-1, "vb200_map_adapt_device: null argument");
+    if (!c->have_map) return fail(-1, "vb200_map_adapt_device: no map set");
+    if (!(alpha > 0)) return fail(-1, "vb200_map_adapt_device: alpha must be positive (use vb200_map_adapt)");
+    int widest = 0;
+    for (int d = 0; d < c->map.dim; ++d) {
+        if (c->map.ninc[d] < 2) return fail(-1, "vb200_map_adapt_device: axis %d has a single increment (use vb200_map_adapt)", d);
+        if (c->map.ninc[d] > hstride) return fail(-1, "vb200_map_adapt_device: hstride too small");
+        if (c->map.ninc[d] > widest) widest = c->map.ninc[d];
+    }
+    const size_t smem = sizeof(double) * (3 * (size_t)widest + 1);
+    if (smem > 200 * 1024) return fail(-1, "vb200_map_adapt_device: %d increments exceed the kernel's shared memory", widest);
+    CK(cudaSetDevice(c->device));
+    static thread_local int attr_set_for = -1;
+    if (smem > 48 * 1024 && attr_set_for != c->device) {
+        CK(cudaFuncSetAttribute(k_map_adapt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set_for = c->device;
+    }
+    k_map_adapt<<<c->map.dim, 256, smem, (cudaStream_t)stream>>>(c->map, (double*)c->grid.p, sum_f_dev,
+                                                                 (const unsigned long long*)n_f_u64_dev, n_f_f64_dev,
+                                                                 (int)hstride, alpha, (const int*)status_dev);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vb200_get_map(vb200_ctx* c, double* grid_host, int64_t gstride, void* stream)
+{
+    if (!c || !grid_host) return fail(-1, "vb200_get_map: null argument");
+    if (!c->have_map) return fail(-1, "vb200_get_map: no map set");
+    if (gstride != c->map.gstride) return fail(-1, "vb200_get_map: gstride %lld != %d", (long long)gstride, c->map.gstride);
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(grid_host, c->grid.p, sizeof(double) * (size_t)c->map.dim * (size_t)gstride, cudaMemcpyDeviceToHost,
+                       (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
