@@ -753,14 +753,17 @@ class Integrator(object):
             if self.analyzer is not None:
                 self.analyzer.begin(itn, self)
             ctx, torch = self._engine()          # map / sigf may have changed
-            hs = int(self.map.inc.shape[1])
+            hs = int(self.map._inc.shape[1])       # (the shape only: must not pull a device-adapted grid back every iteration)
             # One allocation and one device-to-host copy per iteration:
             #   buf_f (fp64):  [mean, cov, sum_sigf | sum_f | n_f as fp64 | samples, NaN count, max samples per
             #                   hypercube of rank 0 .. world-1]   -- the part a sharded run all-reduces (SUM), once
             #   buf_i (int64): [n_f | NaN flag | statistics of the next iteration's allocation pre-pass]
             nacc, nh = nf + nv + 1, self.dim * hs
             n_bf, n_bi = nacc + 2 * nh + 2 + world, nh + 1 + 6
-            raw = torch.zeros(8 * (n_bf + n_bi), dtype=torch.uint8, device=dev)
+            raw = getattr(self, '_raw', None)          # one device buffer for the integrator's lifetime, zeroed per iteration
+            if raw is None or raw.numel() != 8 * (n_bf + n_bi) or raw.device != torch.device(dev):
+                raw = self._raw = torch.empty(8 * (n_bf + n_bi), dtype=torch.uint8, device=dev)
+            raw.zero_()
             buf_f = raw[:8 * n_bf].view(torch.float64)
             buf_i = raw[8 * n_bf:].view(torch.int64)
             acc, sum_f = buf_f[:nacc], buf_f[nacc:nacc + nh].view(self.dim, hs)
