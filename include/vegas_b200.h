@@ -167,6 +167,16 @@ int  vb200_map_adapt(const double* grid_host, const int64_t* ninc, int dim, int6
                      const double* sum_f_host, const double* n_f_host, int64_t hstride, double alpha,
                      const int64_t* new_ninc, double* new_grid_host, int64_t ngstride);
 
+/* One fused iteration in one call (everyday sizes: the binding calls cost more than the kernels): zero the
+ * iteration buffer buf_dev (nwords 8-byte words: fp64 [mean, cov, sum_sigf | sum_f | ...] then, from word nf64 on,
+ * int64 [n_f | NaN flag | 6 pre-pass statistics]), vb200_iterate_fused, vb200_map_adapt_device (alpha_adapt > 0),
+ * vb200_plan_ahead (plan_neval_scaled > 0), then head_host[0 .. nacc) = the fp64 head and head_host[nacc .. nacc+7)
+ * = NaN flag + statistics (int64 bit patterns), synchronised.  Replaces pyx:2096-2230 for one iteration. */
+int  vb200_iteration(vb200_ctx* ctx, uint32_t itn, double beta, int flags, double* sigf_dev, void* buf_dev,
+                     int64_t nacc, int64_t nh, int64_t hstride, int64_t nf64, int64_t nwords, double alpha_adapt,
+                     double plan_neval_scaled, int64_t plan_min, int64_t plan_max, int64_t plan_uniform,
+                     double* head_host, void* stream);
+
 /* AdaptiveMap.adapt on the device (pyx:467-594 for alpha > 0, training data on every axis, ninc unchanged): the
  * context's grid is adapted in place from the iteration's histogram (sum_f_dev[dim][hstride]; counts as u64 or,
  * after a sharded run's all-reduce, as fp64 -- exactly one of the two pointers non-NULL); skipped when

@@ -500,14 +500,16 @@ class Integrator(object):
             return int(self.slab)
         if world == 1:
             return _lib.CHUNK
-        # Slabs of at most 2048 hypercubes, at least 64 per rank: the vegas+ allocation varies smoothly over the
-        # hypercube index, so fine slabs balance the SAMPLES of the ranks, not just their cubes.  Measured on 8 GPUs
-        # (8-D ridge, neval = 1e8 fixed; tools/skew_probe.py): slabs of 16384 cubes (round 1) left the ranks'
-        # sample counts 5.2 % apart (max / mean) and the step at 26.0 ms; 2048: 0.8 %, 25.2 ms; 512: 25.2 ms.
-        per = -(-int(self.nhcube) // (world * 64))
+        # At least 512 slabs per rank, of 256 ... 16384 hypercubes: the vegas+ allocation varies smoothly over the
+        # hypercube index, so many small slabs balance the SAMPLES of the ranks, not just their cubes.  Measured on
+        # 8 GPUs (tools/skew_probe.py, 8-D ridge at neval = 1e8 fixed, 1.1e7 hypercubes): slabs of 16384 cubes (86 per
+        # rank) left the ranks' sample counts 5.2 % apart (max / mean) and the step at 26.0 ms; 2048 (686 per rank):
+        # 0.8 %, 25.2 ms; 512: 25.2 ms.  Large problems keep large slabs (config 5, 7.8e8 hypercubes: 346 ms per step
+        # with 16384-cube slabs, 376 ms with 2048 -- windows move at every slab boundary).
+        per = -(-int(self.nhcube) // (world * 512))
         unit = 2 * _lib.CHUNK if per >= 2 * _lib.CHUNK else _lib.CHUNK    # whole chunks of the light geometry (512 cubes)
         per = -(-per // unit) * unit
-        return int(max(_lib.CHUNK, min(8 * _lib.CHUNK, per)))
+        return int(max(_lib.CHUNK, min(64 * _lib.CHUNK, per)))
 
     def _engine(self):
         """bring the device context up to date with map / strata / sigf; returns (ctx, torch)"""
@@ -763,13 +765,13 @@ class Integrator(object):
             raw = getattr(self, '_raw', None)          # one device buffer for the integrator's lifetime, zeroed per iteration
             if raw is None or raw.numel() != 8 * (n_bf + n_bi) or raw.device != torch.device(dev):
                 raw = self._raw = torch.empty(8 * (n_bf + n_bi), dtype=torch.uint8, device=dev)
-            raw.zero_()
-            buf_f = raw[:8 * n_bf].view(torch.float64)
-            buf_i = raw[8 * n_bf:].view(torch.int64)
-            acc, sum_f = buf_f[:nacc], buf_f[nacc:nacc + nh].view(self.dim, hs)
-            n_f = buf_i[:nh].view(self.dim, hs)
-            status = buf_i[nh:nh + 1].view(torch.int32)       # the kernels set its low word
-            stats_next = buf_i[nh + 1:]
+
+            def views():
+                raw.zero_()
+                bf = raw[:8 * n_bf].view(torch.float64)
+                bi = raw[8 * n_bf:].view(torch.int64)
+                return (bf, bf[:nacc], bf[nacc:nacc + nh].view(self.dim, hs), bi[:nh].view(self.dim, hs),
+                        bi[nh:nh + 1].view(torch.int32), bi[nh + 1:])       # (status: the kernels set its low word)
             if self._timing is not None:
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 ev[0].record()
@@ -778,7 +780,39 @@ class Integrator(object):
             pitn = self._next_itn()
             if self._timing is not None:
                 ev[1].record()
-            if device_fcn is not None:
+            # AdaptiveMap.adapt on the device, behind the kernels (the grid stays in HBM; the host copy is refreshed
+            # when somebody looks at integ.map.grid).  The host route remains for everything the kernel does not
+            # cover: analyzers / trace hooks that want the histogram, adapt_to_errors, alpha <= 0, single-increment
+            # axes, training data added by hand.
+            dev_adapt = (bool(flags & _lib.TRAIN) and self.alpha > 0 and self.adapt and self.analyzer is None
+                         and self._trace is None and self.map.sum_f is None and int(np.min(self.map.ninc)) > 1
+                         and not os.environ.get('VB200_HOST_ADAPT'))
+            # the next iteration's allocation pre-pass rides behind this one (sum_sigf is final on the device)
+            plan_next = bool((flags & _lib.UPDATE_SIGF) and itn + 1 < self.nitn and self._sigf_dev is not None
+                             and not os.environ.get('VB200_NO_PLAN_AHEAD'))     # (developer switch)
+            # Everyday sizes: the whole iteration in one library call (vb200_iteration: zero, engine, adapt, pre-pass
+            # of the next iteration, one small copy back) -- a handful of binding calls cost more than the kernels.
+            fast = (device_fcn is not None and world == 1 and self._timing is None and self._trace is None
+                    and (dev_adapt or not (flags & (_lib.TRAIN | _lib.TRAIN_ERRORS)))
+                    and not os.environ.get('VB200_NO_FAST_ITERATION'))
+            head = None
+            if fast:
+                head = np.empty(nacc + 7, dtype=np.float64)
+                _, _, max_nh, uniform = self._plan_args()
+                try:
+                    ctx.iteration(pitn, self.beta, flags, self._sigf_dev, raw, nacc, nh, hs, n_bf, n_bf + n_bi,
+                                  self.alpha if dev_adapt else 0.,
+                                  (self.neval_frac * self.neval, self.min_neval_hcube, max_nh, uniform) if plan_next else None,
+                                  head)
+                except _lib.VegasB200Error as err:
+                    if getattr(err, 'code', 0) != -4:
+                        raise
+                    device_fcn, fast, head = None, False, None      # no fused instantiation: callback path from here on
+            if not fast:
+                buf_f, acc, sum_f, n_f, status, stats_next = views()
+            if fast:
+                pass
+            elif device_fcn is not None:
                 try:
                     ctx.iterate_fused(pitn, self.beta, flags, self._sigf_dev, acc, sum_f, n_f, hs, status)
                     self._launches += 2
@@ -793,14 +827,7 @@ class Integrator(object):
             if world > 1:
                 pack_iteration(buf_f, nacc, nh, n_f, status, total, nmax, rank)
                 exchange_iteration(buf_f)
-            # AdaptiveMap.adapt on the device, behind the kernels (the grid stays in HBM; the host copy is refreshed
-            # when somebody looks at integ.map.grid).  The host route remains for everything the kernel does not
-            # cover: analyzers / trace hooks that want the histogram, adapt_to_errors, alpha <= 0, single-increment
-            # axes, training data added by hand.
-            dev_adapt = (bool(flags & _lib.TRAIN) and self.alpha > 0 and self.adapt and self.analyzer is None
-                         and self._trace is None and self.map.sum_f is None and int(np.min(self.map.ninc)) > 1
-                         and not os.environ.get('VB200_HOST_ADAPT'))
-            if dev_adapt:
+            if dev_adapt and not fast:
                 if world > 1:       # all-reduced counts (fp64) and NaN count of all ranks: every rank decides alike
                     counts = buf_f[nacc + nh:nacc + 2 * nh].view(self.dim, hs)
                     nan_any = (buf_f[nacc + 2 * nh + 1:nacc + 2 * nh + 2] != 0).to(torch.int32)
@@ -808,18 +835,20 @@ class Integrator(object):
                     counts, nan_any = n_f, status
                 ctx.map_adapt_device(sum_f, counts, hs, self.alpha, nan_any)
                 self._launches += 1
-            # the next iteration's allocation pre-pass rides behind this one (sum_sigf is final on the device)
-            plan_next = ((flags & _lib.UPDATE_SIGF) and itn + 1 < self.nitn and self._sigf_dev is not None
-                         and not os.environ.get('VB200_NO_PLAN_AHEAD'))     # (developer switch)
-            if plan_next:
+            if plan_next and not fast:
                 self._plan_next(ctx, acc[nf + nv:], stats_next)
             if self._timing is not None:
                 ev[3].record()
                 self._timing.append((ev, total))
-            hraw = raw.cpu().numpy()
-            hf, hi = hraw[:8 * n_bf].view(np.float64), hraw[8 * n_bf:].view(np.int64)
-            nan_seen = int(hi[nh]) != 0
-            n_f_h = hi[:nh]
+            if fast:
+                hf, tail_i = head, head[nacc:].view(np.int64)
+                nan_seen, stats6 = (int(tail_i[0]) & 0xffffffff) != 0, tail_i[1:7].copy()
+                n_f_h = None
+            else:
+                hraw = raw.cpu().numpy()
+                hf, hi = hraw[:8 * n_bf].view(np.float64), hraw[8 * n_bf:].view(np.int64)
+                nan_seen, stats6 = int(hi[nh]) != 0, hi[nh + 1:nh + 7].copy()
+                n_f_h = hi[:nh]
             if world > 1:
                 tail = hf[nacc + 2 * nh:]
                 total, nan_seen, nmax = int(tail[0]), tail[1] != 0, int(np.max(tail[2:]))
@@ -833,7 +862,8 @@ class Integrator(object):
                     self.sum_sigf = self._sigf_len
                 raise ValueError('integrand evaluates to nan')
             acc_h = hf[:nacc]
-            sum_f_h, n_f_h = hf[nacc:nacc + nh].reshape(self.dim, hs), n_f_h.reshape(self.dim, hs)
+            if not fast:
+                sum_f_h, n_f_h = hf[nacc:nacc + nh].reshape(self.dim, hs), n_f_h.reshape(self.dim, hs)
             mean = acc_h[:nf].copy()
             if self.correlate_integrals:
                 var = np.zeros((nf, nf), float)
@@ -852,7 +882,7 @@ class Integrator(object):
                     self.sum_sigf = sum_sigf
                     if plan_next:
                         _, neval_sigf, max_nh, uniform = self._plan_args()
-                        self._plan_ahead = (self._plan_key(ctx, neval_sigf, max_nh, uniform), hi[nh + 1:nh + 7].copy())
+                        self._plan_ahead = (self._plan_key(ctx, neval_sigf, max_nh, uniform), stats6)
                 else:
                     # integrand appears to be a constant => even distribution of points
                     if self._sigf_dev is not None:

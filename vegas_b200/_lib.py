@@ -27,7 +27,7 @@ SYMBOLS = (
     'vb200_add_training_data', 'vb200_map_adapt', 'vb200_uniforms', 'vb200_fp64_peak', 'vb200_launch_count',
     'vb200_last_launch', 'vb200_eval_integrand', 'vb200_dy_profile', 'vb200_sample_from_uniforms',
     'vb200_plan_ahead', 'vb200_plan_commit', 'vb200_pdf_map', 'vb200_pdf_weight',
-    'vb200_map_adapt_device', 'vb200_get_map',
+    'vb200_map_adapt_device', 'vb200_get_map', 'vb200_iteration',
 )
 
 
@@ -104,6 +104,7 @@ def load():
     L.vb200_pdf_weight.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp]
     L.vb200_map_adapt_device.argtypes = [vp, vp, vp, vp, i64, f64, vp, vp]
     L.vb200_get_map.argtypes = [vp, vp, i64, vp]
+    L.vb200_iteration.argtypes = [vp, u32, f64, i32, vp, vp, i64, i64, i64, i64, i64, f64, f64, i64, i64, i64, vp, vp]
     L.vb200_fp64_peak.argtypes = [i32, i32, ctypes.POINTER(f64), ctypes.POINTER(f64)]
     L.vb200_launch_count.argtypes = [vp]
     L.vb200_launch_count.restype = i64
@@ -229,6 +230,13 @@ class Context(object):
     def iterate_fused(self, itn, beta, flags, sigf, acc, sum_f, n_f, hstride, status):
         check(self.L.vb200_iterate_fused(self.h, itn, float(beta), flags, _ptr(sigf), _ptr(acc), _ptr(sum_f),
                                          _ptr(n_f), hstride, _ptr(status), _stream()))
+
+    def iteration(self, itn, beta, flags, sigf, buf, nacc, nh, hstride, nf64, nwords, alpha_adapt, plan, head):
+        """one fused iteration in one call (``vb200_iteration``); ``plan`` = (neval_scaled, min, max, uniform) or None;
+        ``head``: host float64 array of nacc + 7 words"""
+        pn, pmin, pmax, puni = plan if plan is not None else (0., 0, 0, 0)
+        check(self.L.vb200_iteration(self.h, itn, float(beta), flags, _ptr(sigf), _ptr(buf), nacc, nh, hstride, nf64, nwords,
+                                     float(alpha_adapt), float(pn), int(pmin), int(pmax), int(puni), head.ctypes.data, _stream()))
 
     def sample(self, itn, c0, c1, x, wgt, y=None, jac1d=None, hcube=None, transposed=False, bins=None, u=None):
         """``u``: uniforms [rows, dim] supplied by the caller (``ran_array_generator``) instead of Philox"""

@@ -677,6 +677,46 @@ extern "C" int vb200_reduce(vb200_ctx* c, uint32_t itn, double beta, int flags, 
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// One fused iteration in ONE call (the everyday sizes, where a handful of binding calls cost more than
+// the kernels): zero the iteration buffer, run the engine, adapt the map on the device, launch the next
+// iteration's allocation pre-pass, copy the small head of the buffer back and synchronise.
+// buf_dev layout (8-byte words; the caller's, see Integrator.__call__):
+//   fp64  [0, nacc)                 mean, covariance, sum_sigf
+//         [nacc, nacc + nh)         sum_f [dim][hstride]
+//         [nacc + nh, nacc + 2 nh)  (counts as fp64: sharded runs only)      then `tail` words
+//   int64 [nf64, nf64 + nh)         n_f [dim][hstride]
+//         [nf64 + nh]               NaN flag (low 32 bits)
+//         [nf64 + nh + 1, + 7)      statistics of the pre-pass
+// head_host receives words [0, nacc) and the 7 words from the NaN flag on (nacc + 7 doubles).
+// ---------------------------------------------------------------------------------------------
+extern "C" int vb200_iteration(vb200_ctx* c, uint32_t itn, double beta, int flags, double* sigf_dev, void* buf_dev,
+                               int64_t nacc, int64_t nh, int64_t hstride, int64_t nf64, int64_t nwords, double alpha_adapt,
+                               double plan_neval_scaled, int64_t plan_min, int64_t plan_max, int64_t plan_uniform,
+                               double* head_host, void* stream)
+{
+    if (!c || !buf_dev || !head_host) return fail(-1, "vb200_iteration: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    double* f = (double*)buf_dev;
+    int64_t* iw = (int64_t*)buf_dev + nf64;
+    CK(cudaMemsetAsync(buf_dev, 0, sizeof(double) * (size_t)nwords, st));
+    int rc = vb200_iterate_fused(c, itn, beta, flags, sigf_dev, f, f + nacc, (uint64_t*)iw, hstride, (int32_t*)(iw + nh), stream);
+    if (rc) return rc;
+    if (alpha_adapt > 0) {
+        rc = vb200_map_adapt_device(c, f + nacc, (const uint64_t*)iw, nullptr, hstride, alpha_adapt, (const int32_t*)(iw + nh), stream);
+        if (rc) return rc;
+    }
+    if (plan_neval_scaled > 0) {
+        rc = vb200_plan_ahead(c, sigf_dev, f + nacc - 1, plan_neval_scaled, plan_min, plan_max, plan_uniform, iw + nh + 1, stream);
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(head_host, f, sizeof(double) * (size_t)nacc, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(head_host + nacc, iw + nh, sizeof(int64_t) * 7, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" int64_t vb200_launch_count(vb200_ctx* c) { return c ? c->launches : 0; }
 
 extern "C" int vb200_last_launch(vb200_ctx* c, int64_t out[6])
