@@ -656,3 +656,28 @@ def test_device_adapt_equals_host_adapt(monkeypatch):
     with pytest.raises(ValueError, match='nan'):
         integ(vegas.integrands.Poly(float('nan'), [1.], [1]), nitn=1)
     np.testing.assert_array_equal(integ.map.grid, before)
+
+
+def test_one_call_iteration_equals_general_path(monkeypatch):
+    """vb200_iteration (zero, engine, device adapt, next pre-pass, small copy back in one library call) against the
+    general path of Integrator.__call__ on the same seed: identical sample counts, results and maps; also without
+    adaptation (no training), with adapt_to_errors (host adapt: general path is taken by itself) and with beta = 0"""
+    vegas = _vegas()
+    f = vegas.integrands.GaussMix([4 * [0.5]], 100., 1013.2118364296088)
+    for kw in (dict(), dict(adapt=False), dict(beta=0.), dict(adapt_to_errors=True), dict(alpha=0.)):
+        out = []
+        for fast in (True, False):
+            if fast:
+                monkeypatch.delenv('VB200_NO_FAST_ITERATION', raising=False)
+            else:
+                monkeypatch.setenv('VB200_NO_FAST_ITERATION', '1')
+            integ = vegas.Integrator([[-1., 1.]] + 3 * [[0., 1.]], neval=10000, seed=31, **kw)
+            r = integ(f, nitn=6)
+            out.append((r, integ))
+        (ra, ia), (rb, ib) = out
+        assert ra.sum_neval == rb.sum_neval and tuple(ia.neval_hcube_range) == tuple(ib.neval_hcube_range)
+        np.testing.assert_allclose([x.mean for x in ra.itn_results], [x.mean for x in rb.itn_results], rtol=1e-11)
+        np.testing.assert_allclose([x.sdev for x in ra.itn_results], [x.sdev for x in rb.itn_results], rtol=1e-8)
+        np.testing.assert_allclose(ia.map.grid, ib.map.grid, rtol=1e-11, atol=1e-14)
+        np.testing.assert_allclose(ia.sigf, ib.sigf, rtol=1e-8)
+        assert abs(ra.mean - 1) < 5 * ra.sdev
