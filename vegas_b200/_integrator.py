@@ -507,7 +507,8 @@ class Integrator(object):
         # 0.8 %, 25.2 ms; 512: 25.2 ms.  Large problems keep large slabs (config 5, 7.8e8 hypercubes: 346 ms per step
         # with 16384-cube slabs, 376 ms with 2048 -- windows move at every slab boundary).
         per = -(-int(self.nhcube) // (world * 512))
-        unit = 2 * _lib.CHUNK if per >= 2 * _lib.CHUNK else _lib.CHUNK    # whole chunks of the light geometry (512 cubes)
+        # whole chunks of the light geometry (512 cubes) unless the problem is too small to give every rank two of them
+        unit = 2 * _lib.CHUNK if int(self.nhcube) >= 4 * _lib.CHUNK * world else _lib.CHUNK
         per = -(-per // unit) * unit
         return int(max(_lib.CHUNK, min(64 * _lib.CHUNK, per)))
 
