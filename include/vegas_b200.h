@@ -84,9 +84,10 @@ int  vb200_chunk_offsets(vb200_ctx* ctx, int64_t* out_host, int64_t count);   /*
 /* The same pre-pass for the NEXT iteration without a host round trip, launched right after an
  * iteration's kernels: neval_sigf = neval_scaled / *sum_sigf_dev is formed on the device from the
  * sum_sigf the iteration has just produced (acc_dev[nf + nf(nf+1)/2], after the all-reduce when the
- * hypercube range is sharded), and the six statistics {sum, min, max, largest chunk, work items, work
- * items of the 512-cube geometry} go to stats_dev, which the caller copies to the host together with
- * the iteration's results.  Asynchronous; the context has no valid plan until vb200_plan_commit
+ * hypercube range is sharded), and the six statistics {sum, min (stored as INT64_MAX - min, so that all
+ * six start from zero), max, largest chunk, work items, work items of the 512-cube geometry} go to
+ * stats_dev -- opaque words the caller copies to the host together with the iteration's results and hands
+ * to vb200_plan_commit.  Asynchronous; the context has no valid plan until vb200_plan_commit
  * installs those statistics (host values) with the neval_sigf the host computed from the same sum_sigf
  * (pyx:1657-1662: identical double arithmetic), or vb200_plan replaces the pre-pass. */
 int  vb200_plan_ahead(vb200_ctx* ctx, const double* sigf_dev, const double* sum_sigf_dev, double neval_scaled,
@@ -176,6 +177,15 @@ int  vb200_iteration(vb200_ctx* ctx, uint32_t itn, double beta, int flags, doubl
                      int64_t nacc, int64_t nh, int64_t hstride, int64_t nf64, int64_t nwords, double alpha_adapt,
                      double plan_neval_scaled, int64_t plan_min, int64_t plan_max, int64_t plan_uniform,
                      double* head_host, void* stream);
+/* The same in two halves, so that the caller's bookkeeping of iteration i-1 overlaps the kernels of iteration i:
+ * _begin launches everything (the head lands in pinned host memory owned by the context, written by the last
+ * kernel of the chain: no device-to-host copies) and returns; _end synchronises and copies the nacc + 7 words out.
+ * vb200_iteration == _begin + _end. */
+int  vb200_iteration_begin(vb200_ctx* ctx, uint32_t itn, double beta, int flags, double* sigf_dev, void* buf_dev,
+                           int64_t nacc, int64_t nh, int64_t hstride, int64_t nf64, int64_t nwords, double alpha_adapt,
+                           double plan_neval_scaled, int64_t plan_min, int64_t plan_max, int64_t plan_uniform,
+                           void* stream);
+int  vb200_iteration_end(vb200_ctx* ctx, double* head_host, int64_t nhead, void* stream);
 
 /* AdaptiveMap.adapt on the device (pyx:467-594 for alpha > 0, training data on every axis, ninc unchanged): the
  * context's grid is adapted in place from the iteration's histogram (sum_f_dev[dim][hstride]; counts as u64 or,

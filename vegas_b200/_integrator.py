@@ -752,10 +752,35 @@ class Integrator(object):
         nv = nf * (nf + 1) // 2
         result = VegasResult(std, weighted=self.adapt)
         result.is_writer = world == 1 or rank == 0
+
+        def book(acc_h, neval, trace=None):
+            """one iteration's [mean, cov] into the running average"""
+            mean = acc_h[:nf].copy()
+            if self.correlate_integrals:
+                var = np.zeros((nf, nf), float)
+                var[_tril(nf)] = acc_h[nf:nf + nv]
+                var = var + np.tril(var, -1).T
+            else:
+                var = acc_h[nf:nf + nv][[s * (s + 1) // 2 + s for s in range(nf)]].copy()
+            if trace is not None:
+                trace(mean, var)
+            result.update(mean, var, neval)
+
+        # One-call iterations with nothing looking at the running average between them (no tolerances, analyzer or
+        # save files): iteration i's results are booked while the kernels of iteration i + 1 run
+        # (vb200_iteration_begin / _end) -- at everyday sizes the Python bookkeeping is a third of an iteration.
+        defer = (self.rtol == 0 and self.atol == 0 and self.analyzer is None and save is None and saveall is None
+                 and not os.environ.get('VB200_NO_DEFER'))
+        pending = None
+        env_host_adapt, env_no_ahead, env_no_fast = (os.environ.get(k) for k in           # (developer switches)
+                                                     ('VB200_HOST_ADAPT', 'VB200_NO_PLAN_AHEAD', 'VB200_NO_FAST_ITERATION'))
+        fast = False
         for itn in range(self.nitn):
             if self.analyzer is not None:
                 self.analyzer.begin(itn, self)
-            ctx, torch = self._engine()          # map / sigf may have changed
+            if not (fast and self.analyzer is None):
+                ctx, torch = self._engine()      # map / sigf may have changed (not behind a one-call iteration: the
+                #                                  device adapted its own grid and nothing else ran in between)
             hs = int(self.map._inc.shape[1])       # (the shape only: must not pull a device-adapted grid back every iteration)
             # One allocation and one device-to-host copy per iteration:
             #   buf_f (fp64):  [mean, cov, sum_sigf | sum_f | n_f as fp64 | samples, NaN count, max samples per
@@ -787,24 +812,27 @@ class Integrator(object):
             # axes, training data added by hand.
             dev_adapt = (bool(flags & _lib.TRAIN) and self.alpha > 0 and self.adapt and self.analyzer is None
                          and self._trace is None and self.map.sum_f is None and int(np.min(self.map.ninc)) > 1
-                         and not os.environ.get('VB200_HOST_ADAPT'))
+                         and not env_host_adapt)
             # the next iteration's allocation pre-pass rides behind this one (sum_sigf is final on the device)
             plan_next = bool((flags & _lib.UPDATE_SIGF) and itn + 1 < self.nitn and self._sigf_dev is not None
-                             and not os.environ.get('VB200_NO_PLAN_AHEAD'))     # (developer switch)
+                             and not env_no_ahead)
             # Everyday sizes: the whole iteration in one library call (vb200_iteration: zero, engine, adapt, pre-pass
             # of the next iteration, one small copy back) -- a handful of binding calls cost more than the kernels.
             fast = (device_fcn is not None and world == 1 and self._timing is None and self._trace is None
                     and (dev_adapt or not (flags & (_lib.TRAIN | _lib.TRAIN_ERRORS)))
-                    and not os.environ.get('VB200_NO_FAST_ITERATION'))
+                    and not env_no_fast)
             head = None
             if fast:
                 head = np.empty(nacc + 7, dtype=np.float64)
                 _, _, max_nh, uniform = self._plan_args()
                 try:
-                    ctx.iteration(pitn, self.beta, flags, self._sigf_dev, raw, nacc, nh, hs, n_bf, n_bf + n_bi,
-                                  self.alpha if dev_adapt else 0.,
-                                  (self.neval_frac * self.neval, self.min_neval_hcube, max_nh, uniform) if plan_next else None,
-                                  head)
+                    ctx.iteration_begin(pitn, self.beta, flags, self._sigf_dev, raw, nacc, nh, hs, n_bf, n_bf + n_bi,
+                                        self.alpha if dev_adapt else 0.,
+                                        (self.neval_frac * self.neval, self.min_neval_hcube, max_nh, uniform) if plan_next else None)
+                    if pending is not None:          # (the previous iteration's bookkeeping, behind this one's kernels)
+                        book(*pending)
+                        pending = None
+                    ctx.iteration_end(head)
                 except _lib.VegasB200Error as err:
                     if getattr(err, 'code', 0) != -4:
                         raise
@@ -865,18 +893,16 @@ class Integrator(object):
             acc_h = hf[:nacc]
             if not fast:
                 sum_f_h, n_f_h = hf[nacc:nacc + nh].reshape(self.dim, hs), n_f_h.reshape(self.dim, hs)
-            mean = acc_h[:nf].copy()
-            if self.correlate_integrals:
-                var = np.zeros((nf, nf), float)
-                var[_tril(nf)] = acc_h[nf:nf + nv]
-                var = var + np.tril(var, -1).T
-            else:
-                var = acc_h[nf:nf + nv][[s * (s + 1) // 2 + s for s in range(nf)]].copy()
             sum_sigf = float(acc_h[nf + nv])
-            if self._trace is not None:
-                self._trace(dict(itn=pitn, mean=mean, var=var, sum_sigf=sum_sigf, last_neval=self.last_neval,
-                                 sum_f=sum_f_h.copy(), n_f=n_f_h.copy(), flags=flags))
-            result.update(mean, var, self.last_neval)
+            if pending is not None:
+                book(*pending)
+                pending = None
+            if fast and defer:
+                pending = (acc_h, self.last_neval)
+            else:
+                book(acc_h, self.last_neval, None if self._trace is None else (lambda mean, var: self._trace(dict(
+                    itn=pitn, mean=mean, var=var, sum_sigf=sum_sigf, last_neval=self.last_neval,
+                    sum_f=sum_f_h.copy(), n_f=n_f_h.copy(), flags=flags))))
 
             if self.beta > 0 and not self.adapt_to_errors and self.adapt:
                 if sum_sigf > 0:
@@ -903,8 +929,10 @@ class Integrator(object):
                 result.save(save)
             if saveall is not None:
                 result.saveall(self, saveall)
-            if result.converged(self.rtol, self.atol):
+            if pending is None and result.converged(self.rtol, self.atol):
                 break
+        if pending is not None:
+            book(*pending)
         return result.result
 
     def _iterate_unfused(self, ctx, torch, std, pitn, flags, acc, sum_f, n_f, hs, status):

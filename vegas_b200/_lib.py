@@ -27,7 +27,7 @@ SYMBOLS = (
     'vb200_add_training_data', 'vb200_map_adapt', 'vb200_uniforms', 'vb200_fp64_peak', 'vb200_launch_count',
     'vb200_last_launch', 'vb200_eval_integrand', 'vb200_dy_profile', 'vb200_sample_from_uniforms',
     'vb200_plan_ahead', 'vb200_plan_commit', 'vb200_pdf_map', 'vb200_pdf_weight',
-    'vb200_map_adapt_device', 'vb200_get_map', 'vb200_iteration',
+    'vb200_map_adapt_device', 'vb200_get_map', 'vb200_iteration', 'vb200_iteration_begin', 'vb200_iteration_end',
 )
 
 
@@ -105,6 +105,8 @@ def load():
     L.vb200_map_adapt_device.argtypes = [vp, vp, vp, vp, i64, f64, vp, vp]
     L.vb200_get_map.argtypes = [vp, vp, i64, vp]
     L.vb200_iteration.argtypes = [vp, u32, f64, i32, vp, vp, i64, i64, i64, i64, i64, f64, f64, i64, i64, i64, vp, vp]
+    L.vb200_iteration_begin.argtypes = [vp, u32, f64, i32, vp, vp, i64, i64, i64, i64, i64, f64, f64, i64, i64, i64, vp]
+    L.vb200_iteration_end.argtypes = [vp, vp, i64, vp]
     L.vb200_fp64_peak.argtypes = [i32, i32, ctypes.POINTER(f64), ctypes.POINTER(f64)]
     L.vb200_launch_count.argtypes = [vp]
     L.vb200_launch_count.restype = i64
@@ -237,6 +239,16 @@ class Context(object):
         pn, pmin, pmax, puni = plan if plan is not None else (0., 0, 0, 0)
         check(self.L.vb200_iteration(self.h, itn, float(beta), flags, _ptr(sigf), _ptr(buf), nacc, nh, hstride, nf64, nwords,
                                      float(alpha_adapt), float(pn), int(pmin), int(pmax), int(puni), head.ctypes.data, _stream()))
+
+    def iteration_begin(self, itn, beta, flags, sigf, buf, nacc, nh, hstride, nf64, nwords, alpha_adapt, plan):
+        """launch half of :meth:`iteration` (``vb200_iteration_begin``): returns with the kernels in flight"""
+        pn, pmin, pmax, puni = plan if plan is not None else (0., 0, 0, 0)
+        check(self.L.vb200_iteration_begin(self.h, itn, float(beta), flags, _ptr(sigf), _ptr(buf), nacc, nh, hstride, nf64,
+                                           nwords, float(alpha_adapt), float(pn), int(pmin), int(pmax), int(puni), _stream()))
+
+    def iteration_end(self, head):
+        """wait for the iteration :meth:`iteration_begin` launched and fetch its head (``vb200_iteration_end``)"""
+        check(self.L.vb200_iteration_end(self.h, head.ctypes.data, head.size, _stream()))
 
     def sample(self, itn, c0, c1, x, wgt, y=None, jac1d=None, hcube=None, transposed=False, bins=None, u=None):
         """``u``: uniforms [rows, dim] supplied by the caller (``ran_array_generator``) instead of Philox"""

@@ -74,9 +74,15 @@ struct vb200_ctx {
     DevBuf fparams;                   // device arrays the functor points to
     // scratch
     DevBuf partials, scratch, counter;
+    DevBuf ecounter;                  // the engine's work-item counter (zero between launches: k_finalize resets it)
     DevBuf sigf_shadow;               // engine output of sigf while chunks are split into items (see run_engine)
+    // vb200_iteration_begin/_end: pinned, device-mapped landing zone of the iteration head
+    void* head_host = nullptr;
+    void* head_dev = nullptr;
+    int64_t head_pending = 0;         // words the iteration in flight will deliver (0: none)
     int64_t launches = 0;
 };
+#define VB_HEAD_WORDS 128
 
 // work items of a local chunk range, per geometry (see set_items in vegas_b200.cu)
 struct ItemsSel { const int64_t* off[2]; int64_t begin[2], end[2]; };

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) k_map_adapt(MapP m, double* grid, const d
                                                    const int* __restrict__ status)
 {
     extern __shared__ double ad_s[];           // w [n] | tmp -> prefix sums [n] | old nodes [n + 1]
-    __shared__ double red[8], seg_s[256];
+    __shared__ double red[8];
     const int d = blockIdx.x, n = m.ninc[d], tid = threadIdx.x, NT = blockDim.x;
     if (status != nullptr && status[0] != 0) return;          // the integrand returned NaN: the caller raises, the map stays
     double* w = ad_s;
@@ -286,10 +286,17 @@ __global__ void __launch_bounds__(256) k_map_adapt(MapP m, double* grid, const d
     const int per = (n + NT - 1) / NT, lo = min(tid * per, n), hi = min(lo + per, n);
     double run = 0.;
     for (int i = lo; i < hi; ++i) { run += w[i]; tmp[i] = run; }
-    seg_s[tid] = run;
+    double scan = run;                                         // exclusive scan of the segments' sums: warp scans + the warps' totals
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, scan, o);
+        if ((tid & 31) >= o) scan += y;
+    }
+    __syncthreads();                                           // (red is still being read by adapt_block_sum's tail)
+    if ((tid & 31) == 31) red[tid >> 5] = scan;
     __syncthreads();
-    double off = 0.;
-    for (int t = 0; t < tid; ++t) off += seg_s[t];             // (256 broadcast reads; n is a few thousand at most)
+    double off = scan - run;
+    for (int w = 0; w < (tid >> 5); ++w) off += red[w];
     for (int i = lo; i < hi; ++i) tmp[i] += off;
     __syncthreads();
     for (int i = 1 + tid; i < n; i += NT) {

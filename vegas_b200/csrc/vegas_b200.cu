@@ -53,7 +53,8 @@ extern "C" void vb200_destroy(vb200_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     c->grid.release(); c->chunk_tot.release(); c->chunk_off.release(); c->chunk_items.release(); c->item_off.release(); c->super_items.release(); c->super_item_off.release(); c->stats.release();
-    c->fparams.release(); c->partials.release(); c->scratch.release(); c->counter.release(); c->sigf_shadow.release();
+    if (c->head_host) cudaFreeHost(c->head_host);
+    c->fparams.release(); c->partials.release(); c->scratch.release(); c->counter.release(); c->ecounter.release(); c->sigf_shadow.release();
     delete c;
 }
 
@@ -238,12 +239,15 @@ extern "C" int vb200_set_integrand(vb200_ctx* c, int id, const void* params, siz
 // ---------------------------------------------------------------------------------------------
 // allocation pre-pass + chunk offsets
 // ---------------------------------------------------------------------------------------------
-// stats: [0] sum  [1] min  [2] max  [3] largest chunk total  [4] items  [5] items of the light geometry
+// stats: [0] sum  [1] VB_STAT_MIN_TOP - min  [2] max  [3] largest chunk total  [4] items  [5] items of the light geometry
+// (every word starts at zero -- the minimum is kept as a maximum of its complement -- so the iteration buffer's one
+// memset is also the initialisation of the statistics that live in it)
 // chunk_items[lc] = work items chunk lc is cut into: 1, or ceil(total / item_samples) when the vegas+
 // allocation piled more than item_samples samples onto its cubes (engine.cuh, "items").  The engine
 // never splits a cube (items that no cube starts in are empty); the samplers split by rows.
 // sum_sigf_dev != nullptr (planning ahead, vb200_plan_ahead): neval_sigf = neval_scaled / *sum_sigf_dev is
 // formed here, with the same correctly rounded division the host performs once it has read sum_sigf back
+#define VB_STAT_MIN_TOP 0x7fffffffffffffffLL
 __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t nchunks, int32_t* neval_out,
                                                 long long* chunk_tot, long long* chunk_items, long long item_samples,
                                                 long long* stats, const double* sum_sigf_dev, double neval_scaled)
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(VB_NT) k_plan(StrataP st, AllocP al, int64_t n
     if (tid == 0) {
         for (int i = 1; i < VB_NT / 32; ++i) { my_min = min(my_min, rmin[i]); my_max = max(my_max, rmax[i]); }
         atomicAdd((unsigned long long*)&stats[0], (unsigned long long)my_sum);
-        atomicMin(&stats[1], (long long)my_min);
+        atomicMax(&stats[1], VB_STAT_MIN_TOP - (long long)my_min);
         atomicMax(&stats[2], (long long)my_max);
         atomicMax(&stats[3], my_maxc);
         atomicAdd((unsigned long long*)&stats[4], (unsigned long long)my_items);
@@ -348,7 +352,7 @@ __global__ void k_super_items(const long long* chunk_tot, int64_t nchunks, int g
 // launch the allocation pre-pass; statistics (6 int64, see above) go to stats_dev.  No synchronisation.
 static int plan_launch(vb200_ctx* c, const double* sigf_dev, double neval_sigf, const double* sum_sigf_dev, double neval_scaled,
                        int64_t min_nh, int64_t max_nh, int64_t uniform_neval, int32_t* neval_hcube_dev, long long* stats_dev,
-                       cudaStream_t st)
+                       cudaStream_t st, bool stats_zeroed = false)
 {
     if (!c->have_strata) return fail(-1, "vb200_plan: call vb200_set_strata first");
     if (min_nh < 1 || min_nh > 0x7fffffff || uniform_neval > 0x7fffffff)
@@ -375,14 +379,17 @@ static int plan_launch(vb200_ctx* c, const double* sigf_dev, double neval_sigf, 
     if (item_samples <= 0) item_samples = (long long)VB_ITEM * nch / (32LL * c->sm_count);
     if (item_samples > VB_ITEM && !vb_env_int("VB200_ITEM", 0)) item_samples = VB_ITEM;
     if (item_samples < 256) item_samples = 256;
-    const long long init[6] = {0, 0x7fffffffffffffffLL, 0, 0, 0, 0};
-    CK(cudaMemcpyAsync(stats_dev, init, sizeof init, cudaMemcpyHostToDevice, st));
+    // the light geometry's chunks are planned only where run_engine can use them (same test as there)
+    const int force_light = vb_env_int("VB200_LIGHT", -1);
+    const bool plan_light = c->light_hint && nch > 0 && force_light != 0
+                            && (force_light == 1 || c->st.nlocal >= (int64_t)VB_LCH * 4 * c->sm_count);
+    if (!stats_zeroed) CK(cudaMemsetAsync(stats_dev, 0, sizeof(long long) * 6, st));
     if (nch > 0) {
         int grid = (int)(nch < (int64_t)c->sm_count * 8 ? nch : (int64_t)c->sm_count * 8);
         k_plan<<<grid, VB_NT, 0, st>>>(c->st, c->al, nch, neval_hcube_dev, (long long*)c->chunk_tot.p,
                                        (long long*)c->chunk_items.p, item_samples, stats_dev, sum_sigf_dev, neval_scaled);
         c->launches += 1;
-        if (c->light_hint) {
+        if (plan_light) {
             const int group = VB_LCH / VB_CH;
             c->nsuper = (nch + group - 1) / group;
             CK(c->super_items.ensure(sizeof(long long) * (size_t)(c->nsuper + 1)));
@@ -394,7 +401,7 @@ static int plan_launch(vb200_ctx* c, const double* sigf_dev, double neval_sigf, 
         }
         CK(cudaGetLastError());
     }
-    c->plan_light = c->light_hint;
+    c->plan_light = plan_light;
     return 0;
 }
 
@@ -403,6 +410,7 @@ static void plan_install(vb200_ctx* c, const long long out_in[6])
 {
     long long out[6];
     memcpy(out, out_in, sizeof out);
+    out[1] = VB_STAT_MIN_TOP - out[1];
     const int64_t nch = c->nchunks;
     c->plan_super_items = (c->plan_light && nch > 0) ? out[5] : -1;
     if (nch == 0) out[1] = 0;
@@ -533,15 +541,20 @@ extern "C" int vb200_chunk_offsets(vb200_ctx* c, int64_t* out_host, int64_t coun
 // ---------------------------------------------------------------------------------------------
 // engine launches
 // ---------------------------------------------------------------------------------------------
-// acc[j] += sum over CTAs of partials[cta][j], serial in CTA order (deterministic)
-__global__ void k_finalize(const double* partials, int nblocks, int nacc, double* acc)
+// acc[j] += sum over CTAs of partials[cta][j]: lane l adds CTAs l, l + 32, ... in order, then a fixed shuffle tree
+// (deterministic for a given grid; one thread walking 592 partials was 5-10 us of a 0.1 ms iteration)
+__global__ void __launch_bounds__(1024) k_finalize(const double* partials, int nblocks, int nacc, double* acc,
+                                                   unsigned long long* work_counter)
 {
-    int j = threadIdx.x;
-    if (j < nacc) {
+    const int lane = threadIdx.x & 31;
+    for (int j = threadIdx.x >> 5; j < nacc; j += (int)(blockDim.x >> 5)) {       // one warp per accumulator
         double t = 0.0;
-        for (int b = 0; b < nblocks; ++b) t += partials[(size_t)b * nacc + j];
-        acc[j] += t;
+        for (int b = lane; b < nblocks; b += 32) t += partials[(size_t)b * nacc + j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) acc[j] += t;
     }
+    if (threadIdx.x == 0) *work_counter = 0ull;      // the engine's item counter starts the next launch at zero
 }
 
 static int fill_engine(vb200_ctx* c, EngineP& p, uint32_t itn, double beta, int flags, double* sigf, double* sum_f,
@@ -617,9 +630,11 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
         CK(c->scratch.ensure(sizeof(double) * (size_t)grid * nf * (size_t)c->plan_max));
         p.scratch = (double*)c->scratch.p;
     }
-    CK(c->counter.ensure(sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), st));
-    p.work_counter = (unsigned long long*)c->counter.p;
+    if (!c->ecounter.p) {                              // zeroed once; k_finalize puts it back to zero after every launch
+        CK(c->ecounter.ensure(sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(c->ecounter.p, 0, sizeof(unsigned long long), st));
+    }
+    p.work_counter = (unsigned long long*)c->ecounter.p;
     // sigf is updated in place and also drives the allocation: while a chunk is shared by several
     // CTAs (items), one of them must not see the new sigf of a cube another has already finished
     // -> write to a shadow buffer and copy the launch's cube range back afterwards
@@ -639,7 +654,7 @@ static int run_engine(vb200_ctx* c, EngineP& p, int nf, bool fused, double* acc,
     }
     c->last_grid = g2; c->last_bps = cfg.blocks_per_sm; c->last_smem = (int64_t)cfg.smem; c->last_wtot = cfg.wtot;
     c->last_nt = cfg.nt; c->last_ch = cfg.ch;
-    k_finalize<<<1, 64, 0, st>>>(p.partials, g2, nacc, acc);
+    k_finalize<<<1, 32 * (nacc < 32 ? nacc : 32), 0, st>>>(p.partials, g2, nacc, acc, p.work_counter);
     c->launches += 2;
     CK(cudaGetLastError());
     return 0;
@@ -695,14 +710,27 @@ extern "C" int vb200_reduce(vb200_ctx* c, uint32_t itn, double beta, int flags, 
 //         [nf64 + nh + 1, + 7)      statistics of the pre-pass
 // head_host receives words [0, nacc) and the 7 words from the NaN flag on (nacc + 7 doubles).
 // ---------------------------------------------------------------------------------------------
-extern "C" int vb200_iteration(vb200_ctx* c, uint32_t itn, double beta, int flags, double* sigf_dev, void* buf_dev,
-                               int64_t nacc, int64_t nh, int64_t hstride, int64_t nf64, int64_t nwords, double alpha_adapt,
-                               double plan_neval_scaled, int64_t plan_min, int64_t plan_max, int64_t plan_uniform,
-                               double* head_host, void* stream)
+// the head of the iteration buffer, gathered into pinned host memory the device writes directly (two small
+// device-to-host copies into pageable memory cost ~20 us of a 0.1 ms iteration)
+__global__ void k_head(const double* __restrict__ f, int nacc, const long long* __restrict__ tail, double* __restrict__ out)
 {
-    if (!c || !buf_dev || !head_host) return fail(-1, "vb200_iteration: null argument");
+    for (int i = threadIdx.x; i < nacc + 7; i += blockDim.x) out[i] = i < nacc ? f[i] : __longlong_as_double(tail[i - nacc]);
+}
+
+extern "C" int vb200_iteration_begin(vb200_ctx* c, uint32_t itn, double beta, int flags, double* sigf_dev, void* buf_dev,
+                                     int64_t nacc, int64_t nh, int64_t hstride, int64_t nf64, int64_t nwords, double alpha_adapt,
+                                     double plan_neval_scaled, int64_t plan_min, int64_t plan_max, int64_t plan_uniform,
+                                     void* stream)
+{
+    if (!c || !buf_dev) return fail(-1, "vb200_iteration: null argument");
+    if (nacc < 1 || nacc + 7 > VB_HEAD_WORDS) return fail(-1, "vb200_iteration: nacc=%lld outside 1..%d", (long long)nacc, VB_HEAD_WORDS - 7);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(c->device));
+    if (!c->head_host) {
+        CK(cudaHostAlloc(&c->head_host, sizeof(double) * VB_HEAD_WORDS, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer(&c->head_dev, c->head_host, 0));
+    }
+    c->head_pending = 0;
     double* f = (double*)buf_dev;
     int64_t* iw = (int64_t*)buf_dev + nf64;
     CK(cudaMemsetAsync(buf_dev, 0, sizeof(double) * (size_t)nwords, st));
@@ -713,13 +741,40 @@ extern "C" int vb200_iteration(vb200_ctx* c, uint32_t itn, double beta, int flag
         if (rc) return rc;
     }
     if (plan_neval_scaled > 0) {
-        rc = vb200_plan_ahead(c, sigf_dev, f + nacc - 1, plan_neval_scaled, plan_min, plan_max, plan_uniform, iw + nh + 1, stream);
+        if (!sigf_dev) return fail(-1, "vb200_iteration: planning ahead needs sigf");
+        rc = plan_launch(c, sigf_dev, 0.0, f + nacc - 1, plan_neval_scaled, plan_min, plan_max, plan_uniform, nullptr,
+                         (long long*)(iw + nh + 1), st, true);          // (the statistics were zeroed with the buffer)
         if (rc) return rc;
     }
-    CK(cudaMemcpyAsync(head_host, f, sizeof(double) * (size_t)nacc, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(head_host + nacc, iw + nh, sizeof(int64_t) * 7, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    k_head<<<1, 64, 0, st>>>(f, (int)nacc, (const long long*)(iw + nh), (double*)c->head_dev);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    c->head_pending = nacc + 7;
     return 0;
+}
+
+extern "C" int vb200_iteration_end(vb200_ctx* c, double* head_host, int64_t nhead, void* stream)
+{
+    if (!c || !head_host) return fail(-1, "vb200_iteration_end: null argument");
+    if (c->head_pending == 0 || nhead != c->head_pending)
+        return fail(-1, "vb200_iteration_end: %lld words asked, %lld in flight", (long long)nhead, (long long)c->head_pending);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    memcpy(head_host, c->head_host, sizeof(double) * (size_t)nhead);
+    c->head_pending = 0;
+    return 0;
+}
+
+extern "C" int vb200_iteration(vb200_ctx* c, uint32_t itn, double beta, int flags, double* sigf_dev, void* buf_dev,
+                               int64_t nacc, int64_t nh, int64_t hstride, int64_t nf64, int64_t nwords, double alpha_adapt,
+                               double plan_neval_scaled, int64_t plan_min, int64_t plan_max, int64_t plan_uniform,
+                               double* head_host, void* stream)
+{
+    if (!head_host) return fail(-1, "vb200_iteration: null argument");
+    int rc = vb200_iteration_begin(c, itn, beta, flags, sigf_dev, buf_dev, nacc, nh, hstride, nf64, nwords, alpha_adapt,
+                                   plan_neval_scaled, plan_min, plan_max, plan_uniform, stream);
+    if (rc) return rc;
+    return vb200_iteration_end(c, head_host, nacc + 7, stream);
 }
 
 extern "C" int64_t vb200_launch_count(vb200_ctx* c) { return c ? c->launches : 0; }
