@@ -681,3 +681,49 @@ def test_one_call_iteration_equals_general_path(monkeypatch):
         np.testing.assert_allclose(ia.map.grid, ib.map.grid, rtol=1e-11, atol=1e-14)
         np.testing.assert_allclose(ia.sigf, ib.sigf, rtol=1e-8)
         assert abs(ra.mean - 1) < 5 * ra.sdev
+
+
+def test_deferred_bookkeeping_changes_nothing(monkeypatch):
+    """iteration i booked behind the kernels of i+1 (vb200_iteration_begin/_end) against booking right away: the same
+    per-iteration results; tolerances (rtol) switch the overlap off and still stop at the same iteration as the general
+    path; a NaN still raises; _end without _begin is an error, not a hang"""
+    vegas = _vegas()
+    from vegas_b200 import _lib
+    f = vegas.integrands.GaussMix([4 * [0.5]], 100., 1013.2118364296088)
+    runs = {}
+
+    def run(key, env, kw):
+        for k in ('VB200_NO_DEFER', 'VB200_NO_FAST_ITERATION'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        integ = vegas.Integrator([[-1., 1.]] + 3 * [[0., 1.]], neval=10000, seed=5)
+        runs[key] = integ(f, nitn=8, **kw)
+
+    run('defer', {}, {})
+    run('now', {'VB200_NO_DEFER': '1'}, {})
+    # a tolerance the weighted average reaches at the 4th iteration (or earlier), from the run just made
+    first4 = runs['defer'].itn_results[:4]
+    rtol = 1.2 / np.sqrt(sum(1. / x.sdev ** 2 for x in first4)) / abs(runs['defer'].mean)
+    run('rtol', {}, dict(rtol=rtol))
+    run('rtol_general', {'VB200_NO_FAST_ITERATION': '1'}, dict(rtol=rtol))
+    a, b = runs['defer'], runs['now']
+    assert len(a.itn_results) == len(b.itn_results) == 8
+    # (not bit-identical: the order of the histogram's fp64 atomics differs from run to run)
+    np.testing.assert_allclose([x.mean for x in a.itn_results], [x.mean for x in b.itn_results], rtol=1e-11)
+    np.testing.assert_allclose([x.sdev for x in a.itn_results], [x.sdev for x in b.itn_results], rtol=1e-8)
+    np.testing.assert_allclose([a.mean, a.sdev], [b.mean, b.sdev], rtol=1e-9)
+    assert a.sum_neval == b.sum_neval
+    c, d = runs['rtol'], runs['rtol_general']
+    assert 1 <= len(c.itn_results) == len(d.itn_results) <= 4 and c.sdev < rtol * abs(c.mean)
+    for k in ('VB200_NO_DEFER', 'VB200_NO_FAST_ITERATION'):
+        monkeypatch.delenv(k, raising=False)
+    integ = vegas.Integrator([[0., 1.]], neval=1000, seed=1)
+    integ(vegas.integrands.Poly(1., [1.], [1]), nitn=3)
+    with pytest.raises(ValueError, match='nan'):
+        integ(vegas.integrands.Poly(float('nan'), [1.], [1]), nitn=3)
+    r = integ(vegas.integrands.Poly(1., [1.], [1]), nitn=3)          # the integrator is usable afterwards
+    assert abs(r.mean - 1.5) < 5 * r.sdev + 1e-9
+    ctx = _lib.Context(None)
+    with pytest.raises(_lib.VegasB200Error):
+        ctx.iteration_end(np.empty(10))

@@ -167,6 +167,17 @@ class Integrator(object):
         self.set(odict)
 
     # ------------------------------------------------------------------ sigf: host view of device state
+    # (a new device tensor -- never an in-place update by the kernels -- voids a pre-pass launched ahead: it may have
+    # been left waiting by the last iteration of an earlier call)
+    @property
+    def _sigf_dev(self):
+        return self.__dict__.get('_sigf_dev_t')
+
+    @_sigf_dev.setter
+    def _sigf_dev(self, t):
+        self.__dict__['_sigf_dev_t'] = t
+        self._plan_ahead = None
+
     def _get_sigf(self):
         if self._sigf_dev is not None:
             local = self._sigf_dev.cpu().numpy()
@@ -813,9 +824,10 @@ class Integrator(object):
             dev_adapt = (bool(flags & _lib.TRAIN) and self.alpha > 0 and self.adapt and self.analyzer is None
                          and self._trace is None and self.map.sum_f is None and int(np.min(self.map.ninc)) > 1
                          and not env_host_adapt)
-            # the next iteration's allocation pre-pass rides behind this one (sum_sigf is final on the device)
-            plan_next = bool((flags & _lib.UPDATE_SIGF) and itn + 1 < self.nitn and self._sigf_dev is not None
-                             and not env_no_ahead)
+            # the next iteration's allocation pre-pass rides behind this one (sum_sigf is final on the device) -- behind
+            # the last one of a call as well: the next call usually continues with the same settings (_plan_key decides),
+            # and a 4 us kernel here saves it the synchronous pre-pass, a third of a one-iteration call at everyday sizes
+            plan_next = bool((flags & _lib.UPDATE_SIGF) and self._sigf_dev is not None and not env_no_ahead)
             # Everyday sizes: the whole iteration in one library call (vb200_iteration: zero, engine, adapt, pre-pass
             # of the next iteration, one small copy back) -- a handful of binding calls cost more than the kernels.
             fast = (device_fcn is not None and world == 1 and self._timing is None and self._trace is None

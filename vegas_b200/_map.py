@@ -99,7 +99,7 @@ class AdaptiveMap(object):
     @property
     def dim(self):
         " Number of dimensions."
-        return self.grid.shape[0]
+        return self._grid.shape[0]         # (the shape only: no copy back of a device-adapted grid)
 
     def region(self, d=-1):
         r""" x-space region: ``(xl, xu)`` for direction ``d``, or the list for all directions. """
