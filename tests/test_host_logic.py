@@ -571,3 +571,22 @@ def test_save_only_on_the_writer_rank(tmp_path):
     assert len(calls) == 2                       # the integrator was pickled on the non-writer too
     r, i = pickle.load(open(str(tmp_path / 'a1.pkl'), 'rb'))
     assert abs(r.mean - 1.0) < 1e-12 and i == {}
+
+
+def test_replacing_sigf_voids_a_waiting_prepass():
+    """the allocation pre-pass launched behind the last iteration of a call waits for the next call
+    (Integrator._plan_ahead); every replacement of the device copy of sigf -- set(sigf=...), a new stratification, a
+    new context -- must void it (the caching allocator may hand the new tensor the old address, so the address in
+    _plan_key proves nothing), while reading it back does not"""
+    integ = vegas.Integrator(3 * [[0., 1.]], neval=1000)
+    integ._plan_ahead = ('key', None)
+    assert integ._sigf_dev is None and integ._plan_ahead == ('key', None)
+    integ.set(sigf=np.ones(integ.nhcube))
+    assert integ._plan_ahead is None
+    integ._plan_ahead = ('key', None)
+    integ.set(nstrat=[2, 2, 2])
+    assert integ._plan_ahead is None
+    integ._plan_ahead = ('key', None)
+    integ._sigf_dev_stale()                      # nothing on the device: nothing replaced
+    assert integ._plan_ahead == ('key', None)
+    assert '_sigf_dev_t' in integ.__dict__ and '_sigf_dev' not in integ.__dict__
