@@ -943,7 +943,7 @@ __global__ void __launch_bounds__(Src::NT, Src::MINB) k_engine(const __grid_cons
 
     if (p.wtot > 0) hist_flush<NT>(p, H, nullptr);               // the loop exits through a barrier
 
-    // ---- per-CTA partial sums (fixed tree inside the CTA), finished by k_finalize in CTA order
+    // ---- per-CTA partial sums (fixed tree inside the CTA), finished by k_finalize (fixed order over the CTAs)
     constexpr int NACC = NF + NV + 1;
     double* out = p.partials + (size_t)blockIdx.x * NACC;
 #pragma unroll
