@@ -590,3 +590,76 @@ def test_replacing_sigf_voids_a_waiting_prepass():
     integ._sigf_dev_stale()                      # nothing on the device: nothing replaced
     assert integ._plan_ahead == ('key', None)
     assert '_sigf_dev_t' in integ.__dict__ and '_sigf_dev' not in integ.__dict__
+
+
+def test_integrand_adapters_every_argument_and_value_form():
+    """VegasIntegrand.eval over the whole matrix the reference supports (pyx:2959-3383): x presented as flat rows,
+    as an index array of xsample's shape or as a dictionary; one point at a time, lbatch, rbatch; values that are
+    numbers, arrays or dictionaries; with and without jac.  Expected rows are computed directly from the flat
+    x[n, D].  (jac reaches a one-point function by keyword for flat x, as second argument for a dictionary, and
+    not at all for an index array: pyx:3200-3213.)"""
+    import itertools
+    from vegas_b200._integrand import VegasIntegrand
+    D, n = 6, 5
+    xsamples = dict(flat=np.linspace(0.1, 0.6, D), grid=np.arange(6.).reshape(2, 3) / 10.,
+                    dict=gv.BufferDict([('a', 0.5), ('b', np.array([0.1, 0.2, 0.3])), ('c', np.array([[0.7, 0.8]]))]))
+
+    def flatten(xa, kind):       # whatever the user function was handed -> c[D] (one point) or c[D, n]
+        parts = [np.asarray(xa[k]) for k in xa] if hasattr(xa, 'keys') else [np.asarray(xa)]
+        if kind == 'scalar':
+            return np.concatenate([p.reshape(-1) for p in parts])
+        if kind == 'lbatch':
+            return np.concatenate([p.reshape(p.shape[0], -1) for p in parts], axis=1).T
+        return np.concatenate([p.reshape(-1, p.shape[-1]) for p in parts], axis=0)
+
+    def user(kind, out, with_jac):
+        def body(x, jac=None):
+            c = flatten(x, kind)
+            if jac is not None:
+                c = c * (1 + flatten(jac, kind))
+            s, v = c.sum(axis=0), [c[0] * c[1], np.sin(c[2]), c[3] ** 2]
+            m = [[c[i] * c[j] for j in (2, 3, 4)] for i in (0, 1)]
+            if kind == 'lbatch':       # batch index first
+                v, m = np.stack(v, axis=-1), np.moveaxis(np.array(m), -1, 0)
+            else:
+                v, m = np.array(v), np.array(m)
+            return dict(number=s, vector=v, matrix=m, dictionary=dict(s=s, v=v, m=m))[out]
+        f = (lambda x, jac=None: body(x, jac)) if with_jac else (lambda x: body(x))
+        return dict(scalar=lambda g: g, lbatch=vegas.lbatchintegrand, rbatch=vegas.rbatchintegrand)[kind](f)
+
+    rng = np.random.default_rng(2)
+    for (xname, xs), kind, out, with_jac in itertools.product(xsamples.items(), ('scalar', 'lbatch', 'rbatch'),
+                                                              ('number', 'vector', 'matrix', 'dictionary'), (False, True)):
+        std = VegasIntegrand(user(kind, out, with_jac), None, with_jac, xs, False)
+        x, jac = rng.uniform(size=(n, D)), (rng.uniform(size=(n, D)) if with_jac else None)
+        c = x if (jac is None or (kind == 'scalar' and xname == 'grid')) else x * (1 + jac)
+        s, v = c.sum(axis=1)[:, None], np.stack([c[:, 0] * c[:, 1], np.sin(c[:, 2]), c[:, 3] ** 2], axis=1)
+        m = np.einsum('ni,nj->nij', c[:, :2], c[:, 2:5]).reshape(n, 6)
+        want = dict(number=s, vector=v, matrix=m, dictionary=np.concatenate([s, v, m], axis=1))[out]
+        label = (xname, kind, out, with_jac)
+        assert std.size == want.shape[1] and std.fcntype == kind, label
+        assert std.shape == dict(number=(), vector=(3,), matrix=(2, 3), dictionary=None)[out], label
+        got = std.eval(x, jac=jac)
+        assert got.shape == want.shape, label
+        np.testing.assert_allclose(got, want, rtol=1e-15, atol=0, err_msg=str(label))
+        np.testing.assert_array_equal(std.training(x, jac), got[:, 0])
+        # the value's own structure back: means, GVars from a covariance matrix / from variances, evalx
+        mean, cov = got.mean(axis=0), np.cov(got.T).reshape(std.size, std.size) + 1e-3 * np.eye(std.size)
+        for formatted, sd in ((std.format_result(mean), None), (std.format_result(mean, cov), np.sqrt(np.diag(cov))),
+                              (std.format_result(mean, np.diag(cov).copy()), np.sqrt(np.diag(cov)))):
+            if out == 'dictionary':
+                assert list(formatted.keys()) == ['s', 'v', 'm'] and np.shape(formatted['m']) == (2, 3)
+                flat = formatted.buf
+            else:
+                assert np.shape(formatted) == std.shape
+                flat = np.reshape(formatted, -1)
+            np.testing.assert_allclose(gv.mean(flat) if sd is not None else np.asarray(flat, float), mean, rtol=1e-15)
+            if sd is not None:
+                np.testing.assert_allclose(gv.sdev(flat), sd, rtol=1e-12)
+        ex = std.format_evalx(got)
+        if out == 'dictionary':
+            assert np.shape(ex['v']) == (n, 3) and np.shape(ex['s']) == (n,)
+        else:
+            assert ex.shape == (n,) + std.shape
+        one = std(x[0], jac=None if jac is None else jac[:1])
+        np.testing.assert_allclose(one.buf if out == 'dictionary' else np.reshape(one, -1), got[0], rtol=1e-15)

@@ -15,57 +15,56 @@ from ._gv import gv
 
 
 # --------------------------------------------------------------------------- decorators / containers
-class LBatchIntegrand(object):
-    r""" Wrapper for lbatch integrands (``x[i, d]``, batch index on the left). """
+class _BatchWrapper(object):
+    """callable that marks a batch integrand: wraps ``fcn`` or -- subclassed with its own ``__call__`` -- is the
+    integrand itself; unknown attributes are looked up on the wrapped function"""
+    fcntype = None
 
     def __init__(self, fcn=None):
         self.fcn = self if fcn is None else fcn
 
+    def __call__(self, *args, **kargs):
+        return self.fcn(*args, **kargs)
+
+    def __getattr__(self, attr):
+        if attr == 'fcn' or self.fcn is self:
+            raise AttributeError(attr)
+        return getattr(self.fcn, attr)
+
+
+class LBatchIntegrand(_BatchWrapper):
+    r""" Wrapper for lbatch integrands (``x[i, d]``, batch index on the left). """
     fcntype = 'lbatch'
 
-    def __call__(self, *args, **kargs):
-        return self.fcn(*args, **kargs)
 
-    def __getattr__(self, attr):
-        if attr == 'fcn' or self.fcn is self:
-            raise AttributeError(attr)
-        return getattr(self.fcn, attr)
-
-
-class RBatchIntegrand(object):
+class RBatchIntegrand(_BatchWrapper):
     r""" Same as :class:`LBatchIntegrand` but with batch indices on the right (``x[d, i]``). """
-
-    def __init__(self, fcn=None):
-        self.fcn = self if fcn is None else fcn
-
     fcntype = 'rbatch'
 
-    def __call__(self, *args, **kargs):
-        return self.fcn(*args, **kargs)
 
-    def __getattr__(self, attr):
-        if attr == 'fcn' or self.fcn is self:
-            raise AttributeError(attr)
-        return getattr(self.fcn, attr)
+def _tag(f, wrapper, **marks):
+    """mark ``f`` itself when it accepts attributes (the meaning of ``f(x)`` is unchanged), else wrap it"""
+    try:
+        for k, v in marks.items():
+            setattr(f, k, v)
+        f.fcntype = wrapper.fcntype
+        return f
+    except Exception:
+        w = wrapper(f)
+        for k, v in marks.items():
+            setattr(w, k, v)
+        return w
 
 
 def lbatchintegrand(f):
     r""" Decorator for batch integrand functions ``f(x[i, d]) -> f[i]`` (or arrays / dicts with a
     leading batch index).  The meaning of ``f(x)`` is unchanged. """
-    try:
-        f.fcntype = 'lbatch'
-        return f
-    except Exception:
-        return LBatchIntegrand(f)
+    return _tag(f, LBatchIntegrand)
 
 
 def rbatchintegrand(f):
     r""" Same as :func:`lbatchintegrand` but with batch indices on the right. """
-    try:
-        f.fcntype = 'rbatch'
-        return f
-    except Exception:
-        return RBatchIntegrand(f)
+    return _tag(f, RBatchIntegrand)
 
 
 def devicebatchintegrand(f):
@@ -73,14 +72,7 @@ def devicebatchintegrand(f):
     ``torch.Tensor`` ``x[i, d]`` (DLPack-exportable: ``cupy.from_dlpack(x)``, ``jax.dlpack`` ...)
     and returns a CUDA tensor (or any object exporting ``__dlpack__``) ``f[i]`` or ``f[i, ...]``.
     Samples and integrand values then stay in HBM (the unfused device-callback path). """
-    try:
-        f.fcntype = 'lbatch'
-        f.on_device = True
-        return f
-    except Exception:
-        w = LBatchIntegrand(f)
-        w.on_device = True
-        return w
+    return _tag(f, LBatchIntegrand, on_device=True)
 
 
 # legacy names (reference _vegas.pyx:3465-3473)
@@ -134,147 +126,84 @@ class DeviceIntegrand(object):
 
 
 # --------------------------------------------------------------------------- standard form
-class _Base(object):
-    """manages xsample: how flat x rows are presented to the user function"""
-
-    def __init__(self, fcn, xsample):
-        self.fcn = fcn
-        self.xsample = xsample
-        if xsample.shape is None:
-            self.dict_arg, self.std_arg = True, False
-        else:
-            self.dict_arg, self.std_arg = False, len(xsample.shape) == 1
-
-    def _one(self, x, jac=None):
-        " fcn(x) for one point when the argument is a dict or a multi-index array "
-        x = np.asarray(x)
-        if self.dict_arg:
-            xd = gv.BufferDict(self.xsample, buf=x)
-            if jac is not None:
-                return self.fcn(xd, gv.BufferDict(self.xsample, buf=jac))
-            return self.fcn(xd)
-        return self.fcn(x.reshape(self.xsample.shape))
-
-    def _batch(self, x, jac=None):
-        " fcn(x) for a batch when the argument is a dict or a multi-index array "
-        x = np.asarray(x)
-        if self.dict_arg:
-            if self.rbatch:
-                xd = gv.BufferDict(self.xsample, rbatch_buf=x.T)
-                if jac is not None:
-                    jac = gv.BufferDict(self.xsample, rbatch_buf=jac.T)
-            else:
-                xd = gv.BufferDict(self.xsample, lbatch_buf=x)
-                if jac is not None:
-                    jac = gv.BufferDict(self.xsample, lbatch_buf=jac)
-            return self.fcn(xd) if jac is None else self.fcn(xd, jac=jac)
-        if self.rbatch:
-            sh = self.xsample.shape + (-1,)
-            return self.fcn(x.T.reshape(sh)) if jac is None else self.fcn(x.T.reshape(sh), jac=jac.T.reshape(sh))
-        sh = (-1,) + self.xsample.shape
-        return self.fcn(x.reshape(sh)) if jac is None else self.fcn(x.reshape(sh), jac=jac.reshape(sh))
+# Every host integrand becomes  eval(x[n, D], jac[n, D] | None) -> f[n, size]  by composing two pieces, both
+# chosen once from the probe call (the reference has one class per combination, _vegas.pyx:3175-3383):
+#   presenter  rows -> the argument the user function takes: flat rows, an index array of xsample's shape, or a
+#              dictionary; one point at a time, or a batch with its index on the left / on the right.  jac is
+#              presented exactly like x.
+#   packer     the user function's value (number, array or dictionary; per point or per batch) -> rows of `size`.
+def _presenter(xsample, kind):
+    if xsample.shape is None:
+        if kind == 'rbatch':
+            return lambda a: gv.BufferDict(xsample, rbatch_buf=a.T)
+        if kind == 'lbatch':
+            return lambda a: gv.BufferDict(xsample, lbatch_buf=a)
+        return lambda row: gv.BufferDict(xsample, buf=row)
+    shape = tuple(xsample.shape)
+    if len(shape) == 1:
+        return (lambda a: a.T) if kind == 'rbatch' else (lambda a: a)
+    if kind == 'rbatch':
+        return lambda a: a.T.reshape(shape + (-1,))
+    if kind == 'lbatch':
+        return lambda a: a.reshape((-1,) + shape)
+    return lambda row: row.reshape(shape)
 
 
-class _FromNonBatch(_Base):
-    """ batch integrand from a scalar (one point at a time) integrand """
-
-    def __init__(self, fcn, size, shape, xsample):
-        self.size, self.shape = size, shape
-        _Base.__init__(self, fcn, xsample)
-
-    def __call__(self, x, jac=None):
-        x = np.asarray(x)
-        f = np.empty((x.shape[0], self.size), float)
-        for i in range(x.shape[0]):
-            ji = None if jac is None else jac[i]
-            if self.std_arg:
-                fx = self.fcn(x[i]) if ji is None else self.fcn(x[i], jac=ji)
-            else:
-                fx = self._one(x[i], ji)
-            if self.shape == ():
-                f[i, 0] = fx
-            else:
-                f[i] = np.asarray(fx).reshape(-1)
-        return f
+def _dict_layout(bdict):
+    """[(key, slice or index into the flat row, shape)] of a BufferDict"""
+    return [(k,) + tuple(bdict.slice_shape(k)) for k in bdict]
 
 
-class _FromNonBatchDict(_Base):
-    """ batch integrand from a scalar integrand that returns a dictionary """
+class _HostEval(object):
+    """``eval`` of a host (numpy) integrand.  ``kind``: 'scalar' | 'lbatch' | 'rbatch'; ``shape``: the value's own
+    shape, or None for a dictionary (then ``bdict`` is a sample of it)."""
 
-    def __init__(self, fcn, size, xsample):
-        self.size = size
-        _Base.__init__(self, fcn, xsample)
+    def __init__(self, fcn, xsample, kind, shape, size, bdict):
+        self.fcn, self.kind, self.shape, self.size = fcn, kind, shape, int(size)
+        self.present = _presenter(xsample, kind)
+        self.layout = None if bdict is None else _dict_layout(bdict)
+        # how jac reaches a one-point function (pyx:3200-3213): by keyword for flat x, positionally for a
+        # dictionary, not at all for an index array
+        self.point_jac = 'second' if xsample.shape is None else ('keyword' if len(xsample.shape) == 1 else 'dropped')
+
+    def _point(self, xrow, jrow):
+        xa = self.present(xrow)
+        if jrow is None or self.point_jac == 'dropped':
+            return self.fcn(xa)
+        if self.point_jac == 'second':
+            return self.fcn(xa, self.present(jrow))
+        return self.fcn(xa, jac=self.present(jrow))
 
     def __call__(self, x, jac=None):
         x = np.asarray(x)
-        f = np.empty((x.shape[0], self.size), float)
-        for i in range(x.shape[0]):
-            ji = None if jac is None else jac[i]
-            if self.std_arg:
-                fx = self.fcn(x[i]) if ji is None else self.fcn(x[i], jac=ji)
-            else:
-                fx = self._one(x[i], ji)
-            if not isinstance(fx, gv.BufferDict):
-                fx = gv.BufferDict(fx)
-            f[i] = fx.buf[:self.size]
-        return f
-
-
-class _FromBatch(_Base):
-    """ standard form of an lbatch / rbatch integrand returning arrays """
-
-    def __init__(self, fcn, rbatch, xsample):
-        self.rbatch = rbatch
-        _Base.__init__(self, fcn, xsample)
-
-    def __call__(self, x, jac=None):
-        if self.std_arg:
-            if self.rbatch:
-                fx = self.fcn(x.T) if jac is None else self.fcn(x.T, jac=jac.T)
-            else:
-                fx = self.fcn(x) if jac is None else self.fcn(x, jac=jac)
-        else:
-            fx = self._batch(x, jac)
-        if not isinstance(fx, np.ndarray):
+        n = x.shape[0]
+        if self.kind == 'scalar':
+            out = np.empty((n, self.size), float)
+            for i in range(n):
+                fx = self._point(x[i], None if jac is None else np.asarray(jac[i]))
+                if self.layout is not None:
+                    out[i] = (fx if isinstance(fx, gv.BufferDict) else gv.BufferDict(fx)).buf[:self.size]
+                elif self.shape == ():
+                    out[i, 0] = fx
+                else:
+                    out[i] = np.asarray(fx).reshape(-1)
+            return out
+        fx = self.fcn(self.present(x)) if jac is None else self.fcn(self.present(x), jac=self.present(np.asarray(jac)))
+        right = self.kind == 'rbatch'
+        if self.layout is None:
             fx = np.asarray(fx)
-        if self.rbatch:
-            return np.ascontiguousarray(fx.reshape((-1, x.shape[0])).T)
-        return fx.reshape((x.shape[0], -1))
+            return np.ascontiguousarray(fx.reshape((-1, n)).T) if right else fx.reshape((n, -1))
+        out = np.empty((n, self.size), float)
+        for k, where, shape in self.layout:
+            v = fx[k]
+            if shape != ():
+                v = np.reshape(v, (-1, n)).T if right else np.asarray(v).reshape((n, -1))
+            out[:, where] = v
+        return out
 
 
-class _FromBatchDict(_Base):
-    """ standard form of an lbatch / rbatch integrand returning a dictionary """
-
-    def __init__(self, fcn, bdict, rbatch, xsample):
-        self.size = bdict.size
-        self.rbatch = rbatch
-        self.slice = collections.OrderedDict()
-        self.shape = collections.OrderedDict()
-        for k in bdict:
-            self.slice[k], self.shape[k] = bdict.slice_shape(k)
-        _Base.__init__(self, fcn, xsample)
-
-    def __call__(self, x, jac=None):
-        buf = np.empty((x.shape[0], self.size), float)
-        if self.std_arg:
-            if self.rbatch:
-                fx = self.fcn(x.T) if jac is None else self.fcn(x.T, jac=jac.T)
-            else:
-                fx = self.fcn(x) if jac is None else self.fcn(x, jac=jac)
-        else:
-            fx = self._batch(x, jac)
-        for k in self.slice:
-            if self.shape[k] == ():
-                buf[:, self.slice[k]] = fx[k]
-            elif self.rbatch:
-                buf[:, self.slice[k]] = np.reshape(fx[k], (-1, x.shape[0])).T
-            else:
-                buf[:, self.slice[k]] = np.asarray(fx[k]).reshape((x.shape[0], -1))
-        return buf
-
-
-class _FromDeviceBatch(object):
-    """ standard form of a ``@devicebatchintegrand``: torch CUDA tensors in, [n, size] tensor out """
+class _DeviceEval(object):
+    """``eval`` of a ``@devicebatchintegrand``: torch CUDA tensors in, [n, size] tensor out"""
 
     def __init__(self, fcn):
         self.fcn = fcn
@@ -289,6 +218,12 @@ class _FromDeviceBatch(object):
         return fx.reshape(x.shape[0], -1).contiguous()
 
 
+def _strip_batch(value, kind):
+    """one point's value out of a one-point batch"""
+    v = np.asarray(value)
+    return v[..., 0] if kind == 'rbatch' else v[0]
+
+
 class VegasIntegrand(object):
     r""" Integrand object --- standard interface for integrands (``_vegas.pyx:2959-3169``).
 
@@ -300,108 +235,72 @@ class VegasIntegrand(object):
     """
 
     def __init__(self, fcn, map, uses_jac, xsample, mpi):
-        if isinstance(fcn, type) and issubclass(fcn, (LBatchIntegrand, RBatchIntegrand)):
+        if isinstance(fcn, type) and issubclass(fcn, _BatchWrapper):
             raise ValueError('integrand given is a class, not an object -- need to initialize?')
         self.mpi_nproc, self.rank = 1, 0
         self.on_device = bool(getattr(fcn, 'on_device', False))
+        self.fcntype = getattr(fcn, 'fcntype', 'scalar')
         self.bdict = None
         xsample = gv.mean(xsample)
-        x0 = xsample
-        if uses_jac:
-            if xsample.shape is None:
-                jac0 = gv.BufferDict(xsample, buf=xsample.size * [1])
-            else:
-                jac0 = np.ones(xsample.shape, dtype=float)
-        else:
-            jac0 = None
-        self.fcntype = getattr(fcn, 'fcntype', 'scalar')
+        x1 = np.array(xsample.buf if xsample.shape is None else xsample, dtype=float).reshape(1, -1)   # one row: the probe
         if self.on_device:
             import torch
-            xs = np.asarray(xsample.buf if xsample.shape is None else xsample, dtype=float).reshape(1, -1)
-            xd = torch.from_numpy(xs).cuda()
-            jd = torch.ones_like(xd) if uses_jac else None
-            fx = fcn(xd, jac=jd) if uses_jac else fcn(xd)
+            xd = torch.from_numpy(x1).cuda()
+            fx = fcn(xd, jac=torch.ones_like(xd)) if uses_jac else fcn(xd)
             if not isinstance(fx, torch.Tensor):
                 fx = torch.from_dlpack(fx)
             self.shape = tuple(fx.shape[1:])
             self.size = int(np.prod(self.shape, dtype=np.int64))
-            self.eval = _FromDeviceBatch(fcn)
-        elif self.fcntype == 'scalar':
-            fx = fcn(x0, jac=jac0) if uses_jac else fcn(x0)
+            self.eval = _DeviceEval(fcn)
+            return
+        kind = self.fcntype if self.fcntype in ('scalar', 'rbatch') else 'lbatch'
+        present = _presenter(xsample, kind)
+        if kind == 'scalar':
+            # (the probe always passes jac by keyword, as pyx:3013 does; eval follows pyx:3200-3213)
+            fx = fcn(present(x1[0]), jac=present(np.ones_like(x1[0]))) if uses_jac else fcn(present(x1[0]))
             if hasattr(fx, 'keys'):
-                if not isinstance(fx, gv.BufferDict):
-                    fx = gv.BufferDict(fx)
-                self.size, self.shape, self.bdict = fx.size, None, fx
-                self.eval = _FromNonBatchDict(fcn, self.size, xsample)
+                self.bdict = fx if isinstance(fx, gv.BufferDict) else gv.BufferDict(fx)
+                self.shape, self.size = None, self.bdict.size
             else:
                 fx = np.asarray(fx)
                 self.shape, self.size = fx.shape, fx.size
-                self.eval = _FromNonBatch(fcn, self.size, self.shape, xsample)
-        elif self.fcntype == 'rbatch':
-            if x0.shape is None:
-                x0 = gv.BufferDict(x0, rbatch_buf=x0.buf.reshape(x0.buf.shape + (1,)))
-                if uses_jac:
-                    jac0 = gv.BufferDict(jac0, rbatch_buf=jac0.buf.reshape(jac0.buf.shape + (1,)))
-            else:
-                x0 = x0.reshape(x0.shape + (1,))
-                if uses_jac:
-                    jac0 = jac0.reshape(jac0.shape + (1,))
-            fx = fcn(x0, jac=jac0) if uses_jac else fcn(x0)
-            if hasattr(fx, 'keys'):
-                fxs = gv.BufferDict()
-                for k in fx:
-                    fxs[k] = np.asarray(fx[k])[..., 0]
-                self.shape, self.bdict, self.size = None, fxs, fxs.size
-                self.eval = _FromBatchDict(fcn, self.bdict, True, xsample)
-            else:
-                self.shape = np.shape(fx)[:-1]
-                self.size = int(np.prod(self.shape, dtype=np.int64))
-                self.eval = _FromBatch(fcn, True, xsample)
         else:
-            if x0.shape is None:
-                x0 = gv.BufferDict(x0, lbatch_buf=x0.buf.reshape((1,) + x0.buf.shape))
-                if uses_jac:
-                    jac0 = gv.BufferDict(jac0, lbatch_buf=jac0.buf.reshape((1,) + jac0.buf.shape))
-            else:
-                x0 = x0.reshape((1,) + x0.shape)
-                if uses_jac:
-                    jac0 = jac0.reshape((1,) + jac0.shape)
-            fx = fcn(x0) if jac0 is None else fcn(x0, jac=jac0)
+            fx = fcn(present(x1), jac=present(np.ones_like(x1))) if uses_jac else fcn(present(x1))
             if hasattr(fx, 'keys'):
-                fxs = gv.BufferDict()
+                self.bdict = gv.BufferDict()
                 for k in fx:
-                    fxs[k] = np.asarray(fx[k])[0]
-                self.shape, self.bdict, self.size = None, fxs, fxs.size
-                self.eval = _FromBatchDict(fcn, self.bdict, False, xsample)
+                    self.bdict[k] = _strip_batch(fx[k], kind)
+                self.shape, self.size = None, self.bdict.size
             else:
-                fx = np.asarray(fx)
-                self.shape = fx.shape[1:]
+                self.shape = tuple(np.shape(fx)[:-1] if kind == 'rbatch' else np.shape(fx)[1:])
                 self.size = int(np.prod(self.shape, dtype=np.int64))
-                self.eval = _FromBatch(fcn, False, xsample)
+        self.eval = _HostEval(fcn, xsample, kind, self.shape, self.size, self.bdict)
 
     def __call__(self, x, jac=None):
         r""" Non-batch version of fcn """
-        if hasattr(x, 'keys'):
-            x = gv.asbufferdict(x).buf.reshape(1, -1)
-        else:
-            x = np.asarray(x).reshape(1, -1)
-        return self.format_result(np.asarray(self.eval(x, jac=jac)))
+        row = gv.asbufferdict(x).buf if hasattr(x, 'keys') else np.asarray(x)
+        return self.format_result(np.asarray(self.eval(row.reshape(1, -1), jac=jac)))
+
+    def _structured(self, flat):
+        """a flat vector of ``size`` entries in the integrand's own structure"""
+        if self.shape is None:
+            return gv.BufferDict(self.bdict, buf=flat.reshape(-1))
+        return flat.reshape(self.shape)
 
     def format_result(self, mean, var=None):
-        r""" Reformat output from integrator to correspond to original output format """
+        r""" Reformat output from integrator to correspond to original output format: ``mean`` alone, or GVars
+        from ``mean`` and ``var`` (a vector of variances or a covariance matrix). """
         if var is None:
-            if self.shape is None:
-                return gv.BufferDict(self.bdict, buf=mean.reshape(-1))
-            if self.shape == ():
-                return mean.flat[0]
-            return mean.reshape(self.shape)
+            return mean.flat[0] if self.shape == () else self._structured(mean)
         if var.shape == mean.shape:
-            var = np.asarray(var) ** 0.5
-        if self.shape is None:
-            return gv.BufferDict(self.bdict, buf=gv.gvar(mean, var).reshape(-1))
-        if self.shape == ():
-            return gv.gvar(mean[0], var[0, 0] ** 0.5 if var.shape != mean.shape else var[0])
-        return gv.gvar(mean, var).reshape(self.shape)
+            spread = np.asarray(var) ** 0.5
+            if self.shape == ():
+                return gv.gvar(mean[0], spread[0])
+        else:
+            spread = var
+            if self.shape == ():
+                return gv.gvar(mean[0], var[0, 0] ** 0.5)
+        return self._structured(gv.gvar(mean, spread))
 
     def format_evalx(self, evalx):
         r""" Reformat output ``evalx[i, c]`` of ``eval(x)`` into the integrand's own structure. """
@@ -412,6 +311,4 @@ class VegasIntegrand(object):
     def training(self, x, jac):
         r""" Calculate first element of integrand at point ``x``. """
         fx = self.eval(x, jac=jac)
-        if fx.ndim == 1:
-            return fx
-        return fx.reshape((x.shape[0], -1))[:, 0]
+        return fx if fx.ndim == 1 else fx.reshape((x.shape[0], -1))[:, 0]
