@@ -663,3 +663,13 @@ def test_integrand_adapters_every_argument_and_value_form():
             assert ex.shape == (n,) + std.shape
         one = std(x[0], jac=None if jac is None else jac[:1])
         np.testing.assert_allclose(one.buf if out == 'dictionary' else np.reshape(one, -1), got[0], rtol=1e-15)
+    # a standard-form integrand pickles whenever the user function does (PDFIntegrator pickles its pdf; saveall)
+    std = VegasIntegrand(vegas.lbatchintegrand(_picklable_lbatch), None, False, xsamples['dict'], False)
+    again = pickle.loads(pickle.dumps(std))
+    x = rng.uniform(size=(n, D))
+    np.testing.assert_array_equal(again.eval(x), std.eval(x))
+    assert again.shape == std.shape == (2,) and again.size == 2
+
+
+def _picklable_lbatch(p):
+    return np.stack([p['a'] * p['b'][:, 0], p['c'][:, 0, 1]], axis=1)

@@ -128,25 +128,36 @@ class DeviceIntegrand(object):
 # --------------------------------------------------------------------------- standard form
 # Every host integrand becomes  eval(x[n, D], jac[n, D] | None) -> f[n, size]  by composing two pieces, both
 # chosen once from the probe call (the reference has one class per combination, _vegas.pyx:3175-3383):
-#   presenter  rows -> the argument the user function takes: flat rows, an index array of xsample's shape, or a
+#   presenter  (_Presenter) rows -> the argument the user function takes: flat rows, an index array of xsample's shape, or a
 #              dictionary; one point at a time, or a batch with its index on the left / on the right.  jac is
 #              presented exactly like x.
 #   packer     the user function's value (number, array or dictionary; per point or per batch) -> rows of `size`.
-def _presenter(xsample, kind):
-    if xsample.shape is None:
-        if kind == 'rbatch':
-            return lambda a: gv.BufferDict(xsample, rbatch_buf=a.T)
-        if kind == 'lbatch':
-            return lambda a: gv.BufferDict(xsample, lbatch_buf=a)
-        return lambda row: gv.BufferDict(xsample, buf=row)
-    shape = tuple(xsample.shape)
-    if len(shape) == 1:
-        return (lambda a: a.T) if kind == 'rbatch' else (lambda a: a)
-    if kind == 'rbatch':
-        return lambda a: a.T.reshape(shape + (-1,))
-    if kind == 'lbatch':
-        return lambda a: a.reshape((-1,) + shape)
-    return lambda row: row.reshape(shape)
+class _Presenter(object):
+    """rows ``a[n, D]`` (``a[D]`` for one point) -> the argument form of the user function"""
+
+    def __init__(self, xsample, kind):
+        self.xsample, self.kind = xsample, kind
+        self.shape = None if xsample.shape is None else tuple(xsample.shape)
+        if self.shape is None:
+            self.how = 'dict'
+        elif len(self.shape) == 1:
+            self.how = 'flat'
+        else:
+            self.how = 'index'
+
+    def __call__(self, a):
+        right = self.kind == 'rbatch'
+        if self.how == 'flat':
+            return a.T if right else a
+        if self.how == 'dict':
+            if right:
+                return gv.BufferDict(self.xsample, rbatch_buf=a.T)
+            if self.kind == 'lbatch':
+                return gv.BufferDict(self.xsample, lbatch_buf=a)
+            return gv.BufferDict(self.xsample, buf=a)
+        if right:
+            return a.T.reshape(self.shape + (-1,))
+        return a.reshape(((-1,) if self.kind == 'lbatch' else ()) + self.shape)
 
 
 def _dict_layout(bdict):
@@ -160,7 +171,7 @@ class _HostEval(object):
 
     def __init__(self, fcn, xsample, kind, shape, size, bdict):
         self.fcn, self.kind, self.shape, self.size = fcn, kind, shape, int(size)
-        self.present = _presenter(xsample, kind)
+        self.present = _Presenter(xsample, kind)
         self.layout = None if bdict is None else _dict_layout(bdict)
         # how jac reaches a one-point function (pyx:3200-3213): by keyword for flat x, positionally for a
         # dictionary, not at all for an index array
@@ -254,7 +265,7 @@ class VegasIntegrand(object):
             self.eval = _DeviceEval(fcn)
             return
         kind = self.fcntype if self.fcntype in ('scalar', 'rbatch') else 'lbatch'
-        present = _presenter(xsample, kind)
+        present = _Presenter(xsample, kind)
         if kind == 'scalar':
             # (the probe always passes jac by keyword, as pyx:3013 does; eval follows pyx:3200-3213)
             fx = fcn(present(x1[0]), jac=present(np.ones_like(x1[0]))) if uses_jac else fcn(present(x1[0]))
