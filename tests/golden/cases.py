@@ -65,3 +65,27 @@ def pdf_f(p):
     """dictionary-valued lbatch function of the parameters p[i, d]"""
     import numpy as np
     return dict(a=p[:, 0] + p[:, 1], b=np.stack([p[:, 1] * p[:, 2], p[:, 0] ** 2], axis=1))
+
+
+# ----------------------------------------------------------------------------- Integrator.settings() strings
+# (limits are given as a recipe so that the same file describes them to the reference and to vegas_b200)
+SETTINGS = {
+    'flat2': dict(limits=('list', [[0., 1.], [-1., 1.]]), kw=dict(neval=254, nitn=123, neval_frac=0.75)),
+    'flat1_grid': dict(limits=('list', [[0., 2.]]), kw=dict(neval=1000), ngrid=4),
+    'flat25_two_columns': dict(limits=('list', [[-0.5 * d, 1. + d] for d in range(25)]), kw=dict(neval=4e4, nitn=7)),
+    'flat21_odd_split': dict(limits=('list', [[0., 1. + d] for d in range(21)]), kw=dict(neval=1e5, rtol=1e-3, atol=1e-9)),
+    'dict_mixed': dict(limits=('dict', [('x', [[0., 1.]]), ('y', [-1., 1.]), ('zz', [[[0., 3.], [1., 2.]]])]),
+                       kw=dict(neval=2000, alpha=0.2, beta=0.5)),
+    'index_array': dict(limits=('list', [[[0., 1.]], [[-1., 1.]]]), kw=dict(neval=500)),
+    'no_adapt': dict(limits=('list', [[0., 1.], [0., 1.], [0., 1.]]), kw=dict(neval=1e4, adapt=False, max_neval_hcube=1e4)),
+    'adapt_to_errors': dict(limits=('list', [[0., 1.], [0., 1.]]), kw=dict(neval=1e3, adapt_to_errors=True), ngrid=2),
+    'beta0': dict(limits=('list', [[0., 1.], [0., 1.]]), kw=dict(neval=1e3, beta=0., min_neval_batch=2000)),
+    'nstrat': dict(limits=('list', [[0., 1.], [0., 1.], [0., 1.]]), kw=dict(nstrat=[6, 2, 1], neval_frac=0.5)),
+    'tiny_numbers': dict(limits=('list', [[1.23456789e-7, 9.87654321e5], [-3.3333333, 7.7777777]]), kw=dict(neval=1e6)),
+}
+
+
+def settings_limits(recipe):
+    import collections
+    kind, val = recipe
+    return val if kind == 'list' else collections.OrderedDict(val)

@@ -673,3 +673,17 @@ def test_integrand_adapters_every_argument_and_value_form():
 
 def _picklable_lbatch(p):
     return np.stack([p['a'] * p['b'][:, 0], p['c'][:, 0, 1]], axis=1)
+
+
+def test_settings_strings_match_the_reference_fixture():
+    """Integrator.settings() / AdaptiveMap.settings() against the strings recorded from the unmodified reference
+    (tests/golden/ref_settings.json, made by make_golden_settings.py): one and two column tables (more than 20
+    axes; an odd split), dictionary and index-array xsample, no adaptation, adapt_to_errors, beta=0, explicit
+    nstrat, limits that need exponents, grid nodes"""
+    import json
+    from tests.golden.cases import SETTINGS, settings_limits
+    ref = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'ref_settings.json')))
+    assert sorted(ref) == sorted(SETTINGS)
+    for name, spec in SETTINGS.items():
+        integ = vegas.Integrator(settings_limits(spec['limits']), **spec['kw'])
+        assert integ.settings(ngrid=spec.get('ngrid', 0)) == ref[name], name

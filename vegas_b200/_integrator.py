@@ -384,103 +384,69 @@ class Integrator(object):
             raise MemoryError('work arrays larger than max_mem; reduce min_neval_batch or max_neval_hcube (or increase max_mem)')
         return old_val
 
-    # ------------------------------------------------------------------ settings (pyx:1448-1590)
+    # ------------------------------------------------------------------ settings (the text of pyx:1448-1590)
+    def _axis_labels(self):
+        """key/index label of every axis in xsample's order (None for a plain list of limits): ``key`` for a
+        number, ``key i,j`` -- the key on the first element only -- for an array, ``i,j`` for an index array"""
+        def index_text(idx):
+            return ','.join(str(i) for i in idx)
+        xs = self.xsample
+        if xs.shape is None:
+            labels = []
+            for k in xs:
+                shape = np.shape(xs[k])
+                if shape == ():
+                    labels.append(str(k))
+                else:
+                    labels.extend(('%s %s' % (k, index_text(idx))) if n == 0 else index_text(idx)
+                                  for n, idx in enumerate(np.ndindex(shape)))
+            return labels
+        if len(xs.shape) > 1:
+            return [index_text(idx) for idx in np.ndindex(xs.shape)]
+        return None
+
     def settings(self, ngrid=0):
         r""" Assemble summary of integrator settings into string. """
+        vegas_plus = self.beta > 0 and not self.adapt_to_errors
         nhcube = np.prod(self.nstrat)
-        neval = nhcube * self.min_neval_hcube if self.beta <= 0 else self.neval
-        ans = "Integrator Settings:\n"
-        if self.beta > 0 and not self.adapt_to_errors:
-            ans += "    %.6g (approx) integrand evaluations in each of %d iterations\n" % (self.neval, self.nitn)
-        else:
-            ans += "    %.6g integrand evaluations in each of %d iterations\n" % (neval, self.nitn)
-        ans += "    number of: strata/axis = %s\n" % np.array2string(
-            np.asarray(self.nstrat), max_line_width=80, prefix=29 * ' ')
-        ans += "               increments/axis = %s\n" % np.array2string(
-            np.asarray(self.map.ninc), max_line_width=80, prefix=33 * ' ')
-        ans += "               h-cubes = %.6g  processors = %d\n" % (nhcube, self.nproc)
-        max_neval_hcube = max(self.max_neval_hcube, self.min_neval_hcube)
-        ans += "               evaluations/batch >= %.2g\n" % (float(self.min_neval_batch),)
-        ans += "               %d <= evaluations/h-cube <= %.2g\n" % (int(self.min_neval_hcube), float(max_neval_hcube))
-        ans += "    minimize_mem = %s  adapt_to_errors = %s  adapt = %s\n" % (
-            str(self.minimize_mem), str(self.adapt_to_errors), str(self.adapt))
-        ans += "    accuracy: relative = %g  absolute = %g\n" % (self.rtol, self.atol)
-        if not self.adapt:
-            ans += "    damping: alpha = %g  beta= %g\n\n" % (0., 0.)
-        elif self.adapt_to_errors:
-            ans += "    damping: alpha = %g  beta= %g\n\n" % (self.alpha, 0.)
-        else:
-            ans += "    damping: alpha = %g  beta= %g\n\n" % (self.alpha, self.beta)
+        per_iteration = self.neval if self.beta > 0 else nhcube * self.min_neval_hcube
+        alpha, beta = (0., 0.) if not self.adapt else (self.alpha, 0. if self.adapt_to_errors else self.beta)
 
-        # integration limits
-        offset = 4 * ' '
-        entries = []
-        axis = 0
-        limits = list(self.map.region())
-        for i in range(len(limits)):
-            limits[i] = '({:.5}, {:.5})'.format(*[float(v) for v in limits[i]])
-        if self.xsample.shape is None:
-            for k in self.xsample:
-                if np.shape(self.xsample[k]) == ():
-                    entries.append((str(k), str(axis), str(limits[axis])))
-                    axis += 1
-                else:
-                    prefix = str(k) + ' '
-                    for idx in np.ndindex(np.shape(self.xsample[k])):
-                        str_idx = ''.join(str(idx)[1:-1].split(' '))
-                        if str_idx[-1] == ',':
-                            str_idx = str_idx[:-1]
-                        entries.append((prefix + str_idx, str(axis), str(limits[axis])))
-                        if prefix != '':
-                            prefix = ''
-                        axis += 1
-            linefmt = '{e0:>{w0}}    {e1:>{w1}}    {e2:>{w2}}'
-            headers = ('key/index', 'axis', 'integration limits')
-            w0 = max(len(ei[0]) for ei in entries)
-        elif len(self.xsample.shape) > 1:
-            for idx in np.ndindex(self.xsample.shape):
-                str_idx = ''.join(str(idx)[1:-1].split(' '))
-                if str_idx[-1] == ',':
-                    str_idx = str_idx[:-1]
-                entries.append((str_idx, str(axis), str(limits[axis])))
-                axis += 1
-            linefmt = '{e0:>{w0}}    {e1:>{w1}}    {e2:>{w2}}'
-            headers = ('key/index', 'axis', 'integration limits')
-            w0 = max(len(ei[0]) for ei in entries)
-        else:
-            for axis, limits_axis in enumerate(limits):
-                entries.append((None, str(axis), str(limits_axis)))
-            linefmt = '{e1:>{w1}}    {e2:>{w2}}'
-            headers = (None, 'axis', 'integration limits')
-            w0 = None
-        w1 = max(len(ei[1]) for ei in entries)
-        w2 = max(len(ei[2]) for ei in entries)
-        ncol = 1 if self.map.dim <= 20 else 2
-        table = ncol * [[]]
-        nl = len(entries) // ncol
-        if nl * ncol < len(entries):
-            nl += 1
-        ns = len(entries) - (ncol - 1) * nl
-        ne = (ncol - 1) * [nl] + [ns]
-        iter_entries = iter(entries)
-        for col in range(ncol):
-            e0, e1, e2 = headers
-            w0 = None if e0 is None else max(len(e0), w0)
-            w1 = max(len(e1), w1)
-            w2 = max(len(e2), w2)
-            table[col] = [linefmt.format(e0=e0, w0=w0, e1=e1, w1=w1, e2=e2, w2=w2)]
-            table[col].append(len(table[col][0]) * '-')
-            for ii in range(ne[col]):
-                e0, e1, e2 = next(iter_entries)
-                table[col].append(linefmt.format(e0=e0, w0=w0, e1=e1, w1=w1, e2=e2, w2=w2))
-        mtable = []
-        ns += 2
-        nl += 2
-        for i in range(ns):
-            mtable.append('  '.join([tabcol[i] for tabcol in table]))
-        for i in range(ns, nl):
-            mtable.append('  '.join([tabcol[i] for tabcol in table[:-1]]))
-        ans += offset + ('\n' + offset).join(mtable) + '\n'
+        def ints(a, label):         # (continuation lines of a long array line up behind the label)
+            return np.array2string(np.asarray(a), max_line_width=80, prefix=len(label) * ' ')
+        strata, incs = '    number of: strata/axis = ', '               increments/axis = '
+        lines = [
+            'Integrator Settings:',
+            '    %.6g%s integrand evaluations in each of %d iterations' % (per_iteration, ' (approx)' if vegas_plus else '', self.nitn),
+            strata + ints(self.nstrat, strata),
+            incs + ints(self.map.ninc, incs),
+            '               h-cubes = %.6g  processors = %d' % (nhcube, self.nproc),
+            '               evaluations/batch >= %.2g' % float(self.min_neval_batch),
+            '               %d <= evaluations/h-cube <= %.2g' % (self.min_neval_hcube, float(max(self.max_neval_hcube, self.min_neval_hcube))),
+            '    minimize_mem = %s  adapt_to_errors = %s  adapt = %s' % (self.minimize_mem, self.adapt_to_errors, self.adapt),
+            '    accuracy: relative = %g  absolute = %g' % (self.rtol, self.atol),
+            '    damping: alpha = %g  beta= %g' % (alpha, beta),
+            '']
+        # the table of integration limits: right-aligned columns [key/index,] axis, limits under a ruled header;
+        # beyond 20 axes two such blocks side by side, the first one taking the extra row of an odd count
+        labels = self._axis_labels()
+        rows = [(str(d), '({:.5}, {:.5})'.format(float(lo), float(hi))) for d, (lo, hi) in enumerate(self.map.region())]
+        header = ('axis', 'integration limits')
+        if labels is not None:
+            rows, header = [(lab,) + r for lab, r in zip(labels, rows)], ('key/index',) + header
+        widths = [max(len(r[c]) for r in rows + [header]) for c in range(len(header))]
+
+        def text(row):
+            return '    '.join(cell.rjust(w) for cell, w in zip(row, widths))
+        nblock = 1 if self.map.dim <= 20 else 2
+        per_block = -(-len(rows) // nblock)
+        blocks = []
+        for b in range(nblock):
+            body = [text(r) for r in rows[b * per_block:(b + 1) * per_block]]
+            blocks.append([text(header), len(text(header)) * '-'] + body)
+        for i in range(per_block + 2):
+            lines.append('    ' + '  '.join(blk[i] for blk in blocks if i < len(blk)))
+        ans = '\n'.join(lines) + '\n'
         if ngrid > 0:
             ans += '\n' + self.map.settings(ngrid=ngrid)
         return ans
