@@ -687,3 +687,109 @@ def test_settings_strings_match_the_reference_fixture():
     for name, spec in SETTINGS.items():
         integ = vegas.Integrator(settings_limits(spec['limits']), **spec['kw'])
         assert integ.settings(ngrid=spec.get('ngrid', 0)) == ref[name], name
+
+
+class _ScriptedContext(object):
+    """stands in for _lib.Context in the host loop of Integrator.__call__: records the calls and delivers scripted
+    iteration heads ([mean, var, sum_sigf | NaN flag, 6 pre-pass words]); no device, no library"""
+    device = 'cpu'
+
+    def __init__(self, heads):
+        self.heads, self.log, self.integrand_serial, self.in_flight = list(heads), [], 0, None
+
+    def set_seed(self, seed):
+        pass
+
+    def set_map(self, grid, ninc):
+        self.log.append('set_map')
+
+    def set_strata(self, nstrat, slab, rank=0, world=1):
+        self.log.append('set_strata')
+        return int(np.prod(nstrat))
+
+    def set_integrand(self, fid, params, keep=None):
+        _lib.note_integrand(self, fid, params)
+        return 1
+
+    def plan(self, sigf, neval_sigf, min_nh, max_nh, uniform, neval_hcube=None):
+        self.log.append('plan')
+        return 1000, 2, 9, 1
+
+    def plan_commit(self, neval_sigf, stats6):
+        self.log.append(('plan_commit', [int(v) for v in stats6]))
+        return 1000, 2, 9, 1
+
+    def iteration_begin(self, itn, beta, flags, sigf, buf, nacc, nh, hstride, nf64, nwords, alpha_adapt, plan):
+        assert self.in_flight is None
+        self.in_flight = self.heads.pop(0)
+        self.log.append(('begin', alpha_adapt > 0, plan is not None))
+
+    def iteration_end(self, head):
+        mean, var, sum_sigf, nan = self.in_flight
+        self.in_flight = None
+        head[:3] = mean, var, sum_sigf
+        head[3:].view(np.int64)[:] = [nan, 11, 12, 13, 14, 15, 16]
+        self.log.append('end')
+
+    def get_map(self, shape):
+        return np.tile(np.linspace(0., 1., shape[1]), (shape[0], 1))
+
+    def launch_count(self):
+        return 0
+
+
+def _scripted_integrator(heads, **kw):
+    integ = vegas.Integrator(2 * [[0., 1.]], neval=1000, seed=1, **kw)
+    integ._ctx, integ._ctx_map_version, integ._ctx_strata = _ScriptedContext(heads), None, None
+    return integ, integ._ctx
+
+
+def test_host_loop_books_iteration_i_behind_the_launch_of_i_plus_1(monkeypatch):
+    """the host side of the one-call iteration path (no GPU: a scripted context): results are booked in order, each
+    behind the next launch, the last one after the loop; the pre-pass words of iteration i are committed before
+    launch i + 1 and -- left by a call's last iteration -- at the start of the next call; with a tolerance every
+    iteration is booked at once and the loop stops where the running average meets it; a NaN raises before anything
+    of that iteration is booked and resets sigf; the context is brought up to date only once per call"""
+    for k in ('VB200_NO_DEFER', 'VB200_NO_FAST_ITERATION', 'VB200_HOST_ADAPT', 'VB200_NO_PLAN_AHEAD'):
+        monkeypatch.delenv(k, raising=False)
+    f = vegas.integrands.Poly(1., [1.], [1])
+    heads = [(1.5 + 0.01 * i, 1e-4, 400., 0) for i in range(4)]
+    integ, ctx = _scripted_integrator(heads)
+    order = []
+    real_update = vegas._results.VegasResult.update
+    monkeypatch.setattr(vegas._results.VegasResult, 'update',
+                        lambda self, mean, var, neval: (order.append((float(mean[0]), len(ctx.log))), real_update(self, mean, var, neval))[1])
+    r = integ(f, nitn=4)
+    assert [x.mean for x in r.itn_results] == [1.5, 1.51, 1.52, 1.53] and r.sum_neval == 4000
+    ends = [i for i, e in enumerate(ctx.log) if e == 'end']
+    begins = [i for i, e in enumerate(ctx.log) if isinstance(e, tuple) and e[0] == 'begin']
+    # iteration i is booked after launch i + 1 went out and before its wait returned; the last one after the loop
+    assert [n for _, n in order] == [begins[1] + 1, begins[2] + 1, begins[3] + 1, ends[3] + 1]
+    assert ctx.log.count('set_map') == 1 and ctx.log.count('set_strata') == 1 and ctx.log.count('plan') == 1
+    assert [e for e in ctx.log if isinstance(e, tuple) and e[0] == 'plan_commit'] == 3 * [('plan_commit', [11, 12, 13, 14, 15, 16])]
+    assert all(e == ('begin', True, True) for e in ctx.log if isinstance(e, tuple) and e[0] == 'begin')
+    assert integ.sum_sigf == 400. and integ.map._device_owner is ctx
+    # the next call starts from the pre-pass its predecessor left behind: no synchronous plan
+    ctx.heads, ctx.log[:] = [(1.5, 1e-4, 400., 0)], []
+    integ(f, nitn=1)
+    assert 'plan' not in ctx.log and ctx.log[0] == ('plan_commit', [11, 12, 13, 14, 15, 16])
+    # ... unless sigf was replaced in between
+    ctx.heads, ctx.log[:] = [(1.5, 1e-4, 400., 0)], []
+    integ.set(sigf=np.ones(integ.nhcube))
+    integ(f, nitn=1)
+    assert 'plan' in ctx.log and not any(isinstance(e, tuple) and e[0] == 'plan_commit' for e in ctx.log)
+
+    # tolerances: booked at once, stops when met (sdev of the weighted average after k iterations: 1e-2 / sqrt(k))
+    del order[:]
+    integ, ctx = _scripted_integrator([(1.5, 1e-4, 400., 0) for _ in range(8)])
+    r = integ(f, nitn=8, rtol=0.0045)
+    assert len(r.itn_results) == 3 and len(ctx.heads) == 5
+    assert [n for _, n in order] == [i + 1 for i, e in enumerate(ctx.log) if e == 'end']
+
+    # NaN in the third iteration: two results booked, ValueError, sigf back to ones
+    integ, ctx = _scripted_integrator([(1.5, 1e-4, 400., 0), (1.5, 1e-4, 400., 0), (float('nan'), 1e-4, 400., 1), (1.5, 1e-4, 400., 0)])
+    del order[:]
+    with pytest.raises(ValueError, match='nan'):
+        integ(f, nitn=4)
+    assert len(order) == 2 and len(ctx.heads) == 1
+    assert integ.sum_sigf == integ.nhcube and float(integ._sigf_dev.min()) == float(integ._sigf_dev.max()) == 1.

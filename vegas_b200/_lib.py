@@ -142,6 +142,16 @@ def _stream():
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def note_integrand(ctx, fid, params):
+    """``ctx.integrand_serial`` counts the integrands a context has seen -- an allocation pre-pass launched ahead of
+    time plans the light geometry's chunks for the integrand of its day (``Integrator._plan_key``).  Setting the
+    same functor again (same id, same parameter bytes: every ``Integrator.__call__`` does) is not a new integrand."""
+    sig = (int(fid), bytes(params))
+    if sig != getattr(ctx, '_integrand_sig', None):
+        ctx._integrand_sig = sig
+        ctx.integrand_serial = getattr(ctx, 'integrand_serial', 0) + 1
+
+
 class Context(object):
     """Owns one ``vb200_ctx`` on one GPU."""
 
@@ -200,7 +210,7 @@ class Context(object):
     def set_integrand(self, fid, params, keep=None):
         nf = ctypes.c_int()
         self._keep = keep
-        self.integrand_serial = getattr(self, 'integrand_serial', 0) + 1
+        note_integrand(self, fid, params)
         check(self.L.vb200_set_integrand(self.h, fid, ctypes.byref(params), ctypes.sizeof(params),
                                          ctypes.byref(nf)))
         return nf.value
